@@ -1,0 +1,159 @@
+/*
+ * seriation_b200.h -- C ABI of the B200-native seriation MCMC sweep.
+ *
+ * This is the drop-in boundary for ONE path of the reference
+ * (PrayagS/Seriation-in-Paleontological-Data-using-MCMC): the per-chain sweep of
+ * C_Implementation/mcmc.c and the cross-chain selection / pair-order steps of
+ * script.py.  Plain C types only; every entry point returns 0 on success or a
+ * negative SER_E_* code, and ser_last_error() describes the failure.  The
+ * library is CUDA-only: without a usable device every compute entry point fails
+ * with SER_E_CUDA -- there is no CPU fallback.
+ *
+ * Reference interfaces replaced (file:line under /root/reference):
+ *   ser_dataset_read_txt      mcmc_readmodel            C_Implementation/mcmc.c:339-401
+ *   ser_dataset_read_names    (.genus/.sites files)     Dataset/g*.genus, Dataset/g*.sites
+ *   ser_run_create/_init      mcmc_init+mcmc_randomize  mcmc.c:581-593, :477-578, :440-474
+ *   ser_run_advance           mcmc_sample loop          mcmc.c:214-258 (main: :140-143, :180-185)
+ *   ser_run_get_state         mcmc_model fields         mcmc.h:32-45
+ *   ser_run_fetch_samples     mcmc_save_chain rows      mcmc.c:69-92
+ *   ser_run_chain_stats       compute/print_exp_data    mcmc.c:53-67
+ *   ser_run_check             mcmc_consistent           mcmc.c:999-1094
+ *   ser_write_chain_files     main's five fopen()s      mcmc.c:148-197, :261-294
+ *   ser_select_chains*        choose_chains             script.py:70-99
+ *   ser_run_po_counts*        compute_pair_order_matrix script.py:155-189
+ *   run_all_chains' Pool(8) over 100 processes (script.py:48-67) is replaced by
+ *   n_chains in ser_run_config: one CTA per chain in one launch.
+ */
+#ifndef SERIATION_B200_H
+#define SERIATION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SER_OK 0
+#define SER_E_ARG (-1)    /* bad argument / unsupported shape */
+#define SER_E_PARSE (-2)  /* dataset parse error (mcmc_readmodel's exit(1) cases) */
+#define SER_E_CUDA (-3)   /* CUDA runtime error or no device */
+#define SER_E_STATE (-4)  /* call order (e.g. advance before init) */
+#define SER_E_IO (-5)     /* file I/O */
+#define SER_E_TAPE (-6)   /* replay tape missing / exhausted */
+#define SER_E_CHECK (-7)  /* consistency check failed */
+
+#define SER_MODE_FREE 0   /* counter-based Philox stream keyed by (seed, global chain id) */
+#define SER_MODE_REPLAY 1 /* consume recorded draw tapes (grammar: DESIGN.md / oracle/draw_source.h) */
+
+#define SER_STORE_NONE 0  /* per-chain running sums only */
+#define SER_STORE_PI 1    /* + pi of every thinned sample (enough for the pair-order matrix) */
+#define SER_STORE_FULL 2  /* + a, b, c, d, loglik of every thinned sample (chain_data.csv) */
+
+/* limits of this build (DESIGN.md "shapes") */
+#define SER_MAX_SITES 1024
+#define SER_MAX_TAXA 4096
+
+typedef struct ser_dataset ser_dataset;
+typedef struct ser_run ser_run;
+
+typedef struct ser_run_config {
+  int32_t n_chains;        /* chains simulated by THIS process / device                        */
+  int32_t chain_offset;    /* global id of local chain 0 (sharding across ranks)              */
+  int32_t sweeps_per_call; /* sweeps per thinned sample; the reference hard-codes 10           */
+  int32_t mode;            /* SER_MODE_*                                                       */
+  uint32_t seed;           /* free-running stream seed (GSL_RNG_SEED's role)                   */
+  int32_t store;           /* SER_STORE_*                                                      */
+  int32_t max_samples;     /* capacity of the thinned-sample store per chain                   */
+  int32_t device;          /* CUDA device ordinal                                              */
+} ser_run_config;
+
+const char *ser_last_error(void);
+const char *ser_version(void);
+
+/* ---------------------------------------------------------------- datasets (host only) */
+/* X: N*M row-major bytes (row = site, column = taxon, non-zero = present); hard: N flags or NULL */
+int ser_dataset_from_bits(int32_t N, int32_t M, const uint8_t *X, const uint8_t *hard, ser_dataset **out);
+/* the reference's .txt format; path == NULL reads stdin */
+int ser_dataset_read_txt(const char *path, ser_dataset **out);
+int ser_dataset_read_stream(FILE *f, ser_dataset **out);
+int ser_dataset_dims(const ser_dataset *ds, int32_t *N, int32_t *M, int32_t *nh);
+int ser_dataset_get(const ser_dataset *ds, uint8_t *X, uint8_t *hard);
+void ser_dataset_free(ser_dataset *ds);
+/* .genus (one taxon name per line) / .sites ("Name [MN,age]" + optional " *") readers.
+ * Attaches labels to the dataset; counts must match M / N. */
+int ser_dataset_read_names(ser_dataset *ds, const char *genus_path, const char *sites_path);
+const char *ser_dataset_taxon_name(const ser_dataset *ds, int32_t m);
+const char *ser_dataset_site_name(const ser_dataset *ds, int32_t n);
+int ser_dataset_site_age(const ser_dataset *ds, int32_t n, int32_t *mn_unit, double *age_ma, int32_t *hard);
+/* deterministic synthetic occurrence matrix (BASELINE.json config 5; generator in DESIGN.md) */
+int ser_dataset_synthetic(int32_t N, int32_t M, int32_t n_hard, uint64_t seed, ser_dataset **out);
+
+/* ---------------------------------------------------------------- runs (device) */
+int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, ser_run **out);
+void ser_run_destroy(ser_run *run);
+/* replay mode: all chains' tapes concatenated; offsets has n_chains+1 entries (in doubles) */
+int ser_run_set_tapes(ser_run *run, const double *flat, const uint64_t *offsets);
+/* randomised start (mcmc_randomize) + a/b from the data + counts + log-likelihood */
+int ser_run_init(ser_run *run);
+/* n_calls x sweeps_per_call sweeps on every chain; if `sampling` a thinned sample is emitted
+ * (and the exp_data sums advanced) after every call.  Asynchronous on the run's stream. */
+int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling);
+int ser_run_sync(ser_run *run);
+/* CUDA-event time of all kernels launched by this run since creation / last reset, in ms */
+int ser_run_elapsed_ms(ser_run *run, double *ms, int32_t reset);
+int ser_run_kernel_launches(const ser_run *run, int64_t *n);
+
+/* full model state of one local chain (any pointer may be NULL) */
+int ser_run_get_state(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32_t *pi, int32_t *rpi,
+                      int32_t *t0, int32_t *f0, int32_t *t1, int32_t *f1, int32_t tot[4],
+                      double cdl[3], int64_t *tape_slots);
+/* acceptance counters of one chain: c, d, ab(changed), pi1, pi2(0), pi2(swap), pi3, sweeps */
+int ser_run_get_counters(ser_run *run, int32_t chain, int64_t out[8]);
+/* mcmc_consistent on every local chain, on device; *n_bad = number of inconsistent chains */
+int ser_run_check(ser_run *run, int32_t *n_bad);
+
+/* per local chain: mean(-loglik), mean(exp c), mean(exp d) over the samples emitted so far;
+ * host arrays of n_chains doubles (any may be NULL).  n_samples receives the divisor. */
+int ser_run_chain_stats(ser_run *run, double *e_negloglik, double *e_c, double *e_d, int32_t *n_samples);
+/* same E[-logL], written on the run's stream into DEVICE memory (e.g. an NCCL send buffer) */
+int ser_run_chain_stats_device(ser_run *run, double *d_e_negloglik);
+/* thinned samples of one local chain (needs SER_STORE_FULL; pi alone needs SER_STORE_PI).
+ * a,b: [n][M]; pi: [n][N]; c,d,loglik: [n].  Returns the number of samples in *n. */
+int ser_run_fetch_samples(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32_t *pi, double *c,
+                          double *d, double *loglik, int32_t *n);
+
+/* ---------------------------------------------------------------- cross-chain steps */
+/* choose_chains: population sigma over all n values, keep min-sigma < x < min+sigma, the k
+ * smallest, ids ascending.  Host arrays. */
+int ser_select_chains(const double *e_negloglik, int32_t n, int32_t k, int32_t *chosen, int32_t *n_chosen,
+                      double *min_out, double *sigma_out);
+/* same on the device (d_e: n doubles in device memory; d_chosen: k ints, -1 padded; d_info:
+ * 3 doubles = n_chosen, min, sigma).  `stream` is a cudaStream_t or NULL. */
+int ser_select_chains_device(const double *d_e, int32_t n, int32_t k, int32_t *d_chosen, double *d_info,
+                             int32_t device, void *stream);
+/* pair-order counts over the stored samples of the chosen chains that live on this run:
+ * cnt[c][i][j] = #{samples t : pi_t(i) < pi_t(j)}, diagonal = -T; chosen holds GLOBAL chain ids,
+ * entries owned by other ranks (or -1) leave their slab untouched.  d_counts: [k][N][N] int32
+ * in DEVICE memory (zero it first; all-reduce it across ranks afterwards). */
+int ser_run_po_counts_device(ser_run *run, const int32_t *d_chosen, int32_t k, int32_t *d_counts);
+/* host convenience wrapper: chosen / counts in host memory */
+int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *counts);
+/* script.py:155-175 finalisation incl. the reference's carry-over between chains when faithful != 0 */
+int ser_po_finalize(const int32_t *counts, int32_t k, int32_t N, int32_t chains_selected, int32_t faithful,
+                    double *po);
+
+/* ---------------------------------------------------------------- reference-compatible files */
+/* Writes Chains-style files for one local chain into `dir` (which must exist, like the
+ * reference): chain_data.csv, exp_data.csv, taxa.csv, sites.csv, hard_sites.csv. */
+int ser_write_chain_files(ser_run *run, int32_t chain, const char *dir);
+
+/* micro-benchmarks of the SM-local ceilings the sweep is bound by (DESIGN.md "roofline"):
+ * out[0] = fp64 FMA TFLOP/s, out[1] = shared-memory load GB/s, out[2] = popc Gop/s */
+int ser_microbench(int32_t device, double out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SERIATION_B200_H */

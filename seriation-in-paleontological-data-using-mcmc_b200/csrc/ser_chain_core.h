@@ -1,0 +1,480 @@
+/*
+ * ser_chain_core.h -- per-taxon building blocks of the B200 sweep.
+ *
+ * One chain = one CTA; one taxon = one thread.  Each thread owns one *column*
+ * of the chain's bit matrix V: V[w][col] (word-major, stride C words) holds the
+ * taxon's occurrences in POSITION order, bit p = X[rpi[p]][m].  Column M is
+ * the hard-site mask in position order.  Everything the reference evaluates
+ * cell by cell (mcmc.c:828-898, :1127-1682) becomes range popcounts on that
+ * column.  The functions below are the per-thread pieces; the block-level
+ * choreography (reductions, draws, accept) lives in ser_kernels.cu and, for
+ * CPU-side testing of the same logic, in tests/emul/chain_emul.cpp.
+ *
+ * Reference (file:line under /root/reference/C_Implementation):
+ *   ser_gibbs_boundary  mcmc_auxa :828-898 + mcmc_logtop :711-748 + mcmc_randompick :901-915
+ *   ser_pi1_delta       mcmc_samplepi1 :1171-1256
+ *   ser_pi2_delta       mcmc_samplepi2 :1363-1436 (with mcmc_ininterval :1097-1124)
+ *   ser_pi3_delta       mcmc_samplepi3 :1564-1631
+ *   ser_mirror_ab       :1446-1465 / :1641-1660
+ *   ser_col_*           the rpi rotations / reversals :1277-1297, :1469-1474, :1664-1670
+ */
+#ifndef SER_CHAIN_CORE_H
+#define SER_CHAIN_CORE_H
+
+#include "ser_detmath.h"
+
+#ifndef __CUDACC__
+#include <math.h>
+#endif
+
+#define SER_MAXW 32 /* words per column: N <= 1024 */
+
+/* ------------------------------------------------------------------ bit intrinsics */
+#if defined(__CUDA_ARCH__)
+#define SER_POPC(x) __popc((x))
+#define SER_BREV(x) __brev((x))
+#define SER_FFS(x) __ffs((int)(x))
+SER_HD uint32_t ser_funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }
+SER_HD double ser_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+SER_HD double ser_fmax(double a, double b) { return fmax(a, b); }
+#else
+#define SER_POPC(x) __builtin_popcount((x))
+#define SER_FFS(x) __builtin_ffs((int)(x))
+SER_HD uint32_t SER_BREV(uint32_t v)
+{
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+  return (v >> 16) | (v << 16);
+}
+SER_HD uint32_t ser_funnel_r(uint32_t lo, uint32_t hi, int sh)
+{
+  sh &= 31;
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+SER_HD double ser_fma(double a, double b, double c) { return fma(a, b, c); }
+SER_HD double ser_fmax(double a, double b) { return a > b ? a : b; }
+#endif
+
+/* bits [0,n), n in [0,32] */
+SER_HD uint32_t ser_mask_lt(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+
+/* bits of word w (positions 32w .. 32w+31) that fall into [lo, hi) */
+SER_HD uint32_t ser_range_mask(int w, int lo, int hi)
+{
+  int l = lo - 32 * w, h = hi - 32 * w;
+  if (l < 0) l = 0;
+  if (h > 32) h = 32;
+  if (h <= l) return 0u;
+  return ser_mask_lt(h) & ~ser_mask_lt(l);
+}
+
+/* position of the (k+1)-th set bit of mask (k from 0); mask must have > k bits set */
+SER_HD int ser_select_bit(uint32_t mask, int k)
+{
+#if defined(__CUDA_ARCH__)
+  return (int)__fns(mask, 0u, k + 1);
+#else
+  for (int i = 0; i < k; i++) mask &= mask - 1u;
+  return SER_FFS(mask) - 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ columns */
+/* A column is addressed as col[w * C]; words >= W and < 0 read as zero. */
+SER_HD uint32_t ser_col_word(const uint32_t *col, int C, int W, int w)
+{
+  return (w >= 0 && w < W) ? col[w * C] : 0u;
+}
+
+/* 32 bits of the column starting at bit position p (p may be negative / beyond the end) */
+SER_HD uint32_t ser_col_extract32(const uint32_t *col, int C, int W, int p)
+{
+  const int w = p >> 5; /* arithmetic shift: floor */
+  return ser_funnel_r(ser_col_word(col, C, W, w), ser_col_word(col, C, W, w + 1), p & 31);
+}
+
+SER_HD int ser_col_bit(const uint32_t *col, int C, int p) { return (col[(p >> 5) * C] >> (p & 31)) & 1u; }
+
+/* popcount of bits [lo, hi) */
+SER_HD int ser_col_popc(const uint32_t *col, int C, int lo, int hi)
+{
+  int n = 0;
+  if (hi <= lo) return 0;
+  for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) n += SER_POPC(col[w * C] & ser_range_mask(w, lo, hi));
+  return n;
+}
+
+/* word j of the logical string s: REV ? s[k] = v[N-1-k] : s = v */
+template <bool REV>
+SER_HD uint32_t ser_logical_word(const uint32_t *col, int C, int W, int N, int j)
+{
+  if (!REV) return col[j * C];
+  return SER_BREV(ser_col_extract32(col, C, W, N - 32 - 32 * j));
+}
+
+/* in-place: reverse bits [i, j] (new[p] = old[i+j-p]) */
+SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j)
+{
+  uint32_t old[SER_MAXW];
+  const int w0 = i >> 5, w1 = j >> 5;
+  if (i + 1 == j && w0 == w1) { /* adjacent swap inside one word: the common (swap) case */
+    uint32_t v = col[w0 * C];
+    const uint32_t x = ((v >> (i & 31)) ^ (v >> (j & 31))) & 1u;
+    col[w0 * C] = v ^ ((x << (i & 31)) | (x << (j & 31)));
+    return;
+  }
+  for (int w = w0; w <= w1; w++) old[w] = col[w * C];
+  const int s = i + j;
+  for (int wn = w0; wn <= w1; wn++) {
+    /* new bit p = old[s - p]: 32 old bits ending at s - 32wn, reversed */
+    const int q = s - 32 * wn - 31;
+    const int qw = q >> 5;
+    const uint32_t lo = (qw >= w0 && qw <= w1) ? old[qw] : 0u;
+    const uint32_t hi = (qw + 1 >= w0 && qw + 1 <= w1) ? old[qw + 1] : 0u;
+    const uint32_t bits = SER_BREV(ser_funnel_r(lo, hi, q & 31));
+    const uint32_t m = ser_range_mask(wn, i, j + 1);
+    col[wn * C] = (old[wn] & ~m) | (bits & m);
+  }
+}
+
+/* in-place: move bit i to position j, shifting the bits in between by one (pi1) */
+SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j)
+{
+  uint32_t old[SER_MAXW];
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  const int w0 = lo >> 5, w1 = hi >> 5;
+  for (int w = w0; w <= w1; w++) old[w] = col[w * C];
+  const uint32_t moved = (old[i >> 5] >> (i & 31)) & 1u;
+  for (int wn = w0; wn <= w1; wn++) {
+    uint32_t bits, m;
+    const uint32_t cur = old[wn];
+    const uint32_t up = (wn + 1 <= w1) ? old[wn + 1] : 0u, dn = (wn - 1 >= w0) ? old[wn - 1] : 0u;
+    if (i < j) { /* new[p] = old[p+1] for p in [i, j-1] */
+      bits = (cur >> 1) | (up << 31);
+      m = ser_range_mask(wn, i, j);
+    } else { /* new[p] = old[p-1] for p in [j+1, i] */
+      bits = (cur << 1) | (dn >> 31);
+      m = ser_range_mask(wn, j + 1, i + 1);
+    }
+    uint32_t nw = (cur & ~m) | (bits & m);
+    if (wn == (j >> 5)) nw = (nw & ~(1u << (j & 31))) | (moved << (j & 31));
+    col[wn * C] = nw;
+  }
+}
+
+/* in-place: new[p] = old[perm[p]] for p in [i, j] (pi3; perm is an involution on the window) */
+SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uint16_t *perm)
+{
+  uint32_t old[SER_MAXW];
+  const int w0 = i >> 5, w1 = j >> 5;
+  for (int w = w0; w <= w1; w++) old[w] = col[w * C];
+  for (int wn = w0; wn <= w1; wn++) {
+    uint32_t nw = old[wn];
+    const int p0 = (32 * wn > i) ? 32 * wn : i, p1 = (32 * wn + 31 < j) ? 32 * wn + 31 : j;
+    for (int p = p0; p <= p1; p++) {
+      const int src = perm[p];
+      const uint32_t bit = (old[src >> 5] >> (src & 31)) & 1u;
+      nw = (nw & ~(1u << (p & 31))) | (bit << (p & 31));
+    }
+    col[wn * C] = nw;
+  }
+}
+
+/* ------------------------------------------------------------------ hard sites */
+/* hcol = column M (hard mask in position order); hcum[w] = #hard positions in words < w */
+struct SerHard {
+  const uint32_t *hcol;
+  const int *hcum; /* W + 1 entries */
+  int C, W, N, nh;
+};
+
+/* number of hard positions < p, p in [0, N] */
+SER_HD int ser_hard_rank(const SerHard &h, int p)
+{
+  const int w = p >> 5;
+  if (w >= h.W) return h.hcum[h.W];
+  return h.hcum[w] + SER_POPC(h.hcol[w * h.C] & ser_mask_lt(p & 31));
+}
+SER_HD int ser_is_hard(const SerHard &h, int p) { return (h.hcol[(p >> 5) * h.C] >> (p & 31)) & 1u; }
+/* number of hard positions in [lo, hi] */
+SER_HD int ser_hard_count(const SerHard &h, int lo, int hi) { return ser_hard_rank(h, hi + 1) - ser_hard_rank(h, lo); }
+/* position of the r-th (from 0) non-hard position; r < N - nh */
+SER_HD int ser_select_nonhard(const SerHard &h, int r)
+{
+  for (int w = 0; w < h.W; w++) {
+    const int next = 32 * (w + 1) - h.hcum[w + 1];
+    if (r < next) return 32 * w + ser_select_bit(~h.hcol[w * h.C], r - (32 * w - h.hcum[w]));
+  }
+  return h.N - 1; /* unreachable for valid r */
+}
+
+/* ------------------------------------------------------------------ likelihood weights */
+struct SerWeights {
+  double c, cc, d, dd; /* log P(false 1), log(1-e^c), log P(false 0), log(1-e^d) */
+  double w1, w0;       /* log-odds of an in-range cell: one -> dd - c (>0), zero -> d - cc (<0) */
+  double r1, r0;       /* exp(-w1), exp(-w0): weight ratio when the boundary passes a one / zero */
+  double eps;          /* exp(LOGEPSILON) as the host libm evaluates it (mcmc.h:26, mcmc.c:734) */
+};
+
+/* exp(x) for x <= ~0 (weights relative to the maximum); 0 below -708.  FMA Horner, ~1 ulp. */
+SER_HD double ser_exp_weight(double x)
+{
+  if (!(x > -708.0)) return 0.0;
+  const double t = ser_fma(x, 1.4426950408889634074, 6755399441055744.0); /* round to nearest int */
+  const double kd = t - 6755399441055744.0;
+  double r = ser_fma(kd, -6.93147180369123816490e-01, x);
+  r = ser_fma(kd, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;                 /* 1/13! */
+  p = ser_fma(p, r, 2.08767569878681e-09);            /* 1/12! */
+  p = ser_fma(p, r, 2.505210838544172e-08);           /* 1/11! */
+  p = ser_fma(p, r, 2.755731922398589e-07);           /* 1/10! */
+  p = ser_fma(p, r, 2.7557319223985893e-06);          /* 1/9!  */
+  p = ser_fma(p, r, 2.48015873015873e-05);            /* 1/8!  */
+  p = ser_fma(p, r, 1.984126984126984e-04);           /* 1/7!  */
+  p = ser_fma(p, r, 1.388888888888889e-03);           /* 1/6!  */
+  p = ser_fma(p, r, 8.333333333333333e-03);           /* 1/5!  */
+  p = ser_fma(p, r, 4.1666666666666664e-02);          /* 1/4!  */
+  p = ser_fma(p, r, 1.6666666666666666e-01);          /* 1/3!  */
+  p = ser_fma(p, r, 0.5);
+  p = ser_fma(p, r, 1.0);
+  p = ser_fma(p, r, 1.0);
+  const int64_t k = (int64_t)(int32_t)(uint32_t)ser_d2u(t); /* low word of the magic sum = k */
+  return ser_u2d(ser_d2u(p) + ((uint64_t)k << 52));
+}
+
+/* log-weight of candidate with `dn1` more ones / `dn0` more zeros below it than the reference point */
+SER_HD double ser_logw(const SerWeights &w, int dn1, int dn0)
+{
+  return -ser_fma((double)dn1, w.w1, SER_MUL((double)dn0, w.w0));
+}
+
+/*
+ * Gibbs draw of one boundary (the a-step, or the b-step on the reversed column).
+ * Logical string s (REV: s[k] = v[N-1-k]); candidates 0..bound; `cur` is the
+ * current value; weight(i) ~ exp(-sum_{p<i} w(s_p)), floored at eps relative to
+ * the maximum, summed in candidate order; pick = first i with cumsum >= U*total.
+ * ck[] is caller-provided scratch of (bound>>5)+1 doubles.
+ */
+template <bool REV>
+SER_HD int ser_gibbs_boundary(const uint32_t *col, int C, int W, int N, int cur, int bound, double U,
+                              const SerWeights &wt, double *ck)
+{
+  const int nw = (bound >> 5) + 1;
+  /* ones / zeros below the current boundary: the reference point of the log-weights */
+  int o_cur;
+  if (!REV) o_cur = ser_col_popc(col, C, 0, cur);
+  else o_cur = ser_col_popc(col, C, N - cur, N);
+  const int z_cur = cur - o_cur;
+
+  /* pass A: maximum log-weight; local maxima sit just below a one, or at `bound` */
+  double lmax;
+  {
+    int obase = 0;
+    lmax = -1.0e300;
+    for (int j = 0; j < nw; j++) {
+      uint32_t word = ser_logical_word<REV>(col, C, W, N, j) & ser_range_mask(j, 0, bound);
+      int o = obase;
+      obase += SER_POPC(word);
+      while (word) {
+        const int t = SER_FFS(word) - 1;
+        word &= word - 1u;
+        const int i = 32 * j + t;
+        lmax = ser_fmax(lmax, ser_logw(wt, o - o_cur, (i - o) - z_cur));
+        o++;
+      }
+    }
+    lmax = ser_fmax(lmax, ser_logw(wt, obase - o_cur, (bound - obase) - z_cur));
+  }
+
+  /* pass B: floored weights summed in candidate order, one checkpoint per word */
+  double S = 0.0;
+  {
+    int obase = 0;
+    for (int j = 0; j < nw; j++) {
+      const uint32_t word = ser_logical_word<REV>(col, C, W, N, j);
+      double y = ser_exp_weight(SER_SUB(ser_logw(wt, obase - o_cur, (32 * j - obase) - z_cur), lmax));
+      const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
+      if (cnt == 32) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 32; k++) {
+          S = SER_ADD(S, ser_fmax(y, wt.eps));
+          y = SER_MUL(y, ((word >> k) & 1u) ? wt.r1 : wt.r0);
+        }
+      } else {
+        for (int k = 0; k < cnt; k++) {
+          S = SER_ADD(S, ser_fmax(y, wt.eps));
+          y = SER_MUL(y, ((word >> k) & 1u) ? wt.r1 : wt.r0);
+        }
+      }
+      ck[j] = S;
+      obase += SER_POPC(word);
+    }
+  }
+
+  /* pass C: inverse CDF (mcmc_randompick): first candidate whose cumulative weight >= U*S */
+  const double target = SER_MUL(U, S);
+  int j = 0;
+  while (j < nw - 1 && ck[j] < target) j++;
+  double s = j ? ck[j - 1] : 0.0;
+  int obase;
+  if (!REV) obase = ser_col_popc(col, C, 0, 32 * j);
+  else obase = ser_col_popc(col, C, N - 32 * j, N);
+  const uint32_t word = ser_logical_word<REV>(col, C, W, N, j);
+  double y = ser_exp_weight(SER_SUB(ser_logw(wt, obase - o_cur, (32 * j - obase) - z_cur), lmax));
+  const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
+  int k = 0;
+  for (; k < cnt - 1; k++) {
+    s = SER_ADD(s, ser_fmax(y, wt.eps));
+    if (s >= target) break;
+    y = SER_MUL(y, ((word >> k) & 1u) ? wt.r1 : wt.r0);
+  }
+  return 32 * j + k;
+}
+
+/* ------------------------------------------------------------------ pi proposals */
+/* mcmc_ininterval, mcmc.c:1097-1124 (lo <= hi at every call site) */
+SER_HD int ser_in_window(int v, int lo, int hi, int inc_lo, int inc_hi)
+{
+  return (inc_lo ? lo <= v : lo < v) && (inc_hi ? v <= hi : v < hi);
+}
+
+SER_HD void ser_mirror_ab(int a, int b, int ain, int bin, int s, int *na, int *nb)
+{
+  *na = a; *nb = b;
+  if (ain && !bin) *na = s - a;
+  else if (!ain && bin) *nb = s - b;
+  else if (ain && bin) { *nb = s - a; *na = s - b; }
+}
+
+/* pi1: site at position i moves to j.  Only the moved site's status can change. */
+SER_HD void ser_pi1_delta(const uint32_t *col, int C, int a, int b, int i, int j, int *dt0, int *dt1)
+{
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  int gain, lose;
+  if (i < j) {
+    const int ain = lo < a && a <= hi + 1, bin = lo < b && b <= hi + 1;
+    gain = ain && !bin; lose = !ain && bin;
+  } else {
+    const int ain = lo <= a && a <= hi, bin = lo <= b && b <= hi;
+    gain = !ain && bin; lose = ain && !bin;
+  }
+  *dt0 = 0; *dt1 = 0;
+  if (gain | lose) {
+    const int one = ser_col_bit(col, C, i);
+    const int sgn = gain ? 1 : -1;
+    if (one) *dt1 = sgn; else *dt0 = -sgn;
+  }
+}
+SER_HD void ser_pi1_apply_ab(int *a, int *b, int i, int j)
+{
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  if (i < j) {
+    if (lo < *a && *a <= hi + 1) (*a)--;
+    if (lo < *b && *b <= hi + 1) (*b)--;
+  } else {
+    if (lo <= *a && *a <= hi) (*a)++;
+    if (lo <= *b && *b <= hi) (*b)++;
+  }
+}
+
+/* pi2: positions [i, j] reversed */
+SER_HD void ser_pi2_delta(const uint32_t *col, int C, int a, int b, int i, int j, int inc1, int inc2,
+                          int *dt0, int *dt1)
+{
+  const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
+  *dt0 = 0; *dt1 = 0;
+  if (ain == bin) return;
+  const int split = ain ? a : b;
+  const int oL = ser_col_popc(col, C, i, split), oR = ser_col_popc(col, C, split, j + 1);
+  const int zL = (split - i) - oL, zR = (j + 1 - split) - oR;
+  if (ain) { *dt1 = oL - oR; *dt0 = zR - zL; }  /* left part becomes alive, right part dies */
+  else { *dt1 = oR - oL; *dt0 = zL - zR; }      /* left part dies, right part becomes alive */
+}
+
+/* window geometry of a pi3 proposal, shared by all taxa */
+struct SerPi3 {
+  int i, j;        /* window positions (both non-hard) */
+  int irank;       /* global non-hard rank of position i */
+  int K;           /* non-hard sites in the window */
+  int hr_i;        /* hard rank of i */
+};
+SER_HD SerPi3 ser_pi3_window(const SerHard &h, int irank, int jrank)
+{
+  SerPi3 g;
+  g.i = ser_select_nonhard(h, irank);
+  g.j = ser_select_nonhard(h, jrank);
+  g.irank = irank;
+  g.K = jrank - irank + 1;
+  g.hr_i = ser_hard_rank(h, g.i);
+  return g;
+}
+/* non-hard positions in [i, x), x in [i, j+1] */
+SER_HD int ser_pi3_wrank(const SerHard &h, const SerPi3 &g, int x) { return (x - g.i) - (ser_hard_rank(h, x) - g.hr_i); }
+/* position of the window's rho-th non-hard site; rho == K -> j+1 */
+SER_HD int ser_pi3_wpos(const SerHard &h, const SerPi3 &g, int rho) { return rho >= g.K ? g.j + 1 : ser_select_nonhard(h, g.irank + rho); }
+/* where position n of the window goes (the involution p[] of mcmc.c:1534-1555) */
+SER_HD int ser_pi3_perm(const SerHard &h, const SerPi3 &g, int n)
+{
+  if (ser_is_hard(h, n)) return n;
+  return ser_select_nonhard(h, g.irank + g.K - 1 - ser_pi3_wrank(h, g, n));
+}
+
+/* pi3: only the non-hard sites of [i, j] are reversed; a/b mirror as in pi2 */
+SER_HD void ser_pi3_delta(const uint32_t *col, int C, const SerHard &h, const SerPi3 &g, int a, int b,
+                          int inc1, int inc2, int *dt0, int *dt1)
+{
+  const int i = g.i, j = g.j;
+  const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
+  *dt0 = 0; *dt1 = 0;
+  if (!ain && !bin) return; /* no boundary inside the window: every cell keeps its status */
+  int na, nb;
+  ser_mirror_ab(a, b, ain, bin, i + j + 1, &na, &nb);
+  /* was alive: [a,b) cut to the window */
+  const int alo = a > i ? a : i, ahi = b < j + 1 ? b : j + 1;
+  /* is alive afterwards, in OLD position coordinates:
+   *   hard sites stay put            -> hard positions in [na,nb)
+   *   non-hard site of window rank r -> lands on rank K-1-r, alive iff that is in [R(na),R(nb)) */
+  int nac = na < i ? i : (na > j + 1 ? j + 1 : na), nbc = nb < i ? i : (nb > j + 1 ? j + 1 : nb);
+  if (nbc < nac) nbc = nac;
+  const int lo2 = ser_pi3_wpos(h, g, g.K - ser_pi3_wrank(h, g, nbc));
+  const int hi2 = ser_pi3_wpos(h, g, g.K - ser_pi3_wrank(h, g, nac));
+  int oA = 0, oB = 0, nA = 0, nB = 0;
+  for (int w = i >> 5; w <= j >> 5; w++) {
+    const uint32_t v = col[w * C], hw = h.hcol[w * h.C];
+    const uint32_t mA = ser_range_mask(w, alo, ahi);
+    const uint32_t mB = (hw & ser_range_mask(w, nac, nbc)) | (~hw & ser_range_mask(w, lo2, hi2));
+    oA += SER_POPC(v & mA); nA += SER_POPC(mA);
+    oB += SER_POPC(v & mB); nB += SER_POPC(mB);
+  }
+  *dt1 = oB - oA;
+  *dt0 = (nA - oA) - (nB - oB); /* true zeros = dead zeros: gain what the alive zeros lose */
+}
+
+/* per-taxon likelihood term in the reference's operand order (mcmc.c:1214/1435/1630),
+ * df0 = -dt0 and df1 = -dt1 always; never contracted into FMAs */
+SER_HD double ser_term(const SerWeights &w, int dt0, int dt1)
+{
+  return SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)dt0, w.cc), SER_MUL((double)(-dt0), w.d)),
+                         SER_MUL((double)dt1, w.dd)),
+                 SER_MUL((double)(-dt1), w.c));
+}
+
+/* per-taxon counts from the column: t1 = ones alive, the rest by difference (mcmc.c:651-708) */
+SER_HD void ser_counts(const uint32_t *col, int C, int N, int a, int b, int ones, int *t0, int *f0, int *t1,
+                       int *f1)
+{
+  const int o = ser_col_popc(col, C, a, b);
+  *t1 = o;
+  *f1 = ones - o;
+  *f0 = (b - a) - o;
+  *t0 = N - (b - a) - (ones - o);
+}
+
+/* draws -> integers exactly as the tape grammar defines them */
+SER_HD int ser_draw_int(double u, int n) { return (int)SER_MUL(u, (double)n); }
+
+#endif /* SER_CHAIN_CORE_H */

@@ -1,0 +1,301 @@
+// chain_emul.cpp -- CPU emulation of the sweep kernel's choreography (TEST ONLY).
+//
+// Runs ONE chain with the very same per-taxon building blocks the CUDA kernel
+// uses (csrc/ser_chain_core.h compiled for the host), "threads" being a plain
+// loop over columns and block reductions being plain sums.  It exists so that
+// the bit-level logic (range popcounts, rank/select over the hard mask, the
+// pi3 mask construction, the Gibbs walk) can be checked against the oracle on
+// a machine without a GPU.  It is not part of the product and not a fallback:
+// nothing in the package loads it.
+//
+// Replay mode only (tape grammar of oracle/draw_source.h).
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../seriation-in-paleontological-data-using-mcmc_b200/csrc/ser_chain_core.h"
+
+namespace {
+
+constexpr double MINC = -6.9077552789821368, MAXC = -2.3025850929940455;
+constexpr double MIND = -1.6094379124341003, MAXD = -0.22314355131420971;
+
+struct Chain {
+  int N, M, W, C, nh;
+  std::vector<uint8_t> X, hard;
+  std::vector<uint32_t> V; // [W][C], column M = hard mask
+  std::vector<int> a, b, ones, hcum;
+  std::vector<uint16_t> rpi;
+  SerWeights wt;
+  double loglik;
+  int t0a, f0a, t1a, f1a;
+  const double *tape;
+  size_t tape_len, cur;
+  long long n_degenerate;
+
+  uint32_t *col(int m) { return V.data() + m; }
+  SerHard hardinfo() const { return SerHard{V.data() + M, hcum.data(), C, W, N, nh}; }
+  double next() {
+    if (cur >= tape_len) { fprintf(stderr, "emul: tape exhausted\n"); exit(3); }
+    return tape[cur++];
+  }
+  void set_cd(double c, double cc, double d, double dd) {
+    wt.c = c; wt.cc = cc; wt.d = d; wt.dd = dd;
+    wt.w1 = dd - c; wt.w0 = d - cc;
+    wt.r1 = std::exp(-wt.w1); wt.r0 = std::exp(-wt.w0);
+  }
+  void rebuild_hcum() {
+    hcum[0] = 0;
+    for (int w = 0; w < W; w++) hcum[w + 1] = hcum[w] + SER_POPC(V[w * C + M]);
+  }
+  void build_columns() {
+    std::fill(V.begin(), V.end(), 0u);
+    for (int p = 0; p < N; p++) {
+      const int site = rpi[p];
+      for (int m = 0; m < M; m++)
+        if (X[(size_t)site * M + m]) V[(p >> 5) * C + m] |= 1u << (p & 31);
+      if (hard[site]) V[(p >> 5) * C + M] |= 1u << (p & 31);
+    }
+    rebuild_hcum();
+  }
+  void initab() {
+    for (int m = 0; m < M; m++) {
+      int first = -1, last = -1;
+      for (int w = 0; w < W; w++) {
+        uint32_t v = V[w * C + m];
+        if (v) { if (first < 0) first = 32 * w + SER_FFS(v) - 1; last = 32 * w + 31 - __builtin_clz(v); }
+      }
+      if (first < 0) { a[m] = 0; b[m] = N; } else { a[m] = first; b[m] = last + 1; }
+    }
+  }
+  void totals() {
+    long T1 = 0, LEN = 0, ONES = 0;
+    for (int m = 0; m < M; m++) { T1 += ser_col_popc(col(m), C, a[m], b[m]); LEN += b[m] - a[m]; ONES += ones[m]; }
+    t1a = (int)T1; f1a = (int)(ONES - T1); f0a = (int)(LEN - T1); t0a = (int)((long)N * M - LEN - f1a);
+    loglik = t0a * wt.cc + f0a * wt.d + t1a * wt.dd + f1a * wt.c;
+  }
+};
+
+// one MH decision from the block-reduced integer deltas; emulates the reference's float sum
+// only where its sign is not determined by the integers (DESIGN.md "degenerate proposals")
+bool decide(Chain &ch, const std::vector<int> &dt0, const std::vector<int> &dt1, double *delta_out) {
+  long D0 = 0, D1 = 0; bool any = false;
+  for (int m = 0; m < ch.M; m++) { D0 += dt0[m]; D1 += dt1[m]; any |= (dt0[m] | dt1[m]) != 0; }
+  double delta;
+  if (D0 == 0 && D1 == 0) {
+    delta = 0.0;
+    if (any) { // sequential sum of the per-taxon terms, in taxon order, like mcmc.c:1214
+      for (int m = 0; m < ch.M; m++) delta = delta + ser_term(ch.wt, dt0[m], dt1[m]);
+      if (delta != 0.0) ch.n_degenerate++;
+    }
+  } else {
+    delta = ser_term(ch.wt, (int)D0, (int)D1);
+  }
+  *delta_out = delta;
+  if (delta >= 0.0) return true;
+  return delta > std::log(ch.next());
+}
+
+void after_accept(Chain &ch, long D0, long D1, double delta) {
+  ch.t0a += (int)D0; ch.f0a -= (int)D0; ch.t1a += (int)D1; ch.f1a -= (int)D1;
+  ch.loglik += delta;
+}
+
+int pi1(Chain &ch) {
+  const int N = ch.N, M = ch.M, C = ch.C, W = ch.W;
+  int i = ser_draw_int(ch.next(), N), j = ser_draw_int(ch.next(), N - 1);
+  if (j >= i) j++;
+  const int lo = i < j ? i : j, hi = i < j ? j : i;
+  SerHard h = ch.hardinfo();
+  if (ser_is_hard(h, i) && ser_hard_count(h, lo, hi) > 1) return 0;
+  std::vector<int> dt0(M), dt1(M);
+  for (int m = 0; m < M; m++) ser_pi1_delta(ch.col(m), C, ch.a[m], ch.b[m], i, j, &dt0[m], &dt1[m]);
+  double delta;
+  if (!decide(ch, dt0, dt1, &delta)) return 0;
+  long D0 = 0, D1 = 0;
+  for (int m = 0; m < M; m++) { D0 += dt0[m]; D1 += dt1[m]; }
+  for (int m = 0; m < M; m++) ser_pi1_apply_ab(&ch.a[m], &ch.b[m], i, j);
+  for (int m = 0; m <= M; m++) ser_col_rotate(ch.col(m), C, W, i, j);
+  const uint16_t t = ch.rpi[i];
+  if (i < j) for (int n = i; n < j; n++) ch.rpi[n] = ch.rpi[n + 1];
+  else for (int n = i; n > j; n--) ch.rpi[n] = ch.rpi[n - 1];
+  ch.rpi[j] = t;
+  ch.rebuild_hcum();
+  after_accept(ch, D0, D1, delta);
+  return 1;
+}
+
+int pi2(Chain &ch, int swap) {
+  const int N = ch.N, M = ch.M, C = ch.C, W = ch.W;
+  int i, j;
+  if (!swap) {
+    i = ser_draw_int(ch.next(), N); j = ser_draw_int(ch.next(), N - 1);
+    if (j >= i) j++; else { int t = i; i = j; j = t; }
+  } else { i = ser_draw_int(ch.next(), N - 1); j = i + 1; }
+  SerHard h = ch.hardinfo();
+  if (ser_hard_count(h, i, j) > 1) return 0;
+  const int inc1 = ser_draw_int(ch.next(), 2), inc2 = ser_draw_int(ch.next(), 2);
+  std::vector<int> dt0(M), dt1(M);
+  for (int m = 0; m < M; m++) ser_pi2_delta(ch.col(m), C, ch.a[m], ch.b[m], i, j, inc1, inc2, &dt0[m], &dt1[m]);
+  double delta;
+  if (!decide(ch, dt0, dt1, &delta)) return 0;
+  long D0 = 0, D1 = 0;
+  for (int m = 0; m < M; m++) { D0 += dt0[m]; D1 += dt1[m]; }
+  for (int m = 0; m < M; m++) {
+    const int ain = ser_in_window(ch.a[m], i, j + 1, inc1, inc2), bin = ser_in_window(ch.b[m], i, j + 1, inc1, inc2);
+    ser_mirror_ab(ch.a[m], ch.b[m], ain, bin, i + j + 1, &ch.a[m], &ch.b[m]);
+  }
+  for (int m = 0; m <= M; m++) ser_col_reverse(ch.col(m), C, W, i, j);
+  for (int l = i, r = j; l < r; l++, r--) { uint16_t t = ch.rpi[l]; ch.rpi[l] = ch.rpi[r]; ch.rpi[r] = t; }
+  ch.rebuild_hcum();
+  after_accept(ch, D0, D1, delta);
+  return 1;
+}
+
+int pi3(Chain &ch) {
+  const int N = ch.N, M = ch.M, C = ch.C, W = ch.W, nfree = N - ch.nh;
+  if (nfree < 2) return 0;
+  const int r1 = ser_draw_int(ch.next(), nfree), r2 = ser_draw_int(ch.next(), nfree - 1);
+  int ir, jr;
+  if (r1 <= r2) { ir = r1; jr = r2 + 1; } else { ir = r2; jr = r1; }
+  SerHard h = ch.hardinfo();
+  const SerPi3 g = ser_pi3_window(h, ir, jr);
+  const int inc1 = ser_draw_int(ch.next(), 2), inc2 = ser_draw_int(ch.next(), 2);
+  std::vector<int> dt0(M), dt1(M);
+  for (int m = 0; m < M; m++) ser_pi3_delta(ch.col(m), C, h, g, ch.a[m], ch.b[m], inc1, inc2, &dt0[m], &dt1[m]);
+  double delta;
+  if (!decide(ch, dt0, dt1, &delta)) return 0;
+  long D0 = 0, D1 = 0;
+  for (int m = 0; m < M; m++) { D0 += dt0[m]; D1 += dt1[m]; }
+  std::vector<uint16_t> perm(N);
+  for (int n = g.i; n <= g.j; n++) perm[n] = (uint16_t)ser_pi3_perm(h, g, n);
+  for (int m = 0; m < M; m++) {
+    const int ain = ser_in_window(ch.a[m], g.i, g.j + 1, inc1, inc2), bin = ser_in_window(ch.b[m], g.i, g.j + 1, inc1, inc2);
+    ser_mirror_ab(ch.a[m], ch.b[m], ain, bin, g.i + g.j + 1, &ch.a[m], &ch.b[m]);
+  }
+  for (int m = 0; m < M; m++) ser_col_permute(ch.col(m), C, W, g.i, g.j, perm.data());
+  std::vector<uint16_t> tmp(ch.rpi);
+  for (int n = g.i; n <= g.j; n++) ch.rpi[n] = tmp[perm[n]];
+  after_accept(ch, D0, D1, delta);
+  return 1;
+}
+
+void sample_cd(Chain &ch) {
+  double c = ch.wt.c, cc = ch.wt.cc, d = ch.wt.d, dd = ch.wt.dd;
+  { const double y = ch.next(), ly = ch.next(), l1 = ch.next();
+    if (y > 0. && MINC <= ly && ly <= MAXC) { c = ly; cc = l1; } }
+  { const double y = ch.next(), ly = ch.next(), l1 = ch.next();
+    if (y > 0. && MIND <= ly && ly <= MAXD) { d = ly; dd = l1; } }
+  ch.set_cd(c, cc, d, dd);
+}
+
+int sample_ab(Chain &ch) {
+  int changed = 0;
+  std::vector<double> ck(ch.W + 1);
+  for (int m = 0; m < ch.M; m++) {
+    const double ua = ch.next(), ub = ch.next();
+    const int na = ser_gibbs_boundary<false>(ch.col(m), ch.C, ch.W, ch.N, ch.a[m], ch.b[m], ua, ch.wt, ck.data());
+    changed += na != ch.a[m];
+    ch.a[m] = na;
+    const int t = ser_gibbs_boundary<true>(ch.col(m), ch.C, ch.W, ch.N, ch.N - ch.b[m], ch.N - ch.a[m], ub, ch.wt, ck.data());
+    changed += (ch.N - t) != ch.b[m];
+    ch.b[m] = ch.N - t;
+  }
+  ch.totals();
+  return changed;
+}
+
+void sweep(Chain &ch) {
+  sample_cd(ch);
+  sample_ab(ch);
+  pi2(ch, 1);
+  for (int j = 0; j < 5; j++) { pi1(ch); pi2(ch, 0); pi3(ch); }
+}
+
+} // namespace
+
+extern "C" {
+
+void *emul_create(int N, int M, const uint8_t *X, const uint8_t *hard, double c0, double cc0, double d0,
+                  double dd0, double eps) {
+  Chain *ch = new Chain();
+  ch->N = N; ch->M = M; ch->W = N / 32 + 1; ch->C = M + 1; ch->nh = 0;
+  ch->X.assign(X, X + (size_t)N * M);
+  ch->hard.assign(hard, hard + N);
+  for (int n = 0; n < N; n++) ch->nh += hard[n] != 0;
+  ch->V.assign((size_t)ch->W * ch->C, 0u);
+  ch->a.assign(M, 0); ch->b.assign(M, 0); ch->ones.assign(M, 0); ch->hcum.assign(ch->W + 1, 0);
+  ch->rpi.resize(N);
+  for (int n = 0; n < N; n++) ch->rpi[n] = (uint16_t)n;
+  for (int m = 0; m < M; m++) for (int n = 0; n < N; n++) ch->ones[m] += X[(size_t)n * M + m] != 0;
+  ch->wt.eps = eps;
+  ch->set_cd(c0, cc0, d0, dd0);
+  ch->tape = nullptr; ch->tape_len = ch->cur = 0; ch->n_degenerate = 0;
+  ch->build_columns();
+  ch->initab();
+  ch->totals();
+  return ch;
+}
+void emul_free(void *p) { delete (Chain *)p; }
+void emul_set_tape(void *p, const double *tape, size_t len) { Chain *ch = (Chain *)p; ch->tape = tape; ch->tape_len = len; ch->cur = 0; }
+
+// mcmc_randomize (mcmc.c:477-578) in draws
+void emul_randomize(void *p) {
+  Chain &ch = *(Chain *)p;
+  const int N = ch.N, nh = ch.nh;
+  std::vector<int> pi(N);
+  for (int n = 0; n < N; n++) pi[n] = n;
+  if (nh == 0) {
+    for (int i = N - 1; i > 0; i--) { int j = ser_draw_int(ch.next(), i + 1); std::swap(pi[i], pi[j]); }
+    for (int n = 0; n < N; n++) ch.rpi[pi[n]] = (uint16_t)n;
+    ch.build_columns(); // a/b deliberately kept (mcmc.c:486-494)
+    ch.totals();
+    return;
+  }
+  if (nh == N) return;
+  std::vector<int> chosen, rest;
+  for (int i = 0; i < N && (int)chosen.size() < nh; i++)
+    if ((double)(N - i) * ch.next() < (double)(nh - (int)chosen.size())) chosen.push_back(i);
+  { size_t j = 0; for (int i = 0; i < N; i++) { if (j < chosen.size() && chosen[j] == i) j++; else rest.push_back(i); } }
+  for (int i = N - nh - 1; i > 0; i--) { int r = ser_draw_int(ch.next(), i + 1); std::swap(rest[i], rest[r]); }
+  { size_t j = 0, k = 0; for (int i = 0; i < N; i++) pi[i] = ch.hard[i] ? chosen[j++] : rest[k++]; }
+  for (int n = 0; n < N; n++) ch.rpi[pi[n]] = (uint16_t)n;
+  ch.build_columns();
+  ch.initab();
+  ch.totals();
+}
+
+void emul_sweeps(void *p, int n) { for (int s = 0; s < n; s++) sweep(*(Chain *)p); }
+int emul_step(void *p, int kind) {
+  Chain &ch = *(Chain *)p;
+  switch (kind) {
+    case 10: sample_cd(ch); return 2; // c and d together (tape slots 0..5 of the sweep)
+    case 12: return sample_ab(ch);
+    case 13: return pi2(ch, 1);
+    case 14: return pi1(ch);
+    case 15: return pi2(ch, 0);
+    case 16: return pi3(ch);
+  }
+  return -1;
+}
+
+void emul_get_state(void *p, int32_t *a, int32_t *b, int32_t *pi, int32_t *rpi, int32_t *t0, int32_t *f0,
+                    int32_t *t1, int32_t *f1, int32_t tot[4], double cdl[3], long long *slots) {
+  Chain &ch = *(Chain *)p;
+  for (int m = 0; m < ch.M; m++) {
+    a[m] = ch.a[m]; b[m] = ch.b[m];
+    int x0, y0, x1, y1;
+    ser_counts(ch.col(m), ch.C, ch.N, ch.a[m], ch.b[m], ch.ones[m], &x0, &y0, &x1, &y1);
+    t0[m] = x0; f0[m] = y0; t1[m] = x1; f1[m] = y1;
+  }
+  for (int n = 0; n < ch.N; n++) { rpi[n] = ch.rpi[n]; pi[ch.rpi[n]] = n; }
+  tot[0] = ch.t0a; tot[1] = ch.f0a; tot[2] = ch.t1a; tot[3] = ch.f1a;
+  cdl[0] = ch.wt.c; cdl[1] = ch.wt.d; cdl[2] = ch.loglik;
+  *slots = (long long)ch.cur;
+}
+long long emul_degenerate(void *p) { return ((Chain *)p)->n_degenerate; }
+
+} // extern "C"
