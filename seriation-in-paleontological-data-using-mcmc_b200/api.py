@@ -1,0 +1,352 @@
+"""ctypes binding of libseriation_b200.so (include/seriation_b200.h) plus a thin host-side mirror
+of the reference's Python driver (script.py): ``run_all_chains``, ``choose_chains``,
+``compute_pair_order_matrix`` keep their names and meaning, but run as one batched GPU launch.
+
+The library is CUDA-only.  Loading fails loudly if it has not been built, and every compute call
+raises ``SeriationError`` when no B200 is usable: there is no CPU fallback on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libseriation_b200.so")
+
+MODE_FREE, MODE_REPLAY = 0, 1
+STORE_NONE, STORE_PI, STORE_FULL = 0, 1, 2
+
+_i32p, _dp, _u8p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+_i64p, _u64p = C.POINTER(C.c_int64), C.POINTER(C.c_uint64)
+
+
+class SeriationError(RuntimeError):
+    pass
+
+
+class RunConfig(C.Structure):
+    _fields_ = [("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("sweeps_per_call", C.c_int32),
+                ("mode", C.c_int32), ("seed", C.c_uint32), ("store", C.c_int32), ("max_samples", C.c_int32),
+                ("device", C.c_int32)]
+
+
+# every symbol include/seriation_b200.h declares: (name, restype, argtypes)
+_vp = C.c_void_p
+SYMBOLS = [
+    ("ser_last_error", C.c_char_p, []),
+    ("ser_version", C.c_char_p, []),
+    ("ser_dataset_from_bits", C.c_int, [C.c_int32, C.c_int32, _u8p, _u8p, C.POINTER(_vp)]),
+    ("ser_dataset_read_txt", C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    ("ser_dataset_read_stream", C.c_int, [_vp, C.POINTER(_vp)]),
+    ("ser_dataset_dims", C.c_int, [_vp, _i32p, _i32p, _i32p]),
+    ("ser_dataset_get", C.c_int, [_vp, _u8p, _u8p]),
+    ("ser_dataset_free", None, [_vp]),
+    ("ser_dataset_read_names", C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    ("ser_dataset_taxon_name", C.c_char_p, [_vp, C.c_int32]),
+    ("ser_dataset_site_name", C.c_char_p, [_vp, C.c_int32]),
+    ("ser_dataset_site_age", C.c_int, [_vp, C.c_int32, _i32p, _dp, _i32p]),
+    ("ser_dataset_synthetic", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(_vp)]),
+    ("ser_run_create", C.c_int, [_vp, C.POINTER(RunConfig), C.POINTER(_vp)]),
+    ("ser_run_destroy", None, [_vp]),
+    ("ser_run_set_tapes", C.c_int, [_vp, _dp, _u64p]),
+    ("ser_run_init", C.c_int, [_vp]),
+    ("ser_run_advance", C.c_int, [_vp, C.c_int32, C.c_int32]),
+    ("ser_run_sync", C.c_int, [_vp]),
+    ("ser_run_elapsed_ms", C.c_int, [_vp, _dp, C.c_int32]),
+    ("ser_run_kernel_launches", C.c_int, [_vp, _i64p]),
+    ("ser_run_get_state", C.c_int, [_vp, C.c_int32] + [_i32p] * 9 + [_dp, _i64p]),
+    ("ser_run_get_counters", C.c_int, [_vp, C.c_int32, _i64p]),
+    ("ser_run_check", C.c_int, [_vp, _i32p]),
+    ("ser_run_chain_stats", C.c_int, [_vp, _dp, _dp, _dp, _i32p]),
+    ("ser_run_chain_stats_device", C.c_int, [_vp, _vp]),
+    ("ser_run_fetch_samples", C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _dp, _dp, _dp, _i32p]),
+    ("ser_select_chains", C.c_int, [_dp, C.c_int32, C.c_int32, _i32p, _i32p, _dp, _dp]),
+    ("ser_select_chains_device", C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp]),
+    ("ser_run_po_counts_device", C.c_int, [_vp, _vp, C.c_int32, _vp]),
+    ("ser_run_po_counts", C.c_int, [_vp, _i32p, C.c_int32, _i32p]),
+    ("ser_po_finalize", C.c_int, [_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]),
+    ("ser_write_chain_files", C.c_int, [_vp, C.c_int32, C.c_char_p]),
+    ("ser_microbench", C.c_int, [C.c_int32, _dp]),
+]
+
+_lib = None
+
+
+def build() -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["sh", os.path.join(HERE, "build.sh")], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SeriationError(f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                                 "(there is no CPU fallback for the sweep)")
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise SeriationError(f"[{rc}] {lib().ser_last_error().decode()}")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class Dataset:
+    """A sites x taxa 0/1 occurrence matrix with hard-site flags (the reference's .txt files)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        n, m, nh = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(lib().ser_dataset_dims(self._h, C.byref(n), C.byref(m), C.byref(nh)))
+        self.N, self.M, self.nh = n.value, m.value, nh.value
+
+    @classmethod
+    def from_bits(cls, X, hard=None):
+        X = np.ascontiguousarray(X, dtype=np.uint8)
+        hard = np.zeros(X.shape[0], np.uint8) if hard is None else np.ascontiguousarray(hard, dtype=np.uint8)
+        h = _vp()
+        _check(lib().ser_dataset_from_bits(X.shape[0], X.shape[1], _p(X, C.c_uint8), _p(hard, C.c_uint8), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def read_txt(cls, path: str):
+        h = _vp()
+        _check(lib().ser_dataset_read_txt(path.encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def synthetic(cls, N: int, M: int, n_hard: int = 16, seed: int = 0x5EB1A710):
+        h = _vp()
+        _check(lib().ser_dataset_synthetic(N, M, n_hard, seed, C.byref(h)))
+        return cls(h)
+
+    def read_names(self, genus_path=None, sites_path=None):
+        _check(lib().ser_dataset_read_names(self._h, genus_path.encode() if genus_path else None,
+                                            sites_path.encode() if sites_path else None))
+        return self
+
+    def taxon_name(self, m):
+        s = lib().ser_dataset_taxon_name(self._h, m)
+        return s.decode() if s else None
+
+    def site_name(self, n):
+        s = lib().ser_dataset_site_name(self._h, n)
+        return s.decode() if s else None
+
+    def site_age(self, n):
+        mn, age, hard = C.c_int32(), C.c_double(), C.c_int32()
+        _check(lib().ser_dataset_site_age(self._h, n, C.byref(mn), C.byref(age), C.byref(hard)))
+        return mn.value, age.value, bool(hard.value)
+
+    def arrays(self):
+        X, hard = np.empty((self.N, self.M), np.uint8), np.empty(self.N, np.uint8)
+        _check(lib().ser_dataset_get(self._h, _p(X, C.c_uint8), _p(hard, C.c_uint8)))
+        return X, hard
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ser_dataset_free(self._h)
+            self._h = None
+
+
+class Run:
+    """A batch of independent chains on one GPU (replaces script.py's Pool of `mcmc` processes)."""
+
+    def __init__(self, ds: Dataset, n_chains: int, *, mode=MODE_FREE, seed=0, chain_offset=0, sweeps_per_call=10,
+                 store=STORE_NONE, max_samples=0, device=0):
+        self.ds = ds
+        self.N, self.M, self.n_chains = ds.N, ds.M, n_chains
+        self.cfg = RunConfig(n_chains, chain_offset, sweeps_per_call, mode, seed, store, max_samples, device)
+        h = _vp()
+        _check(lib().ser_run_create(ds._h, C.byref(self.cfg), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ser_run_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_tapes(self, tapes):
+        """tapes: list of 1-D float64 arrays, one per local chain (replay mode)."""
+        offs = np.zeros(len(tapes) + 1, np.uint64)
+        offs[1:] = np.cumsum([t.size for t in tapes])
+        flat = np.ascontiguousarray(np.concatenate(tapes), dtype=np.float64)
+        _check(lib().ser_run_set_tapes(self._h, _p(flat, C.c_double), _p(offs, C.c_uint64)))
+        return self
+
+    def init(self):
+        _check(lib().ser_run_init(self._h))
+        return self
+
+    def advance(self, n_calls: int, sampling: bool):
+        _check(lib().ser_run_advance(self._h, n_calls, int(sampling)))
+        return self
+
+    def sync(self):
+        _check(lib().ser_run_sync(self._h))
+        return self
+
+    def elapsed_ms(self, reset=False) -> float:
+        ms = C.c_double()
+        _check(lib().ser_run_elapsed_ms(self._h, C.byref(ms), int(reset)))
+        return ms.value
+
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        _check(lib().ser_run_kernel_launches(self._h, C.byref(n)))
+        return n.value
+
+    def state(self, chain: int) -> dict:
+        N, M = self.N, self.M
+        a, b, t0, f0, t1, f1 = (np.empty(M, np.int32) for _ in range(6))
+        pi, rpi = np.empty(N, np.int32), np.empty(N, np.int32)
+        tot, cdl, slots = np.empty(4, np.int32), np.empty(3), C.c_int64()
+        _check(lib().ser_run_get_state(self._h, chain, *(_p(v, C.c_int32) for v in (a, b, pi, rpi, t0, f0, t1, f1, tot)),
+                                       _p(cdl, C.c_double), C.byref(slots)))
+        return dict(a=a, b=b, pi=pi, rpi=rpi, t0=t0, f0=f0, t1=t1, f1=f1, tot=tot, c=cdl[0], d=cdl[1],
+                    loglik=cdl[2], slots=slots.value)
+
+    def counters(self, chain: int) -> np.ndarray:
+        out = np.empty(8, np.int64)
+        _check(lib().ser_run_get_counters(self._h, chain, _p(out, C.c_int64)))
+        return out
+
+    def check(self) -> int:
+        bad = C.c_int32()
+        rc = lib().ser_run_check(self._h, C.byref(bad))
+        if rc not in (0, -7):
+            _check(rc)
+        return bad.value
+
+    def chain_stats(self):
+        e, c, d = (np.empty(self.n_chains) for _ in range(3))
+        n = C.c_int32()
+        _check(lib().ser_run_chain_stats(self._h, _p(e, C.c_double), _p(c, C.c_double), _p(d, C.c_double), C.byref(n)))
+        return dict(e_negloglik=e, e_c=c, e_d=d, n_samples=n.value)
+
+    def chain_stats_device(self, device_ptr: int):
+        _check(lib().ser_run_chain_stats_device(self._h, device_ptr))
+
+    def fetch_samples(self, chain: int, full=True) -> dict:
+        n = C.c_int32()
+        _check(lib().ser_run_fetch_samples(self._h, chain, None, None, None, None, None, None, C.byref(n)))
+        S, N, M = n.value, self.N, self.M
+        pi = np.empty((S, N), np.int32)
+        if not full:
+            _check(lib().ser_run_fetch_samples(self._h, chain, None, None, _p(pi, C.c_int32), None, None, None, C.byref(n)))
+            return dict(pi=pi)
+        a, b = np.empty((S, M), np.int32), np.empty((S, M), np.int32)
+        c, d, ll = np.empty(S), np.empty(S), np.empty(S)
+        _check(lib().ser_run_fetch_samples(self._h, chain, _p(a, C.c_int32), _p(b, C.c_int32), _p(pi, C.c_int32),
+                                           _p(c, C.c_double), _p(d, C.c_double), _p(ll, C.c_double), C.byref(n)))
+        return dict(a=a, b=b, pi=pi, c=c, d=d, loglik=ll)
+
+    def po_counts(self, chosen) -> np.ndarray:
+        chosen = np.ascontiguousarray(chosen, dtype=np.int32)
+        out = np.zeros((len(chosen), self.N, self.N), np.int32)
+        _check(lib().ser_run_po_counts(self._h, _p(chosen, C.c_int32), len(chosen), _p(out, C.c_int32)))
+        return out
+
+    def po_counts_device(self, chosen_ptr: int, k: int, counts_ptr: int):
+        _check(lib().ser_run_po_counts_device(self._h, chosen_ptr, k, counts_ptr))
+
+    def write_chain_files(self, chain: int, directory: str):
+        _check(lib().ser_write_chain_files(self._h, chain, directory.encode()))
+
+
+def select_chains(e_negloglik, k: int):
+    """choose_chains (script.py:70-99) on the host. Returns (sorted ids, min, sigma)."""
+    e = np.ascontiguousarray(e_negloglik, dtype=np.float64)
+    chosen, n = np.empty(max(k, 1), np.int32), C.c_int32()
+    mn, sd = C.c_double(), C.c_double()
+    _check(lib().ser_select_chains(_p(e, C.c_double), e.size, k, _p(chosen, C.c_int32), C.byref(n), C.byref(mn), C.byref(sd)))
+    return chosen[:n.value].copy(), mn.value, sd.value
+
+
+def select_chains_device(e_ptr: int, n: int, k: int, chosen_ptr: int, info_ptr: int, device=0, stream=None):
+    _check(lib().ser_select_chains_device(e_ptr, n, k, chosen_ptr, info_ptr, device, stream))
+
+
+def po_finalize(counts: np.ndarray, chains_selected: int, faithful=True) -> np.ndarray:
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    k, N, _ = counts.shape
+    po = np.empty((N, N))
+    _check(lib().ser_po_finalize(_p(counts, C.c_int32), k, N, chains_selected, int(faithful), _p(po, C.c_double)))
+    return po
+
+
+def microbench(device=0) -> dict:
+    out = np.empty(3)
+    _check(lib().ser_microbench(device, _p(out, C.c_double)))
+    return dict(fp64_tflops=out[0], lds_gbs=out[1], popc_gops=out[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side mirror of script.py
+class ChainBatch:
+    """What ``run_all_chains(dataset)`` leaves behind in the reference -- 100 ``Chains/chain_XX/``
+    directories -- kept on the GPU instead: E[-logL] per chain and the pi history."""
+
+    def __init__(self, run: Run, burn_calls: int, sample_calls: int):
+        self.run, self.burn_calls, self.sample_calls = run, burn_calls, sample_calls
+        self._stats = None
+
+    def stats(self):
+        if self._stats is None:
+            self._stats = self.run.chain_stats()
+        return self._stats
+
+
+def run_all_chains(dataset, n_chains: int = 100, burn_calls: int = 1000, sample_calls: int = 1000, *, seed: int = 0,
+                   device: int = 0, store: int = STORE_PI, chains_dir: str | None = None) -> ChainBatch:
+    """script.py:48-67.  ``dataset`` is a path to a reference .txt file or a Dataset.  One launch
+    simulates all chains (the reference: Pool(8) over 100 ``./mcmc <i> < dataset`` processes).
+    With ``chains_dir`` the reference's per-chain files are written for the first 100 chains."""
+    ds = dataset if isinstance(dataset, Dataset) else Dataset.read_txt(str(dataset))
+    if chains_dir is not None:
+        store = STORE_FULL
+    run = Run(ds, n_chains, mode=MODE_FREE, seed=seed, store=store, max_samples=sample_calls, device=device)
+    run.init().advance(burn_calls, False).advance(sample_calls, True).sync()
+    batch = ChainBatch(run, burn_calls, sample_calls)
+    if chains_dir is not None:
+        for i in range(min(n_chains, 100)):
+            d = os.path.join(chains_dir, "chain_%02d" % i)
+            os.makedirs(d, exist_ok=True)
+            run.write_chain_files(i, d)
+    return batch
+
+
+def choose_chains(batch: ChainBatch, chains_selected: int):
+    """script.py:70-99 over the batch's E[-logL]."""
+    chosen, _, _ = select_chains(batch.stats()["e_negloglik"], chains_selected)
+    return [int(c) for c in chosen]
+
+
+def compute_pair_order_matrix(batch: ChainBatch, chains, chains_selected: int, sites: int | None = None, faithful=True):
+    """script.py:155-189 for the chosen chains; counts on the GPU, the reference's division quirks on
+    the host.  ``sites`` is accepted for signature compatibility."""
+    counts = batch.run.po_counts(np.asarray(chains, dtype=np.int32))
+    return po_finalize(counts, chains_selected, faithful)
+
+
+def compute_exp_cd(batch: ChainBatch, chains, chains_selected: int):
+    """script.py:102-126: mean over the chosen chains of the per-chain means of exp(c), exp(d)
+    (divided by ``chains_selected``, as the reference does)."""
+    st = batch.stats()
+    return (float(np.sum(st["e_c"][list(chains)]) / chains_selected),
+            float(np.sum(st["e_d"][list(chains)]) / chains_selected))

@@ -1,0 +1,1187 @@
+/*
+ * ser_kernels.cu -- sm_100a kernels of the seriation sweep and the run object behind the C ABI.
+ *
+ * Mapping: one CTA per chain, one thread per taxon (+ one thread owning the hard-site mask).
+ * The chain's occurrence matrix lives in shared memory as position-ordered bit columns
+ * V[word][column]; a/b of a taxon live in its thread's registers.  A sweep is
+ *   stage draws -> c,d -> a/b Gibbs (per thread) -> 16 pi proposals (per-thread integer deltas,
+ *   REDUX + one __syncthreads, redundant uniform decision, per-thread column update on accept).
+ * No tensor cores, no global traffic inside a sweep except the draw tape (replay) and the
+ * thinned samples.  See DESIGN.md for the layout and the roofline that bounds each phase.
+ *
+ * Reference: /root/reference/C_Implementation/mcmc.c (line numbers next to each device function).
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ser_chain_core.h"
+#include "ser_internal.h"
+
+#define SER_MINC (-6.9077552789821368)
+#define SER_MAXC (-2.3025850929940455)
+#define SER_MIND (-1.6094379124341003)
+#define SER_MAXD (-0.22314355131420971)
+
+#define SER_PI_DRAWS 72 /* >= 4 + 5*13 = 69 draws a sweep's pi part can consume */
+#define SER_MAX_WARPS 32
+
+/* ------------------------------------------------------------------ per-chain global state */
+struct ChainScalars {
+  double c, cc, d, dd; /* log P(false 1), log(1-e^c), log P(false 0), log(1-e^d) */
+  double loglik;
+  double sum_negll, sum_ec, sum_ed; /* compute_exp_data, mcmc.c:53-58 */
+  long long cursor;                 /* replay: tape slots consumed */
+  long long counters[8];            /* c, d, ab changed, pi1, pi2(0), pi2(swap), pi3, sweeps */
+  int t0a, f0a, t1a, f1a;
+  unsigned int sweep; /* free-running: sweep index = Philox counter word */
+  int n_samples;
+  int flags; /* bit0 tape exhausted, bit1.. consistency failures */
+  int pad;
+};
+
+struct KParams {
+  int N, M, W, C, nh, Mw, Npad, Mpad;
+  const uint32_t *Xs;  /* [N][Mw] site-major bits */
+  const uint8_t *hard; /* [N] file order */
+  const int *ones;     /* [M] ones per taxon */
+  uint16_t *ab;        /* [chain][2][Mpad] */
+  uint16_t *rpi;       /* [chain][Npad] */
+  ChainScalars *scal;  /* [chain] */
+  int mode, chain_offset;
+  unsigned int seed;
+  const double *tape;
+  const unsigned long long *tape_off;
+  int n_calls, sweeps_per_call, sampling;
+  int store, max_samples;
+  uint16_t *samp_a, *samp_b, *samp_pi;
+  double *samp_cdl;
+  double c0, cc0, d0, dd0, eps;
+  long long ones_total;
+};
+
+/* ------------------------------------------------------------------ shared-memory carve-up */
+struct Smem {
+  double *draws_pi; /* SER_PI_DRAWS */
+  double *draws_cd; /* 8 */
+  double *terms;    /* C */
+  uint32_t *V;      /* W*C */
+  int *red;         /* 2 * SER_MAX_WARPS * 4 */
+  int *hcum;        /* W+1 */
+  uint16_t *rpi, *tmp16, *perm16; /* N each */
+};
+
+__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C)
+{
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
+  size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
+  size_t o_h = take(sizeof(int) * (W + 1));
+  size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
+  if (s) {
+    s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
+    s->V = (uint32_t *)(base + o_v); s->red = (int *)(base + o_r); s->hcum = (int *)(base + o_h);
+    s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q); s->perm16 = (uint16_t *)(base + o_m);
+  }
+  return off;
+}
+
+/* ------------------------------------------------------------------ block helpers */
+/* sum of three ints over the CTA; every thread gets the totals.  One __syncthreads; `buf`
+ * alternates between calls so a warp that runs ahead never overwrites live partials. */
+__device__ __forceinline__ void block_sum3(int v0, int v1, int v2, int *red, int &buf, int *o0, int *o1, int *o2)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v0 = __reduce_add_sync(0xffffffffu, v0);
+  v1 = __reduce_add_sync(0xffffffffu, v1);
+  v2 = __reduce_add_sync(0xffffffffu, v2);
+  int *r = red + buf * (SER_MAX_WARPS * 4);
+  if (lane == 0) { r[warp * 4 + 0] = v0; r[warp * 4 + 1] = v1; r[warp * 4 + 2] = v2; }
+  __syncthreads();
+  int s0 = 0, s1 = 0, s2 = 0;
+  for (int w = 0; w < nwarp; w++) { s0 += r[w * 4 + 0]; s1 += r[w * 4 + 1]; s2 += r[w * 4 + 2]; }
+  buf ^= 1;
+  *o0 = s0; *o1 = s1; *o2 = s2;
+}
+
+/* position-ordered columns from the site-major data and rpi; column M = hard mask */
+__device__ void build_columns(const KParams &p, const Smem &sm)
+{
+  const int tid = threadIdx.x, C = p.C;
+  const int mw = tid >> 5, mb = tid & 31;
+  for (int w = 0; w < p.W; w++) {
+    uint32_t word = 0;
+    const int pend = min(32 * w + 32, p.N);
+    if (tid < p.M) {
+      for (int pos = 32 * w; pos < pend; pos++)
+        word |= ((p.Xs[(size_t)sm.rpi[pos] * p.Mw + mw] >> mb) & 1u) << (pos & 31);
+    } else if (tid == p.M) {
+      for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)(p.hard[sm.rpi[pos]] != 0) << (pos & 31);
+    }
+    sm.V[w * C + tid] = word;
+  }
+}
+
+__device__ void rebuild_hcum(const KParams &p, const Smem &sm)
+{
+  int acc = 0;
+  sm.hcum[0] = 0;
+  for (int w = 0; w < p.W; w++) { acc += __popc(sm.V[w * p.C + p.M]); sm.hcum[w + 1] = acc; }
+}
+
+/* mcmc_initab, mcmc.c:440-474, on the thread's own column */
+__device__ void init_ab(const KParams &p, const uint32_t *col, int *a, int *b)
+{
+  int first = -1, last = -1;
+  for (int w = 0; w < p.W; w++) {
+    const uint32_t v = col[w * p.C];
+    if (v) { if (first < 0) first = 32 * w + __ffs(v) - 1; last = 32 * w + 31 - __clz(v); }
+  }
+  if (first < 0) { *a = 0; *b = p.N; } else { *a = first; *b = last + 1; }
+}
+
+__device__ __forceinline__ void set_weights(SerWeights &wt, double c, double cc, double d, double dd)
+{
+  wt.c = c; wt.cc = cc; wt.d = d; wt.dd = dd;
+  wt.w1 = dd - c; wt.w0 = d - cc;
+  wt.r1 = exp(-wt.w1); wt.r0 = exp(-wt.w0);
+}
+
+/* totals and log-likelihood from the block-reduced alive-ones / lifespan sums (mcmc.c:977-986) */
+__device__ __forceinline__ void totals_from(const KParams &p, const SerWeights &wt, int T1, int LEN, int *t0a, int *f0a,
+                                            int *t1a, int *f1a, double *loglik)
+{
+  const int f1 = (int)p.ones_total - T1, f0 = LEN - T1, t0 = p.N * p.M - LEN - f1;
+  *t1a = T1; *f1a = f1; *f0a = f0; *t0a = t0;
+  *loglik = SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)t0, wt.cc), SER_MUL((double)f0, wt.d)), SER_MUL((double)T1, wt.dd)),
+                    SER_MUL((double)f1, wt.c));
+}
+
+/* ------------------------------------------------------------------ init kernel */
+/* mcmc_readmodel's initial state + mcmc_randomize (mcmc.c:405-433, :477-578) */
+__global__ void ser_init_kernel(KParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem sm;
+  const size_t used = smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+  /* extra scratch behind the common layout: 2N staged draws, pi / rest / chosen as u16 */
+  double *stage = (double *)(smem_raw + used);
+  uint16_t *pi16 = (uint16_t *)(stage + 2 * p.N);
+  uint16_t *rest16 = pi16 + p.N, *chosen16 = rest16 + p.N;
+
+  const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, nh = p.nh;
+  const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+  const double *tape = nullptr;
+  long long tape_len = 0;
+  if (p.mode == SER_MODE_REPLAY) {
+    tape = p.tape + p.tape_off[chain];
+    tape_len = (long long)(p.tape_off[chain + 1] - p.tape_off[chain]);
+  }
+  for (int t = tid; t < 2 * N; t += C) {
+    if (p.mode == SER_MODE_REPLAY) stage[t] = (t < tape_len) ? tape[t] : 0.0;
+    else stage[t] = ser_stream_uniform(p.seed, gchain, SER_SWEEP_INIT, SER_BLK_INIT, (uint32_t)t);
+  }
+  for (int n = tid; n < N; n += C) sm.rpi[n] = (uint16_t)n;
+  __syncthreads();
+
+  int a = 0, b = 0;
+  const uint32_t *col = sm.V + tid;
+  if (nh == 0) { /* identity-order a/b are kept although pi is shuffled (mcmc.c:486-494) */
+    build_columns(p, sm);
+    if (tid < M) init_ab(p, col, &a, &b);
+    __syncthreads();
+  }
+
+  __shared__ int s_used;
+  if (tid == 0) {
+    int used_draws = 0;
+    for (int n = 0; n < N; n++) pi16[n] = (uint16_t)n;
+    if (nh == 0) {
+      for (int i = N - 1; i > 0; i--) {
+        const int j = ser_draw_int(stage[used_draws++], i + 1);
+        const uint16_t t = pi16[i]; pi16[i] = pi16[j]; pi16[j] = t;
+      }
+    } else if (nh < N) {
+      int j = 0;
+      for (int i = 0; i < N && j < nh; i++)
+        if (SER_MUL((double)(N - i), stage[used_draws++]) < (double)(nh - j)) chosen16[j++] = (uint16_t)i;
+      int k = 0;
+      j = 0;
+      for (int i = 0; i < N; i++) {
+        if (j < nh && i == chosen16[j]) j++;
+        else rest16[k++] = (uint16_t)i;
+      }
+      for (int i = N - nh - 1; i > 0; i--) {
+        const int r = ser_draw_int(stage[used_draws++], i + 1);
+        const uint16_t t = rest16[i]; rest16[i] = rest16[r]; rest16[r] = t;
+      }
+      j = k = 0;
+      for (int i = 0; i < N; i++) pi16[i] = p.hard[i] ? chosen16[j++] : rest16[k++];
+    }
+    s_used = used_draws;
+  }
+  __syncthreads();
+  for (int n = tid; n < N; n += C) sm.rpi[pi16[n]] = (uint16_t)n;
+  __syncthreads();
+  build_columns(p, sm);
+  if (nh != 0 && tid < M) init_ab(p, col, &a, &b);
+  __syncthreads();
+
+  SerWeights wt;
+  wt.eps = p.eps;
+  set_weights(wt, p.c0, p.cc0, p.d0, p.dd0);
+  int t1 = 0, len = 0;
+  if (tid < M) { t1 = ser_col_popc(col, C, a, b); len = b - a; }
+  int buf = 0, T1, LEN, dummy;
+  block_sum3(t1, len, 0, sm.red, buf, &T1, &LEN, &dummy);
+  int t0a, f0a, t1a, f1a;
+  double loglik;
+  totals_from(p, wt, T1, LEN, &t0a, &f0a, &t1a, &f1a, &loglik);
+
+  if (tid < M) {
+    p.ab[(size_t)chain * 2 * p.Mpad + tid] = (uint16_t)a;
+    p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid] = (uint16_t)b;
+  }
+  for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
+  if (tid == 0) {
+    ChainScalars sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.c = p.c0; sc.cc = p.cc0; sc.d = p.d0; sc.dd = p.dd0;
+    sc.loglik = loglik;
+    sc.t0a = t0a; sc.f0a = f0a; sc.t1a = t1a; sc.f1a = f1a;
+    sc.cursor = s_used;
+    sc.flags = (p.mode == SER_MODE_REPLAY && s_used > tape_len) ? 1 : 0;
+    p.scal[chain] = sc;
+  }
+}
+
+/* ------------------------------------------------------------------ the sweep kernel */
+struct PropState { /* thread-uniform bookkeeping of the pi part */
+  int k;           /* next slot of draws_pi */
+  int buf;         /* reduction double-buffer index */
+};
+
+/* MH tail shared by the three proposals (mcmc.c:1261/:1441/:1636): block-reduce the integer
+ * deltas, form delta, accept.  Every thread computes the same decision. */
+__device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, const SerWeights &wt, PropState &ps, int dt0,
+                                          int dt1, int *D0, int *D1, double *delta_out)
+{
+  int nz;
+  block_sum3(dt0, dt1, (dt0 | dt1) != 0, sm.red, ps.buf, D0, D1, &nz);
+  double delta;
+  if (*D0 == 0 && *D1 == 0) {
+    delta = 0.0;
+    if (nz) {
+      /* The integer totals cancel but single taxa changed: the reference's sequential float sum
+       * (mcmc.c:1214/1435/1630) may leave a residual whose SIGN decides whether a draw is
+       * consumed.  Re-create that sum exactly: per-taxon terms in taxon order. */
+      if (threadIdx.x < p.M) sm.terms[threadIdx.x] = ser_term(wt, dt0, dt1);
+      __syncthreads();
+      for (int m = 0; m < p.M; m++) delta = SER_ADD(delta, sm.terms[m]);
+    }
+  } else {
+    delta = ser_term(wt, *D0, *D1);
+  }
+  *delta_out = delta;
+  if (delta >= 0.0) return true;
+  const double u = sm.draws_pi[ps.k++];
+  return delta > log(u);
+}
+
+__global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem sm;
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+
+  const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
+  const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+  uint32_t *col = sm.V + tid;
+  const bool is_taxon = tid < M, is_col = tid <= M;
+
+  /* ---- load chain state */
+  ChainScalars sc = p.scal[chain];
+  for (int n = tid; n < N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
+  int a = 0, b = 0, ones = 0;
+  if (is_taxon) {
+    a = p.ab[(size_t)chain * 2 * p.Mpad + tid];
+    b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
+    ones = p.ones[tid];
+  }
+  __syncthreads();
+  build_columns(p, sm);
+  __syncthreads();
+  if (tid == M) rebuild_hcum(p, sm);
+  __syncthreads();
+
+  const double *tape = nullptr;
+  long long tape_len = 0;
+  if (p.mode == SER_MODE_REPLAY) {
+    tape = p.tape + p.tape_off[chain];
+    tape_len = (long long)(p.tape_off[chain + 1] - p.tape_off[chain]);
+  }
+
+  SerWeights wt;
+  wt.eps = p.eps;
+  set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+  SerHard hd;
+  hd.hcol = sm.V + M; hd.hcum = sm.hcum; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh;
+  PropState ps;
+  ps.k = 0; ps.buf = 0;
+  double ck[SER_MAXW + 1];
+
+  for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
+    for (int s = 0; s < p.sweeps_per_call; s++) {
+      /* ================= stage this sweep's draws ================= */
+      double ua = 0.0, ub = 0.0;
+      if (p.mode == SER_MODE_REPLAY) {
+        const long long need = sc.cursor + 6 + 2 * (long long)M;
+        if (need > tape_len) { sc.flags |= 1; break; } /* uniform across the CTA */
+        if (tid < 6) sm.draws_cd[tid] = tape[sc.cursor + tid];
+        for (int t = tid; t < SER_PI_DRAWS; t += C) {
+          const long long idx = need + t;
+          sm.draws_pi[t] = idx < tape_len ? tape[idx] : 0.5;
+        }
+        if (is_taxon) { ua = tape[sc.cursor + 6 + 2 * tid]; ub = tape[sc.cursor + 7 + 2 * tid]; }
+      } else {
+        if (tid < 4) { /* Beta(1+f1a,1+t0a) and Beta(1+f0a,1+t1a) as Gamma ratios (mcmc.c:790, :820) */
+          const int cnt = tid == 0 ? sc.f1a : tid == 1 ? sc.t0a : tid == 2 ? sc.f0a : sc.t1a;
+          const double g = ser_gamma_ge1(1.0 + (double)cnt, p.seed, gchain, sc.sweep, (uint32_t)tid);
+          const double go = __shfl_xor_sync(0xfu, g, 1);
+          if (tid == 0 || tid == 2) {
+            const double y = ser_beta_from_gammas(g, go);
+            double val = tid == 0 ? sc.c : sc.d, l1m = tid == 0 ? sc.cc : sc.dd;
+            const double lo = tid == 0 ? SER_MINC : SER_MIND, hi = tid == 0 ? SER_MAXC : SER_MAXD;
+            if (y > 0.0) { /* mcmc_samplebeta, mcmc.c:751-765 */
+              const double ly = ser_log(y);
+              if (lo <= ly && ly <= hi) { val = ly; l1m = ser_log(SER_SUB(1.0, ser_exp(ly))); }
+            }
+            sm.draws_cd[tid] = val; sm.draws_cd[tid + 1] = l1m;
+          }
+        }
+        for (int t = tid; t < SER_PI_DRAWS; t += C)
+          sm.draws_pi[t] = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+        if (is_taxon) {
+          uint32_t o[4];
+          ser_philox4x32_10((uint32_t)tid, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+          ua = ser_u53(o[0], o[1]); ub = ser_u53(o[2], o[3]);
+        }
+      }
+      __syncthreads();
+
+      /* ================= c and d (mcmc_samplec / mcmc_sampled) ================= */
+      if (p.mode == SER_MODE_REPLAY) {
+        const double yc = sm.draws_cd[0], lyc = sm.draws_cd[1], l1c = sm.draws_cd[2];
+        const double yd = sm.draws_cd[3], lyd = sm.draws_cd[4], l1d = sm.draws_cd[5];
+        if (yc > 0.0 && SER_MINC <= lyc && lyc <= SER_MAXC) { sc.c = lyc; sc.cc = l1c; }
+        if (yd > 0.0 && SER_MIND <= lyd && lyd <= SER_MAXD) { sc.d = lyd; sc.dd = l1d; }
+      } else {
+        sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3];
+      }
+      set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+      sc.counters[0]++; sc.counters[1]++;
+
+      /* ================= a/b Gibbs (mcmc_sampleab, mcmc.c:918-996) ================= */
+      int t1 = 0, len = 0, changed = 0;
+      if (is_taxon) {
+        const int na = ser_gibbs_boundary<false>(col, C, W, N, a, b, ua, wt, ck);
+        changed += na != a;
+        a = na;
+        const int t = ser_gibbs_boundary<true>(col, C, W, N, N - b, N - a, ub, wt, ck);
+        changed += (N - t) != b;
+        b = N - t;
+        t1 = ser_col_popc(col, C, a, b);
+        len = b - a;
+      }
+      {
+        int T1, LEN, CH;
+        block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
+        totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
+        sc.counters[2] += CH;
+      }
+
+      /* ================= 16 proposals for pi (mcmc.c:237-243) ================= */
+      ps.k = 0;
+      for (int prop = 0; prop < 16; prop++) {
+        /* order: pi2(swap), then 5 x (pi1, pi2(0), pi3) */
+        const int kind = prop == 0 ? 3 : ((prop - 1) % 3); /* 0 pi1, 1 pi2(0), 2 pi3, 3 pi2(swap) */
+        int dt0 = 0, dt1 = 0, D0, D1;
+        double delta;
+        if (kind == 0) { /* ---------------- mcmc_samplepi1, mcmc.c:1127-1308 */
+          const int i = ser_draw_int(sm.draws_pi[ps.k], N);
+          int j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+          ps.k += 2;
+          if (j >= i) j++;
+          const int lo = min(i, j), hi = max(i, j);
+          if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
+          if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
+          if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
+          if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
+          if (is_col) ser_col_rotate(col, C, W, i, j);
+          for (int n = lo + tid; n <= hi; n += C)
+            sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
+          __syncthreads();
+          for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
+          if (tid == M) rebuild_hcum(p, sm);
+          sc.counters[3]++;
+        } else if (kind == 1 || kind == 3) { /* ---------------- mcmc_samplepi2, mcmc.c:1311-1486 */
+          int i, j;
+          if (kind == 1) {
+            i = ser_draw_int(sm.draws_pi[ps.k], N);
+            j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+            ps.k += 2;
+            if (j >= i) j++;
+            else { const int t = i; i = j; j = t; }
+          } else {
+            i = ser_draw_int(sm.draws_pi[ps.k], N - 1);
+            ps.k += 1;
+            j = i + 1;
+          }
+          if (ser_hard_count(hd, i, j) > 1) continue;
+          const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+          ps.k += 2;
+          if (is_taxon) ser_pi2_delta(col, C, a, b, i, j, inc1, inc2, &dt0, &dt1);
+          if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
+          if (is_taxon) {
+            const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
+            ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
+          }
+          if (is_col) ser_col_reverse(col, C, W, i, j);
+          for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
+          __syncthreads();
+          for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
+          if (tid == M) rebuild_hcum(p, sm);
+          sc.counters[kind == 1 ? 4 : 5]++;
+        } else { /* ---------------- mcmc_samplepi3, mcmc.c:1489-1682 */
+          const int nfree = N - p.nh;
+          if (nfree < 2) continue;
+          const int r1 = ser_draw_int(sm.draws_pi[ps.k], nfree), r2 = ser_draw_int(sm.draws_pi[ps.k + 1], nfree - 1);
+          ps.k += 2;
+          int ir, jr;
+          if (r1 <= r2) { ir = r1; jr = r2 + 1; } else { ir = r2; jr = r1; }
+          const SerPi3 g = ser_pi3_window(hd, ir, jr);
+          const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+          ps.k += 2;
+          if (is_taxon) ser_pi3_delta(col, C, hd, g, a, b, inc1, inc2, &dt0, &dt1);
+          if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
+          for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
+          __syncthreads();
+          if (is_taxon) {
+            const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
+            ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
+            ser_col_permute(col, C, W, g.i, g.j, sm.perm16);
+          }
+          for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
+          __syncthreads();
+          for (int n = g.i + tid; n <= g.j; n += C) sm.rpi[n] = sm.tmp16[n];
+          sc.counters[6]++;
+        }
+        /* accepted: fold the integer deltas into the totals (the reference recounts, mcmc.c:1303) */
+        sc.t0a += D0; sc.f0a -= D0; sc.t1a += D1; sc.f1a -= D1;
+        sc.loglik = SER_ADD(sc.loglik, delta);
+        __syncthreads(); /* columns / hard mask / rpi visible before the next proposal */
+      }
+
+      if (p.mode == SER_MODE_REPLAY) sc.cursor += 6 + 2 * (long long)M + ps.k;
+      else sc.sweep++;
+      sc.counters[7]++;
+    }
+    if (sc.flags & 1) break;
+
+    /* ================= thinned sample (mcmc_save_chain + compute_exp_data) ================= */
+    if (p.sampling) {
+      const int sidx = sc.n_samples;
+      if (sidx < p.max_samples) {
+        const size_t row = (size_t)chain * p.max_samples + sidx;
+        if (p.store >= SER_STORE_PI)
+          for (int pos = tid; pos < N; pos += C) p.samp_pi[row * N + sm.rpi[pos]] = (uint16_t)pos;
+        if (p.store >= SER_STORE_FULL) {
+          if (is_taxon) { p.samp_a[row * M + tid] = (uint16_t)a; p.samp_b[row * M + tid] = (uint16_t)b; }
+          if (tid == 0) { p.samp_cdl[row * 3 + 0] = sc.c; p.samp_cdl[row * 3 + 1] = sc.d; p.samp_cdl[row * 3 + 2] = sc.loglik; }
+        }
+      }
+      sc.sum_negll = SER_ADD(sc.sum_negll, -sc.loglik);
+      sc.sum_ec = SER_ADD(sc.sum_ec, exp(sc.c));
+      sc.sum_ed = SER_ADD(sc.sum_ed, exp(sc.d));
+      sc.n_samples++;
+    }
+  }
+
+  /* ---- save chain state */
+  __syncthreads();
+  if (is_taxon) {
+    p.ab[(size_t)chain * 2 * p.Mpad + tid] = (uint16_t)a;
+    p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid] = (uint16_t)b;
+  }
+  for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
+  if (tid == 0) p.scal[chain] = sc;
+  (void)ones;
+}
+
+/* ------------------------------------------------------------------ export / check kernels */
+/* int32 view of one chain's state incl. the derived per-taxon counts (mcmc_count01) */
+__global__ void ser_export_kernel(KParams p, int chain, int *out_a, int *out_b, int *out_pi, int *out_rpi, int *out_cnt)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem sm;
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+  const int tid = threadIdx.x, C = p.C;
+  for (int n = tid; n < p.N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
+  __syncthreads();
+  build_columns(p, sm);
+  for (int n = tid; n < p.N; n += C) { out_rpi[n] = sm.rpi[n]; out_pi[sm.rpi[n]] = n; }
+  if (tid < p.M) {
+    const int a = p.ab[(size_t)chain * 2 * p.Mpad + tid], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
+    int t0, f0, t1, f1;
+    ser_counts(sm.V + tid, C, p.N, a, b, p.ones[tid], &t0, &f0, &t1, &f1);
+    out_a[tid] = a; out_b[tid] = b;
+    out_cnt[tid] = t0; out_cnt[p.M + tid] = f0; out_cnt[2 * p.M + tid] = t1; out_cnt[3 * p.M + tid] = f1;
+  }
+}
+
+/* mcmc_consistent (mcmc.c:999-1094) for every chain; flags |= 2 a/b range, 4 permutation,
+ * 8 hard-site order, 16 totals / log-likelihood */
+__global__ void ser_check_kernel(KParams p, int *bad_count)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem sm;
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+  const int chain = blockIdx.x, tid = threadIdx.x, C = p.C, N = p.N, M = p.M;
+  __shared__ int s_flags;
+  if (tid == 0) s_flags = 0;
+  for (int n = tid; n < N; n += C) { sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n]; sm.tmp16[n] = 0xffff; }
+  __syncthreads();
+  for (int n = tid; n < N; n += C) {
+    const int site = sm.rpi[n];
+    if (site >= N) atomicOr(&s_flags, 4);
+    else sm.tmp16[site] = (uint16_t)n; /* pi */
+  }
+  __syncthreads();
+  for (int n = tid; n < N; n += C) if (sm.tmp16[n] == 0xffff) atomicOr(&s_flags, 4);
+  if (tid == 0) { /* hard sites in increasing position in file order */
+    int last = -1, cnt = 0;
+    for (int n = 0; n < N; n++)
+      if (p.hard[n]) { cnt++; if (last >= 0 && (int)sm.tmp16[n] < last) s_flags |= 8; last = sm.tmp16[n]; }
+    if (cnt != p.nh) atomicOr(&s_flags, 8);
+  }
+  build_columns(p, sm);
+  int t1 = 0, len = 0;
+  if (tid < M) {
+    const int a = p.ab[(size_t)chain * 2 * p.Mpad + tid], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
+    if (!(0 <= a && a <= b && b <= N)) atomicOr(&s_flags, 2);
+    else { t1 = ser_col_popc(sm.V + tid, C, a, b); len = b - a; }
+  }
+  int buf = 0, T1, LEN, dummy;
+  block_sum3(t1, len, 0, sm.red, buf, &T1, &LEN, &dummy);
+  if (tid == 0) {
+    const ChainScalars sc = p.scal[chain];
+    SerWeights wt;
+    set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+    int t0a, f0a, t1a, f1a;
+    double ll;
+    totals_from(p, wt, T1, LEN, &t0a, &f0a, &t1a, &f1a, &ll);
+    if (t0a != sc.t0a || f0a != sc.f0a || t1a != sc.t1a || f1a != sc.f1a || fabs(ll - sc.loglik) > 1e-8) s_flags |= 16;
+    const int fl = s_flags | (sc.flags & 1);
+    if (fl) atomicAdd(bad_count, 1);
+    p.scal[chain].flags = (sc.flags & 1) | fl;
+  }
+}
+
+/* ------------------------------------------------------------------ cross-chain kernels */
+__global__ void ser_stats_kernel(const ChainScalars *scal, int n, double *out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = scal[i].n_samples > 0 ? scal[i].sum_negll / (double)scal[i].n_samples : 0.0;
+}
+
+__device__ double block_reduce_d(double v, double *sh, int op) /* 0 sum, 1 min */
+{
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = op ? fmin(v, t) : v + t;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = sh[0];
+  for (int w = 1; w < nw; w++) r = op ? fmin(r, sh[w]) : r + sh[w];
+  return r;
+}
+
+/* choose_chains (script.py:70-99) on one CTA: min, population sigma over all chains, the k
+ * smallest inside (min-sigma, min+sigma), ids ascending */
+__global__ void ser_select_kernel(const double *e, int n, int k, int *chosen, double *info)
+{
+  __shared__ double sh[32];
+  __shared__ double s_best;
+  __shared__ int s_besti;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double s = 0.0, mn = 1.0e300;
+  for (int i = tid; i < n; i += nt) { s += e[i]; mn = fmin(mn, e[i]); }
+  const double mean = block_reduce_d(s, sh, 0) / (double)n;
+  mn = block_reduce_d(mn, sh, 1);
+  double v = 0.0;
+  for (int i = tid; i < n; i += nt) { const double d = e[i] - mean; v += d * d; }
+  const double sigma = sqrt(block_reduce_d(v, sh, 0) / (double)n);
+  const double lo = mn - sigma, hi = mn + sigma;
+  /* k rounds of arg-min over the not-yet-taken candidates, ties by lower id */
+  double last_v = -1.0e300;
+  int last_i = -1, found = 0;
+  for (int r = 0; r < k; r++) {
+    double bv = 1.0e300;
+    int bi = -1;
+    for (int i = tid; i < n; i += nt) {
+      const double x = e[i];
+      if (!(x > lo && x < hi)) continue;
+      if (x < last_v || (x == last_v && i <= last_i)) continue;
+      if (x < bv || (x == bv && i < bi)) { bv = x; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (tid == 0) { s_best = 1.0e300; s_besti = -1; }
+    __syncthreads();
+    for (int w = 0; w < (nt >> 5); w++) {
+      if ((tid >> 5) == w && (tid & 31) == 0 && bi >= 0)
+        if (s_besti < 0 || bv < s_best || (bv == s_best && bi < s_besti)) { s_best = bv; s_besti = bi; }
+      __syncthreads();
+    }
+    if (s_besti < 0) break;
+    last_v = s_best; last_i = s_besti;
+    if (tid == 0) chosen[found] = s_besti;
+    found++;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int r = found; r < k; r++) chosen[r] = -1;
+    for (int x = 1; x < found; x++) { /* ids ascending (script.py:98) */
+      const int key = chosen[x];
+      int y = x - 1;
+      while (y >= 0 && chosen[y] > key) { chosen[y + 1] = chosen[y]; y--; }
+      chosen[y + 1] = key;
+    }
+    info[0] = (double)found; info[1] = mn; info[2] = sigma;
+  }
+}
+
+/* pair-order counts (script.py:178-189) for one chosen chain per blockIdx.z */
+__global__ void ser_po_kernel(const uint16_t *samp_pi, int N, int max_samples, int n_samples, const int *chosen,
+                              int chain_offset, int n_local, int *counts)
+{
+  const int g = chosen[blockIdx.z];
+  if (g < chain_offset || g >= chain_offset + n_local) return;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || j >= N) return;
+  const uint16_t *pi = samp_pi + (size_t)(g - chain_offset) * max_samples * N;
+  int c = 0;
+  for (int t = 0; t < n_samples; t++) c += pi[(size_t)t * N + i] < pi[(size_t)t * N + j];
+  counts[((size_t)blockIdx.z * N + i) * N + j] = (i == j) ? -n_samples : c;
+}
+
+/* ------------------------------------------------------------------ micro-benchmarks */
+__global__ void mb_fp64_kernel(double *out, int iters)
+{
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void mb_lds_kernel(unsigned *out, int iters)
+{
+  __shared__ uint4 buf[1024];
+  buf[threadIdx.x] = make_uint4(threadIdx.x, 1, 2, 3);
+  __syncthreads();
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  int idx = threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const uint4 v = buf[(idx + u * 32) & 1023];
+      acc.x += v.x; acc.y ^= v.y; acc.z += v.z; acc.w ^= v.w;
+    }
+    idx = (idx + acc.y) & 1023;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
+}
+__global__ void mb_popc_kernel(unsigned *out, int iters)
+{
+  unsigned x0 = threadIdx.x + 1, x1 = x0 * 3, x2 = x0 * 5, x3 = x0 * 7, s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int i = 0; i < iters; i++) {
+    s0 += __popc(x0 ^ s3); s1 += __popc(x1 ^ s0); s2 += __popc(x2 ^ s1); s3 += __popc(x3 ^ s2);
+    s0 += __popc(x0 + s2); s1 += __popc(x1 + s3); s2 += __popc(x2 + s0); s3 += __popc(x3 + s1);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s0 + s1 + s2 + s3;
+}
+
+/* ================================================================== host side: the run object */
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ser_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return SER_E_CUDA;                                                                        \
+    }                                                                                           \
+  } while (0)
+
+struct ser_run {
+  ser_run_config cfg;
+  KParams kp;
+  int N, M, W, C, nh;
+  uint8_t *h_hard;
+  uint32_t *d_Xs;
+  uint8_t *d_hard;
+  int *d_ones;
+  uint16_t *d_ab, *d_rpi;
+  ChainScalars *d_scal;
+  double *d_tape;
+  unsigned long long *d_tape_off;
+  uint16_t *d_samp_a, *d_samp_b, *d_samp_pi;
+  double *d_samp_cdl;
+  int *d_scratch_i; /* export buffers: a,b,pi,rpi,cnt[4M] */
+  int *d_bad;
+  cudaStream_t stream;
+  cudaEvent_t ev_start, ev_stop;
+  int timing_open;
+  double elapsed_ms;
+  long long launches;
+  size_t smem_sweep, smem_init;
+  int initialized, have_tapes;
+};
+
+static int set_device(const ser_run *run) { CUDA_TRY(cudaSetDevice(run->cfg.device)); return SER_OK; }
+
+static void mark_launch(ser_run *run)
+{
+  if (!run->timing_open) { cudaEventRecord(run->ev_start, run->stream); run->timing_open = 1; }
+  run->launches++;
+}
+
+extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, ser_run **out)
+{
+  if (!ds || !cfg || !out) { ser_set_error("ser_run_create: null argument"); return SER_E_ARG; }
+  const int N = ds->N, M = ds->M;
+  if (N < 2 || N > SER_MAX_SITES) { ser_set_error("ser_run_create: N=%d outside [2,%d]", N, SER_MAX_SITES); return SER_E_ARG; }
+  if (M < 1 || M + 1 > 1024) { ser_set_error("ser_run_create: M=%d: this build maps one taxon per thread, M <= 1023", M); return SER_E_ARG; }
+  if (cfg->n_chains < 1 || cfg->sweeps_per_call < 1) { ser_set_error("ser_run_create: n_chains and sweeps_per_call must be >= 1"); return SER_E_ARG; }
+  if (cfg->mode != SER_MODE_FREE && cfg->mode != SER_MODE_REPLAY) { ser_set_error("ser_run_create: bad mode"); return SER_E_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    ser_set_error("ser_run_create: no CUDA device (this library has no CPU path)");
+    return SER_E_CUDA;
+  }
+  ser_run *run = (ser_run *)calloc(1, sizeof(ser_run));
+  run->cfg = *cfg;
+  run->N = N; run->M = M; run->nh = ds->nh;
+  run->W = N / 32 + 1;
+  run->C = ((M + 1) + 31) / 32 * 32;
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&run->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&run->ev_start));
+  CUDA_TRY(cudaEventCreate(&run->ev_stop));
+
+  KParams &kp = run->kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.N = N; kp.M = M; kp.W = run->W; kp.C = run->C; kp.nh = ds->nh;
+  kp.Mw = (M + 31) / 32; kp.Npad = (N + 7) / 8 * 8; kp.Mpad = (M + 7) / 8 * 8;
+  kp.mode = cfg->mode; kp.chain_offset = cfg->chain_offset; kp.seed = cfg->seed;
+  kp.sweeps_per_call = cfg->sweeps_per_call; kp.store = cfg->store; kp.max_samples = cfg->max_samples;
+  /* initial c, d and the flooring constant with the HOST libm: the bits the reference gets */
+  kp.c0 = log(.01); kp.d0 = log(.3);
+  kp.cc0 = log(1. - exp(kp.c0)); kp.dd0 = log(1. - exp(kp.d0));
+  kp.eps = exp(-32.236191301916641); /* exp(LOGEPSILON), mcmc.h:26 */
+
+  /* site-major bit matrix + per-taxon ones */
+  std::vector<uint32_t> Xs((size_t)N * kp.Mw, 0u);
+  std::vector<int> ones(M, 0);
+  long long ones_total = 0;
+  for (int n = 0; n < N; n++)
+    for (int m = 0; m < M; m++)
+      if (ds->X[(size_t)n * M + m]) { Xs[(size_t)n * kp.Mw + (m >> 5)] |= 1u << (m & 31); ones[m]++; ones_total++; }
+  kp.ones_total = ones_total;
+  run->h_hard = (uint8_t *)malloc(N);
+  memcpy(run->h_hard, ds->hard, N);
+
+  const size_t nc = (size_t)cfg->n_chains;
+  CUDA_TRY(cudaMalloc(&run->d_Xs, Xs.size() * 4));
+  CUDA_TRY(cudaMalloc(&run->d_hard, N));
+  CUDA_TRY(cudaMalloc(&run->d_ones, M * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&run->d_ab, nc * 2 * kp.Mpad * sizeof(uint16_t)));
+  CUDA_TRY(cudaMalloc(&run->d_rpi, nc * kp.Npad * sizeof(uint16_t)));
+  CUDA_TRY(cudaMalloc(&run->d_scal, nc * sizeof(ChainScalars)));
+  CUDA_TRY(cudaMalloc(&run->d_scratch_i, (size_t)(2 * N + 6 * M + 16) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&run->d_bad, sizeof(int)));
+  CUDA_TRY(cudaMemcpyAsync(run->d_Xs, Xs.data(), Xs.size() * 4, cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(run->d_hard, ds->hard, N, cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(run->d_ones, ones.data(), M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemsetAsync(run->d_scal, 0, nc * sizeof(ChainScalars), run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  if (cfg->store >= SER_STORE_PI && cfg->max_samples > 0) {
+    CUDA_TRY(cudaMalloc(&run->d_samp_pi, nc * cfg->max_samples * N * sizeof(uint16_t)));
+  }
+  if (cfg->store >= SER_STORE_FULL && cfg->max_samples > 0) {
+    CUDA_TRY(cudaMalloc(&run->d_samp_a, nc * cfg->max_samples * M * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&run->d_samp_b, nc * cfg->max_samples * M * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&run->d_samp_cdl, nc * cfg->max_samples * 3 * sizeof(double)));
+  }
+  kp.Xs = run->d_Xs; kp.hard = run->d_hard; kp.ones = run->d_ones;
+  kp.ab = run->d_ab; kp.rpi = run->d_rpi; kp.scal = run->d_scal;
+  kp.samp_a = run->d_samp_a; kp.samp_b = run->d_samp_b; kp.samp_pi = run->d_samp_pi; kp.samp_cdl = run->d_samp_cdl;
+
+  run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C);
+  run->smem_init = run->smem_sweep + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
+  if (run->smem_init > 227 * 1024) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_init); return SER_E_ARG; }
+  CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+  CUDA_TRY(cudaFuncSetAttribute(ser_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_init));
+  CUDA_TRY(cudaFuncSetAttribute(ser_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+  CUDA_TRY(cudaFuncSetAttribute(ser_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+  *out = run;
+  return SER_OK;
+}
+
+extern "C" void ser_run_destroy(ser_run *run)
+{
+  if (!run) return;
+  cudaSetDevice(run->cfg.device);
+  cudaStreamSynchronize(run->stream);
+  cudaFree(run->d_Xs); cudaFree(run->d_hard); cudaFree(run->d_ones); cudaFree(run->d_ab); cudaFree(run->d_rpi);
+  cudaFree(run->d_scal); cudaFree(run->d_tape); cudaFree(run->d_tape_off); cudaFree(run->d_samp_a);
+  cudaFree(run->d_samp_b); cudaFree(run->d_samp_pi); cudaFree(run->d_samp_cdl); cudaFree(run->d_scratch_i);
+  cudaFree(run->d_bad);
+  cudaEventDestroy(run->ev_start); cudaEventDestroy(run->ev_stop);
+  cudaStreamDestroy(run->stream);
+  free(run->h_hard);
+  free(run);
+}
+
+extern "C" int ser_run_dims(const ser_run *run, int32_t *N, int32_t *M, int32_t *nh, int32_t *n_chains)
+{
+  if (!run) return SER_E_ARG;
+  if (N) *N = run->N;
+  if (M) *M = run->M;
+  if (nh) *nh = run->nh;
+  if (n_chains) *n_chains = run->cfg.n_chains;
+  return SER_OK;
+}
+extern "C" const uint8_t *ser_run_hard_flags(const ser_run *run) { return run ? run->h_hard : nullptr; }
+
+extern "C" int ser_run_set_tapes(ser_run *run, const double *flat, const uint64_t *offsets)
+{
+  if (!run || !flat || !offsets) { ser_set_error("ser_run_set_tapes: null argument"); return SER_E_ARG; }
+  if (run->cfg.mode != SER_MODE_REPLAY) { ser_set_error("ser_run_set_tapes: run is not in replay mode"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  const size_t nc = (size_t)run->cfg.n_chains, total = (size_t)offsets[nc];
+  cudaFree(run->d_tape); cudaFree(run->d_tape_off);
+  run->d_tape = nullptr; run->d_tape_off = nullptr;
+  CUDA_TRY(cudaMalloc(&run->d_tape, (total ? total : 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&run->d_tape_off, (nc + 1) * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemcpyAsync(run->d_tape, flat, total * sizeof(double), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(run->d_tape_off, offsets, (nc + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  run->kp.tape = run->d_tape; run->kp.tape_off = run->d_tape_off;
+  run->have_tapes = 1;
+  return SER_OK;
+}
+
+extern "C" int ser_run_init(ser_run *run)
+{
+  if (!run) return SER_E_ARG;
+  if (run->cfg.mode == SER_MODE_REPLAY && !run->have_tapes) { ser_set_error("ser_run_init: replay mode needs ser_run_set_tapes first"); return SER_E_TAPE; }
+  if (set_device(run)) return SER_E_CUDA;
+  mark_launch(run);
+  ser_init_kernel<<<run->cfg.n_chains, run->C, run->smem_init, run->stream>>>(run->kp);
+  CUDA_TRY(cudaGetLastError());
+  run->initialized = 1;
+  return SER_OK;
+}
+
+extern "C" int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling)
+{
+  if (!run) return SER_E_ARG;
+  if (!run->initialized) { ser_set_error("ser_run_advance: call ser_run_init first"); return SER_E_STATE; }
+  if (n_calls <= 0) return SER_OK;
+  if (set_device(run)) return SER_E_CUDA;
+  KParams kp = run->kp;
+  kp.n_calls = n_calls; kp.sampling = sampling;
+  mark_launch(run);
+  ser_sweep_kernel<<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  return SER_OK;
+}
+
+extern "C" int ser_run_sync(ser_run *run)
+{
+  if (!run) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  return SER_OK;
+}
+
+extern "C" int ser_run_elapsed_ms(ser_run *run, double *ms, int32_t reset)
+{
+  if (!run || !ms) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  if (run->timing_open) {
+    CUDA_TRY(cudaEventRecord(run->ev_stop, run->stream));
+    CUDA_TRY(cudaEventSynchronize(run->ev_stop));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, run->ev_start, run->ev_stop));
+    run->elapsed_ms += t;
+    run->timing_open = 0;
+  }
+  *ms = run->elapsed_ms;
+  if (reset) run->elapsed_ms = 0.0;
+  return SER_OK;
+}
+
+extern "C" int ser_run_kernel_launches(const ser_run *run, int64_t *n)
+{
+  if (!run || !n) return SER_E_ARG;
+  *n = run->launches;
+  return SER_OK;
+}
+
+static int chain_ok(ser_run *run, int chain)
+{
+  if (!run) { ser_set_error("null run"); return 0; }
+  if (chain < 0 || chain >= run->cfg.n_chains) { ser_set_error("chain %d out of range [0,%d)", chain, run->cfg.n_chains); return 0; }
+  return 1;
+}
+
+extern "C" int ser_run_get_state(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32_t *pi, int32_t *rpi, int32_t *t0,
+                                 int32_t *f0, int32_t *t1, int32_t *f1, int32_t tot[4], double cdl[3], int64_t *tape_slots)
+{
+  if (!chain_ok(run, chain)) return SER_E_ARG;
+  if (!run->initialized) { ser_set_error("ser_run_get_state: run not initialised"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  const int N = run->N, M = run->M;
+  int *d = run->d_scratch_i;
+  int *d_a = d, *d_b = d + M, *d_pi = d + 2 * M, *d_rpi = d + 2 * M + N, *d_cnt = d + 2 * M + 2 * N;
+  mark_launch(run);
+  ser_export_kernel<<<1, run->C, run->smem_sweep, run->stream>>>(run->kp, chain, d_a, d_b, d_pi, d_rpi, d_cnt);
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> h(2 * N + 6 * M);
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  if (a) memcpy(a, h.data(), M * 4);
+  if (b) memcpy(b, h.data() + M, M * 4);
+  if (pi) memcpy(pi, h.data() + 2 * M, N * 4);
+  if (rpi) memcpy(rpi, h.data() + 2 * M + N, N * 4);
+  const int *cnt = h.data() + 2 * M + 2 * N;
+  if (t0) memcpy(t0, cnt, M * 4);
+  if (f0) memcpy(f0, cnt + M, M * 4);
+  if (t1) memcpy(t1, cnt + 2 * M, M * 4);
+  if (f1) memcpy(f1, cnt + 3 * M, M * 4);
+  if (tot) { tot[0] = sc.t0a; tot[1] = sc.f0a; tot[2] = sc.t1a; tot[3] = sc.f1a; }
+  if (cdl) { cdl[0] = sc.c; cdl[1] = sc.d; cdl[2] = sc.loglik; }
+  if (tape_slots) *tape_slots = sc.cursor;
+  if (sc.flags & 1) { ser_set_error("chain %d: replay tape exhausted", chain); return SER_E_TAPE; }
+  return SER_OK;
+}
+
+extern "C" int ser_run_get_counters(ser_run *run, int32_t chain, int64_t out[8])
+{
+  if (!chain_ok(run, chain) || !out) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  for (int i = 0; i < 8; i++) out[i] = sc.counters[i];
+  return SER_OK;
+}
+
+extern "C" int ser_run_check(ser_run *run, int32_t *n_bad)
+{
+  if (!run || !n_bad) return SER_E_ARG;
+  if (!run->initialized) { ser_set_error("ser_run_check: run not initialised"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  CUDA_TRY(cudaMemsetAsync(run->d_bad, 0, sizeof(int), run->stream));
+  mark_launch(run);
+  ser_check_kernel<<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(run->kp, run->d_bad);
+  CUDA_TRY(cudaGetLastError());
+  int bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, run->d_bad, sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  *n_bad = bad;
+  if (bad) { ser_set_error("ser_run_check: %d inconsistent chain(s)", bad); return SER_E_CHECK; }
+  return SER_OK;
+}
+
+extern "C" int ser_run_chain_sums(ser_run *run, int32_t chain, double sums[3], int32_t *n_samples)
+{
+  if (!chain_ok(run, chain)) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  if (sums) { sums[0] = sc.sum_negll; sums[1] = sc.sum_ec; sums[2] = sc.sum_ed; }
+  if (n_samples) *n_samples = sc.n_samples;
+  return SER_OK;
+}
+
+extern "C" int ser_run_chain_stats(ser_run *run, double *e_negloglik, double *e_c, double *e_d, int32_t *n_samples)
+{
+  if (!run) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  const int nc = run->cfg.n_chains;
+  std::vector<ChainScalars> sc(nc);
+  CUDA_TRY(cudaMemcpyAsync(sc.data(), run->d_scal, (size_t)nc * sizeof(ChainScalars), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  for (int i = 0; i < nc; i++) {
+    const double n = sc[i].n_samples > 0 ? (double)sc[i].n_samples : 1.0;
+    if (e_negloglik) e_negloglik[i] = sc[i].sum_negll / n;
+    if (e_c) e_c[i] = sc[i].sum_ec / n;
+    if (e_d) e_d[i] = sc[i].sum_ed / n;
+  }
+  if (n_samples) *n_samples = sc[0].n_samples;
+  return SER_OK;
+}
+
+extern "C" int ser_run_chain_stats_device(ser_run *run, double *d_e_negloglik)
+{
+  if (!run || !d_e_negloglik) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  const int nc = run->cfg.n_chains;
+  mark_launch(run);
+  ser_stats_kernel<<<(nc + 255) / 256, 256, 0, run->stream>>>(run->d_scal, nc, d_e_negloglik);
+  CUDA_TRY(cudaGetLastError());
+  return SER_OK;
+}
+
+extern "C" int ser_run_fetch_samples(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32_t *pi, double *c, double *d,
+                                     double *loglik, int32_t *n)
+{
+  if (!chain_ok(run, chain)) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples;
+  if (n) *n = ns;
+  const int N = run->N, M = run->M;
+  const size_t row0 = (size_t)chain * run->cfg.max_samples;
+  if ((a || b || c || d || loglik) && run->cfg.store < SER_STORE_FULL) { ser_set_error("ser_run_fetch_samples: run was created without SER_STORE_FULL"); return SER_E_STATE; }
+  if (pi && run->cfg.store < SER_STORE_PI) { ser_set_error("ser_run_fetch_samples: run was created without a sample store"); return SER_E_STATE; }
+  std::vector<uint16_t> tmp;
+  auto fetch16 = [&](const uint16_t *src, int width, int32_t *dst) -> int {
+    tmp.resize((size_t)ns * width);
+    if (cudaMemcpyAsync(tmp.data(), src + row0 * width, tmp.size() * 2, cudaMemcpyDeviceToHost, run->stream) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(run->stream) != cudaSuccess) return 1;
+    for (size_t i = 0; i < tmp.size(); i++) dst[i] = tmp[i];
+    return 0;
+  };
+  if (ns > 0) {
+    if (a && fetch16(run->d_samp_a, M, a)) { ser_set_error("fetch a failed"); return SER_E_CUDA; }
+    if (b && fetch16(run->d_samp_b, M, b)) { ser_set_error("fetch b failed"); return SER_E_CUDA; }
+    if (pi && fetch16(run->d_samp_pi, N, pi)) { ser_set_error("fetch pi failed"); return SER_E_CUDA; }
+    if (c || d || loglik) {
+      std::vector<double> cdl((size_t)ns * 3);
+      CUDA_TRY(cudaMemcpyAsync(cdl.data(), run->d_samp_cdl + row0 * 3, cdl.size() * 8, cudaMemcpyDeviceToHost, run->stream));
+      CUDA_TRY(cudaStreamSynchronize(run->stream));
+      for (int s = 0; s < ns; s++) {
+        if (c) c[s] = cdl[3 * s];
+        if (d) d[s] = cdl[3 * s + 1];
+        if (loglik) loglik[s] = cdl[3 * s + 2];
+      }
+    }
+  }
+  return SER_OK;
+}
+
+extern "C" int ser_select_chains_device(const double *d_e, int32_t n, int32_t k, int32_t *d_chosen, double *d_info, int32_t device,
+                                        void *stream)
+{
+  if (!d_e || !d_chosen || !d_info || n < 1 || k < 1) { ser_set_error("ser_select_chains_device: bad argument"); return SER_E_ARG; }
+  CUDA_TRY(cudaSetDevice(device));
+  ser_select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_e, n, k, d_chosen, d_info);
+  CUDA_TRY(cudaGetLastError());
+  return SER_OK;
+}
+
+extern "C" int ser_run_po_counts_device(ser_run *run, const int32_t *d_chosen, int32_t k, int32_t *d_counts)
+{
+  if (!run || !d_chosen || !d_counts || k < 1) return SER_E_ARG;
+  if (run->cfg.store < SER_STORE_PI) { ser_set_error("ser_run_po_counts: run has no pi sample store"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples;
+  dim3 blk(32, 8), grd((run->N + 31) / 32, (run->N + 7) / 8, k);
+  mark_launch(run);
+  ser_po_kernel<<<grd, blk, 0, run->stream>>>(run->d_samp_pi, run->N, run->cfg.max_samples, ns, d_chosen, run->cfg.chain_offset,
+                                              run->cfg.n_chains, d_counts);
+  CUDA_TRY(cudaGetLastError());
+  return SER_OK;
+}
+
+extern "C" int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *counts)
+{
+  if (!run || !chosen || !counts || k < 1) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  int *d_ch = nullptr, *d_cnt = nullptr;
+  const size_t nn = (size_t)k * run->N * run->N;
+  CUDA_TRY(cudaMalloc(&d_ch, k * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&d_cnt, nn * sizeof(int)));
+  CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, nn * sizeof(int), run->stream));
+  int rc = ser_run_po_counts_device(run, d_ch, k, d_cnt);
+  if (rc == SER_OK) {
+    if (cudaMemcpyAsync(counts, d_cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, run->stream) != cudaSuccess ||
+        cudaStreamSynchronize(run->stream) != cudaSuccess) { ser_set_error("ser_run_po_counts: copy back failed"); rc = SER_E_CUDA; }
+  }
+  cudaFree(d_ch); cudaFree(d_cnt);
+  return rc;
+}
+
+extern "C" int ser_microbench(int32_t device, double out[3])
+{
+  if (!out) return SER_E_ARG;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 2, threads = 1024, iters = 20000;
+  void *buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  float ms = 0.f;
+  for (int rep = 0; rep < 2; rep++) { /* first pass warms up */
+    CUDA_TRY(cudaEventRecord(e0));
+    mb_fp64_kernel<<<blocks, threads>>>((double *)buf, iters);
+    CUDA_TRY(cudaEventRecord(e1)); CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  out[0] = (double)blocks * threads * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+  for (int rep = 0; rep < 2; rep++) {
+    CUDA_TRY(cudaEventRecord(e0));
+    mb_lds_kernel<<<blocks, threads>>>((unsigned *)buf, iters / 4);
+    CUDA_TRY(cudaEventRecord(e1)); CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  out[1] = (double)blocks * threads * (iters / 4) * 8.0 * 16.0 / (ms * 1e-3) / 1e9;
+  for (int rep = 0; rep < 2; rep++) {
+    CUDA_TRY(cudaEventRecord(e0));
+    mb_popc_kernel<<<blocks, threads>>>((unsigned *)buf, iters);
+    CUDA_TRY(cudaEventRecord(e1)); CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  out[2] = (double)blocks * threads * iters * 8.0 / (ms * 1e-3) / 1e9;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  return SER_OK;
+}

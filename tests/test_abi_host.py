@@ -1,0 +1,130 @@
+"""The C-ABI library: loads, exports every symbol include/seriation_b200.h declares, and its
+host-only entry points (readers, synthetic generator, host selection, PO finalisation) behave like
+the reference.  No compute calls: this file runs without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import NOW, ROOT, load_hex_dataset
+
+
+@pytest.fixture(scope="module")
+def S():
+    import seriation_b200 as S
+    if not os.path.exists(S.LIB_PATH):
+        S.build()
+    S.lib()
+    return S
+
+
+def test_every_declared_symbol_is_exported(S):
+    header = open(os.path.join(ROOT, "include", "seriation_b200.h")).read()
+    declared = set(re.findall(r"\b(ser_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ser_run_config"}
+    bound = {name for name, _, _ in S.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    L = S.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.ser_version()
+
+
+@pytest.mark.parametrize("name", NOW)
+def test_txt_reader_matches_oracle_parser(S, oracle_mod, tmp_path, name):
+    X, hard = load_hex_dataset(name)
+    p = tmp_path / (name + ".txt")
+    p.write_text(oracle_mod.format_dataset(X, hard))
+    ds = S.Dataset.read_txt(str(p))
+    X2, h2 = ds.arrays()
+    assert (ds.N, ds.M, ds.nh) == (X.shape[0], X.shape[1], int(hard.sum()))
+    assert np.array_equal(X, X2) and np.array_equal(hard, h2)
+    Xo, ho = oracle_mod.load_dataset(str(p))
+    assert np.array_equal(Xo, X2) and np.array_equal(ho, h2)
+
+
+def test_txt_reader_grammar_quirks(S, tmp_path):
+    # any separator, '*' anywhere after the M-th cell, short rows zero-filled (mcmc.c:366-400)
+    p = tmp_path / "q.txt"
+    p.write_text("3 4\n1,0;1 1 *\n0011 trailing\n1 1\n")
+    X, hard = S.Dataset.read_txt(str(p)).arrays()
+    assert X.tolist() == [[1, 0, 1, 1], [0, 0, 1, 1], [1, 1, 0, 0]]
+    assert hard.tolist() == [1, 0, 0]
+    # a '*' between cells is skipped like any separator and does not mark the site
+    p.write_text("1 3\n1 * 0 1\n")
+    X, hard = S.Dataset.read_txt(str(p)).arrays()
+    assert X.tolist() == [[1, 0, 1]] and hard.tolist() == [0]
+
+
+@pytest.mark.parametrize("text", ["", "x y\n", "0 4\n", "2 2\n1 0\n"])
+def test_txt_reader_errors(S, tmp_path, text):
+    p = tmp_path / "bad.txt"
+    p.write_text(text)
+    with pytest.raises(S.SeriationError) as e:
+        S.Dataset.read_txt(str(p))
+    assert "read error" in str(e.value)  # the reference's own messages (mcmc.c:349,355,371)
+
+
+def test_genus_and_sites_readers(S, tmp_path):
+    X = np.eye(3, 2, dtype=np.uint8)
+    ds = S.Dataset.from_bits(X, np.array([0, 1, 0], np.uint8))
+    g = tmp_path / "t.genus"
+    s = tmp_path / "t.sites"
+    g.write_text("Pseudocyon \nHemicyon \n")
+    s.write_text("Laugnac [2,21.38] *\nEsvres___Continental_Sands [3,19.5]\nWintershof_West [3,19] *\n")
+    ds.read_names(str(g), str(s))
+    assert ds.taxon_name(1) == "Hemicyon" and ds.site_name(1) == "Esvres___Continental_Sands"
+    assert ds.site_age(0) == (2, 21.38, True) and ds.site_age(1) == (3, 19.5, False)
+    g.write_text("only_one\n")
+    with pytest.raises(S.SeriationError):
+        ds.read_names(str(g), None)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Dataset"), reason="reference tree not present")
+@pytest.mark.parametrize("name", NOW)
+def test_readers_on_the_reference_files(S, name):
+    ds = S.Dataset.read_txt(f"/root/reference/Dataset/{name}.txt")
+    X, hard = load_hex_dataset(name)
+    X2, h2 = ds.arrays()
+    assert np.array_equal(X, X2) and np.array_equal(hard, h2)
+    ds.read_names(f"/root/reference/Dataset/{name}.genus", f"/root/reference/Dataset/{name}.sites")
+    stars = [ds.site_age(n)[2] for n in range(ds.N)]
+    assert np.array_equal(np.array(stars, np.uint8), hard)  # '*' in .sites == '*' in .txt
+
+
+def test_synthetic_generator(S):
+    ds = S.Dataset.synthetic(1024, 4096, 16)
+    X, hard = ds.arrays()
+    assert X.shape == (1024, 4096) and hard.sum() == 16
+    assert X.any(axis=0).all() and X.any(axis=1).all()
+    assert 0.03 < X.mean() < 0.12
+    X2, h2 = S.Dataset.synthetic(1024, 4096, 16).arrays()
+    assert np.array_equal(X, X2) and np.array_equal(hard, h2)  # deterministic
+    small = S.Dataset.synthetic(40, 25, 3, 7)
+    assert small.nh == 3
+
+
+def test_host_selection_matches_script_semantics(S, oracle_mod):
+    rng = np.random.default_rng(3)
+    for n, k in ((100, 8), (100, 2), (7, 3), (1, 1), (4096, 2)):
+        e = rng.normal(5000, 40, n)
+        got, mn, sd = S.select_chains(e, k)
+        assert list(got) == oracle_mod.choose_chains(e, k)
+        assert mn == e.min() and abs(sd - np.std(e)) <= 1e-12 * max(1.0, np.std(e))
+    assert list(S.select_chains(np.array([3.0]), 1)[0]) == []  # one chain: sigma = 0, strict -> empty
+
+
+def test_po_finalize_matches_script_semantics(S, oracle_mod):
+    rng = np.random.default_rng(5)
+    N, T = 17, 40
+    per_chain = []
+    for c in range(3):
+        pis = np.array([rng.permutation(N) for _ in range(T)])
+        per_chain.append(oracle_mod.pair_order_counts(pis))
+    counts = np.stack(per_chain).astype(np.int32)
+    for faithful in (True, False):
+        want = oracle_mod.pair_order_matrix(per_chain, 3, faithful)
+        got = S.po_finalize(counts, 3, faithful)
+        assert np.allclose(got, want, rtol=0, atol=1e-15)

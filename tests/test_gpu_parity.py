@@ -1,0 +1,228 @@
+"""Parity of the CUDA sweep (through the C ABI) with the oracle.  Run on the B200 box.
+
+Replay mode (north_star check 1+2): with the same draw tape, a, b, pi, every integer count and the
+tape cursor are bit-identical to the oracle after every thinned sample; c and d carry the tape's own
+libm bits; log-likelihood within 1e-9 relative.
+Free-running mode: the structured Philox stream is reproduced by the oracle (detmath mode), so the
+same comparison holds without a tape.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import EDGE_SHAPES, GOLDEN, NOW, load_hex_dataset, random_dataset
+
+pytestmark = pytest.mark.gpu
+LL_RTOL = 1e-9  # north_star: "per-state log-likelihood agrees within 1e-9 relative in fp64"
+
+
+@pytest.fixture(scope="module")
+def S():
+    import seriation_b200 as S
+    S.lib()
+    return S
+
+
+def _oracle_chain(O, X, hard, seed, burn, samp, philox=None, detmath=False):
+    o = O.Oracle(X, hard)
+    if philox is not None:
+        o.source_philox(*philox)
+    else:
+        o.source_mt(seed)
+    o.record(True).detmath(detmath)
+    o.randomize()
+    init = o.state()
+    res = o.run(burn, samp)
+    return o, init, res, o.state(), o.tape()
+
+
+def _cmp_state(got, want, what):
+    for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+        assert np.array_equal(got[k], getattr(want, k)), (what, k)
+    assert got["slots"] == want.slots, what
+    assert got["c"] == want.c and got["d"] == want.d, what
+    assert abs(got["loglik"] - want.loglik) <= LL_RTOL * abs(want.loglik), what
+
+
+def _cmp_samples(got, res, what):
+    for k in ("a", "b", "pi"):
+        assert np.array_equal(got[k], res[k]), (what, k)
+    assert np.array_equal(got["c"], res["c"]) and np.array_equal(got["d"], res["d"]), what
+    assert np.all(np.abs(got["loglik"] - res["loglik"]) <= LL_RTOL * np.abs(res["loglik"])), what
+
+
+def _replay_case(S, O, X, hard, seeds, burn, samp):
+    ds = S.Dataset.from_bits(X, hard)
+    chains = [_oracle_chain(O, X, hard, s, burn, samp) for s in seeds]
+    run = S.Run(ds, len(seeds), mode=S.MODE_REPLAY, store=S.STORE_FULL, max_samples=samp)
+    run.set_tapes([c[4] for c in chains]).init().sync()
+    for i, c in enumerate(chains):
+        _cmp_state(run.state(i), c[1], ("init", i))
+    run.advance(burn, False).advance(samp, True).sync()
+    assert run.check() == 0
+    stats = run.chain_stats()
+    for i, (o, init, res, final, tape) in enumerate(chains):
+        _cmp_state(run.state(i), final, ("final", i))
+        assert run.state(i)["slots"] == tape.size
+        _cmp_samples(run.fetch_samples(i), res, ("samples", i))
+        assert abs(stats["e_negloglik"][i] - res["sums"][0] / samp) <= LL_RTOL * abs(res["sums"][0] / samp)
+        assert abs(stats["e_c"][i] - res["sums"][1] / samp) <= 1e-12
+        assert abs(stats["e_d"][i] - res["sums"][2] / samp) <= 1e-12
+    run.close()
+
+
+@pytest.mark.parametrize("name,burn,samp", [("g10s10", 20, 20), ("g10s2", 4, 4), ("g5s5", 5, 5), ("g2s2", 4, 4)])
+def test_replay_bit_exact_now_subsets(S, oracle_mod, name, burn, samp):
+    X, hard = load_hex_dataset(name)
+    _replay_case(S, oracle_mod, X, hard, [11, 12, 13, 0], burn, samp)
+
+
+@pytest.mark.parametrize("shape", EDGE_SHAPES)
+def test_replay_bit_exact_edge_shapes(S, oracle_mod, shape):
+    rng = np.random.default_rng(hash(shape) & 0xffff)
+    X, hard = random_dataset(rng, *shape)
+    _replay_case(S, oracle_mod, X, hard, [1, 2, 3], 10, 10)
+
+
+@pytest.mark.parametrize("name", NOW)
+def test_replay_of_unmodified_reference_traces(S, name):
+    """Golden fixtures recorded from the UNMODIFIED reference binary (tools/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    X, hard = load_hex_dataset(name)
+    burn, samp = int(g["meta"][0]), int(g["meta"][1])
+    run = S.Run(S.Dataset.from_bits(X, hard), 1, mode=S.MODE_REPLAY, store=S.STORE_FULL, max_samples=burn + samp)
+    run.set_tapes([g["tape"]]).init()
+    for r in range(len(g["kind"])):
+        if r:
+            run.advance(1, True)
+        st = run.state(0)
+        for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+            assert np.array_equal(st[k], g[k][r].astype(np.int32)), (k, r)
+        assert st["slots"] == int(g["slots"][r])
+        assert st["c"] == g["cdl"][r][0] and st["d"] == g["cdl"][r][1]
+        assert abs(st["loglik"] - g["cdl"][r][2]) <= LL_RTOL * abs(g["cdl"][r][2])
+    assert run.state(0)["slots"] == g["tape"].size
+    run.close()
+
+
+def test_replay_100_chains_g10s2(S, oracle_mod):
+    """BASELINE.json config 2 at reduced length: 100 chains of g10s2, seeds 0..99."""
+    X, hard = load_hex_dataset("g10s2")
+    _replay_case(S, oracle_mod, X, hard, list(range(100)), 1, 2)
+
+
+@pytest.mark.parametrize("name,burn,samp", [("g10s10", 10, 10), ("g2s2", 2, 3)])
+def test_free_running_equals_oracle_philox(S, oracle_mod, name, burn, samp):
+    X, hard = load_hex_dataset(name)
+    seed, offset, n = 20060206, 40, 6
+    run = S.Run(S.Dataset.from_bits(X, hard), n, mode=S.MODE_FREE, seed=seed, chain_offset=offset,
+                store=S.STORE_FULL, max_samples=samp)
+    run.init().advance(burn, False).advance(samp, True).sync()
+    assert run.check() == 0
+    for i in range(n):
+        o, init, res, final, tape = _oracle_chain(oracle_mod, X, hard, 0, burn, samp, philox=(seed, offset + i), detmath=True)
+        got = run.state(i)
+        for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+            assert np.array_equal(got[k], getattr(final, k)), (i, k)
+        assert got["c"] == final.c and got["d"] == final.d
+        _cmp_samples(run.fetch_samples(i), res, ("free", i))
+    run.close()
+
+
+def test_sharding_is_invisible(S):
+    """Chains keyed by GLOBAL id: 8 chains in one run == two runs of 4 with chain_offset."""
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    whole = S.Run(ds, 8, seed=5, store=S.STORE_PI, max_samples=3).init().advance(3, False).advance(3, True).sync()
+    parts = [S.Run(ds, 4, seed=5, chain_offset=o, store=S.STORE_PI, max_samples=3).init().advance(3, False).advance(3, True).sync()
+             for o in (0, 4)]
+    for i in range(8):
+        a, b = whole.state(i), parts[i // 4].state(i % 4)
+        for k in ("a", "b", "pi", "tot"):
+            assert np.array_equal(a[k], b[k])
+        assert a["loglik"] == b["loglik"]
+
+
+def test_selection_and_pair_order_on_device(S, oracle_mod):
+    X, hard = load_hex_dataset("g10s10")
+    n, samp, k = 64, 12, 4
+    run = S.Run(S.Dataset.from_bits(X, hard), n, seed=7, store=S.STORE_PI, max_samples=samp)
+    run.init().advance(20, False).advance(samp, True).sync()
+    e = run.chain_stats()["e_negloglik"]
+    import torch
+    d_e = torch.empty(n, dtype=torch.float64, device="cuda")
+    d_ch = torch.empty(k, dtype=torch.int32, device="cuda")
+    d_info = torch.empty(3, dtype=torch.float64, device="cuda")
+    run.chain_stats_device(d_e.data_ptr())
+    run.sync()
+    assert np.array_equal(d_e.cpu().numpy(), e)
+    S.select_chains_device(d_e.data_ptr(), n, k, d_ch.data_ptr(), d_info.data_ptr())
+    torch.cuda.synchronize()
+    want = oracle_mod.choose_chains(e, k)
+    got = [int(v) for v in d_ch.cpu().numpy() if v >= 0]
+    assert got == want and int(d_info[0].item()) == len(want)
+    assert d_info[1].item() == e.min() and abs(d_info[2].item() - np.std(e)) < 1e-9
+    assert list(S.select_chains(e, k)[0]) == want
+    counts = run.po_counts(want)
+    for c, ch in enumerate(want):
+        pis = run.fetch_samples(ch, full=False)["pi"]
+        assert np.array_equal(counts[c], oracle_mod.pair_order_counts(pis))
+    po = S.po_finalize(counts, k)
+    ref = oracle_mod.pair_order_matrix([oracle_mod.pair_order_counts(run.fetch_samples(ch, full=False)["pi"]) for ch in want], k)
+    assert np.max(np.abs(po - ref)) < 1e-12
+
+
+def test_invariants_at_scale_g2s2(S):
+    """mcmc_consistent on every chain of a 2048-chain g2s2 batch (size-independent property)."""
+    X, hard = load_hex_dataset("g2s2")
+    run = S.Run(S.Dataset.from_bits(X, hard), 2048, seed=1).init().advance(3, False).advance(2, True).sync()
+    assert run.check() == 0
+    st = run.chain_stats()
+    assert st["n_samples"] == 2 and np.all(st["e_negloglik"] > 0) and np.all((st["e_c"] > .001) & (st["e_c"] < .1))
+
+
+def test_error_paths(S):
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    with pytest.raises(S.SeriationError):
+        S.Run(ds, 2).advance(1, False)                      # advance before init
+    with pytest.raises(S.SeriationError):
+        S.Run(ds, 2, mode=S.MODE_REPLAY).init()             # replay without tapes
+    short = S.Run(ds, 1, mode=S.MODE_REPLAY).set_tapes([np.full(300, 0.5)]).init().advance(1, False).sync()
+    with pytest.raises(S.SeriationError) as e:
+        short.state(0)                                      # tape exhausted mid-run
+    assert "tape" in str(e.value)
+    with pytest.raises(S.SeriationError):
+        S.Run(S.Dataset.from_bits(np.ones((4, 2000), np.uint8)), 1)  # unsupported shape says so
+
+
+def test_reference_file_writers(S, oracle_mod, tmp_path):
+    """Chains/chain_XX/ files: same layout and numbers as the reference's writers (mcmc.c:69-92,
+    :60-67, :261-294), checked by parsing them the way script.py does."""
+    X, hard = load_hex_dataset("g10s10")
+    o, init, res, final, tape = _oracle_chain(oracle_mod, X, hard, 21, 3, 5)
+    run = S.Run(S.Dataset.from_bits(X, hard), 1, mode=S.MODE_REPLAY, store=S.STORE_FULL, max_samples=5)
+    run.set_tapes([tape]).init().advance(3, False).advance(5, True).sync()
+    run.write_chain_files(0, str(tmp_path))
+    lines = (tmp_path / "chain_data.csv").read_text().split("\n")
+    assert len(lines) == 6 and lines[-1] == ""
+    N, M = X.shape
+    for s, line in enumerate(lines[:5]):
+        f = line.split(",")
+        assert [int(v) for v in f[0].split()] == res["a"][s].tolist()
+        assert [int(v) for v in f[1].split()] == res["b"][s].tolist()
+        assert [int(v.strip()) for v in f[2].split(" ")[:N]] == res["pi"][s].tolist()  # script.py:144-145
+        assert f[3].split(" ")[0] == "%.14f" % np.exp(res["c"][s]) and len(f[3].split()) == M
+        assert f[4].split(" ")[0] == "%.14f" % np.exp(res["d"][s])
+        assert abs(float(f[5]) - res["loglik"][s]) <= LL_RTOL * abs(res["loglik"][s])
+    exp = (tmp_path / "exp_data.csv").read_text().split("\n")
+    assert exp[0] == "exp_loglik,exp_c,exp_d" and len(exp) == 2
+    vals = [float(v) for v in exp[1].split(",")]
+    assert abs(vals[0] - res["sums"][0] / 1000) < 1e-9 and abs(vals[1] - res["sums"][1] / 1000) < 1e-13
+    taxa = (tmp_path / "taxa.csv").read_text().split("\n")
+    assert taxa[0] == "a,b,c,d" and taxa[1].startswith("%d,%d," % (final.a[0], final.b[0]))
+    sites = (tmp_path / "sites.csv").read_text().split("\n")
+    assert sites[0] == "sites" and [int(v) for v in sites[1:N + 1]] == final.pi.tolist()
+    hs = (tmp_path / "hard_sites.csv").read_text().split("\n")
+    assert hs[0] == "i,pi_i" and len(hs) == int(hard.sum()) + 2

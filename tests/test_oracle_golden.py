@@ -1,0 +1,88 @@
+"""The oracle restatement against traces of the UNMODIFIED reference (committed fixtures made by
+tools/make_golden.py from oracle/_ref/ref_mcmc).  Bit-exact on every integer and on c, d, loglik."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, NOW, load_hex_dataset
+
+
+def _bits(x):
+    return struct.pack("d", float(x))
+
+
+def _cmp(state, g, r):
+    for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+        assert np.array_equal(getattr(state, k), g[k][r].astype(np.int32)), (k, r)
+    assert state.slots == int(g["slots"][r]), r
+    for got, want in zip((state.c, state.d, state.loglik), g["cdl"][r]):
+        assert _bits(got) == _bits(want), r
+
+
+@pytest.mark.parametrize("name", NOW)
+def test_restatement_matches_reference_trace(oracle_mod, name):
+    g = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    X, hard = load_hex_dataset(name)
+    o = oracle_mod.Oracle(X, hard).source_tape(g["tape"])
+    o.randomize()
+    _cmp(o.state(), g, 0)
+    for r in range(1, len(g["kind"])):
+        o.sample()  # (the reference's return value accumulates in statics, mcmc.c:220 -- not compared)
+        _cmp(o.state(), g, r)
+    assert o.slots == g["tape"].size
+    assert o.tape_mismatches == 0 and o.consistent() == 0
+
+
+def test_restatement_matches_reference_per_subsampler(oracle_mod):
+    g = np.load(os.path.join(GOLDEN, "ref_g10s10_step.npz"))
+    X, hard = load_hex_dataset("g10s10")
+    o = oracle_mod.Oracle(X, hard).source_tape(g["tape"])
+    o.randomize()
+    _cmp(o.state(), g, 0)
+    step = {10: o.samplec, 11: o.sampled, 12: o.sampleab, 13: lambda: o.samplepi2(1), 14: o.samplepi1,
+            15: lambda: o.samplepi2(0), 16: o.samplepi3}
+    for r in range(1, len(g["kind"])):
+        k = int(g["kind"][r])
+        if k == 1:
+            continue
+        assert step[k]() == int(g["ret"][r]), r
+        _cmp(o.state(), g, r)
+
+
+def test_restatement_matches_reference_on_philox_stream(oracle_mod):
+    """The reference driven by the structured Philox stream through the shim == the restatement
+    generating the same stream itself (no tape involved)."""
+    g = np.load(os.path.join(GOLDEN, "ref_g10s10_philox.npz"))
+    X, hard = load_hex_dataset("g10s10")
+    o = oracle_mod.Oracle(X, hard).source_philox(20060206, 17).record(True)
+    o.randomize()
+    _cmp(o.state(), g, 0)
+    for r in range(1, len(g["kind"])):
+        o.sample()
+        _cmp(o.state(), g, r)
+    assert np.array_equal(o.tape(), g["tape"])
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    src = r'''
+    #include <stdio.h>
+    #include "%s/seriation-in-paleontological-data-using-mcmc_b200/csrc/ser_detmath.h"
+    int main(void){ uint32_t o[4];
+      ser_philox4x32_10(0,0,0,0,0,0,o); printf("%%08x %%08x %%08x %%08x\n",o[0],o[1],o[2],o[3]);
+      ser_philox4x32_10(0xffffffffu,0xffffffffu,0xffffffffu,0xffffffffu,0xffffffffu,0xffffffffu,o); printf("%%08x %%08x %%08x %%08x\n",o[0],o[1],o[2],o[3]);
+      ser_philox4x32_10(0x243f6a88u,0x85a308d3u,0x13198a2eu,0x03707344u,0xa4093822u,0x299f31d0u,o); printf("%%08x %%08x %%08x %%08x\n",o[0],o[1],o[2],o[3]);
+      return 0; }''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        with open(td + "/k.c", "w") as f:
+            f.write(src)
+        subprocess.run(["gcc", "-std=gnu99", "-O1", "-o", td + "/k", td + "/k.c", "-lm"], check=True)
+        out = subprocess.run([td + "/k"], check=True, capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "6627e8d5 e169c58d bc57ac4c 9b00dbd8"
+    assert out[1] == "408f276d 41c83b0e a20bc7c6 6d5451fd"
+    assert out[2] == "d16cfe09 94fdcceb 5001e420 24126ea1"
