@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
     for (int s = 0; s < p.sweeps_per_call; s++) {
       /* ================= stage this sweep's draws ================= */
+      __syncthreads(); /* every thread is done reading the previous sweep's staged draws */
       double ua = 0.0, ub = 0.0;
       if (p.mode == SER_MODE_REPLAY) {
         const long long need = sc.cursor + 6 + 2 * (long long)M;

@@ -16,18 +16,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-def load_hex_dataset(name):
-    """tests/golden/datasets/<name>.hex -> (X uint8 [N][M], hard uint8 [N])"""
-    with open(os.path.join(GOLDEN, "datasets", name + ".hex")) as f:
-        n, m = (int(t) for t in f.readline().split())
-        X = np.zeros((n, m), np.uint8)
-        hard = np.zeros(n, np.uint8)
-        for i in range(n):
-            parts = f.readline().split()
-            bits = np.unpackbits(np.frombuffer(bytes.fromhex(parts[0]), np.uint8), bitorder="little")
-            X[i] = bits[:m]
-            hard[i] = len(parts) > 1 and parts[1] == "*"
-    return X, hard
+from tools.datasets import load_hex_dataset  # noqa: E402,F401
 
 
 @pytest.fixture(scope="session")
