@@ -211,12 +211,43 @@ SER_HD int ser_select_nonhard(const SerHard &h, int r)
 }
 
 /* ------------------------------------------------------------------ likelihood weights */
+#define SER_LOGEPSILON (-32.236191301916641) /* log(1e-14), mcmc.h:26 */
+
 struct SerWeights {
   double c, cc, d, dd; /* log P(false 1), log(1-e^c), log P(false 0), log(1-e^d) */
   double w1, w0;       /* log-odds of an in-range cell: one -> dd - c (>0), zero -> d - cc (<0) */
-  double r1, r0;       /* exp(-w1), exp(-w0): weight ratio when the boundary passes a one / zero */
-  double eps;          /* exp(LOGEPSILON) as the host libm evaluates it (mcmc.h:26, mcmc.c:734) */
+  double g, A;         /* g = -w0: log-weight gained per zero passed; A = w0 - w1: change per one passed */
+  double inv_g;
+  double eps;          /* exp(LOGEPSILON) as the host libm evaluates it (mcmc.c:734) */
+  const double *H;     /* H[m] = sum_{u<m} exp(-u g), m = 0..hmax: geometric partial sums (per sweep) */
+  int hmax;
 };
+
+/* number of entries (-1) the per-sweep table H needs for a given g and N */
+SER_HD int ser_hmax(double g, int N)
+{
+  int h = (int)(-SER_LOGEPSILON / g) + 3;
+  return h > N + 1 ? N + 1 : h;
+}
+/* H[m] = (1 - q^m) / (1 - q), q = exp(-g); evaluated per entry so threads can fill it in parallel */
+SER_HD double ser_h_entry(double g, int m) { return (1.0 - exp(-g * (double)m)) / (1.0 - exp(-g)); }
+
+/* derived quantities of (c, cc, d, dd); H is filled separately (ser_h_entry) */
+SER_HD void ser_set_weights(struct SerWeights *wt, double c, double cc, double d, double dd);
+
+SER_HD void ser_set_weights(struct SerWeights *wt, double c, double cc, double d, double dd)
+{
+  wt->c = c; wt->cc = cc; wt->d = d; wt->dd = dd;
+  wt->w1 = dd - c; wt->w0 = d - cc;
+  wt->g = -wt->w0; wt->A = wt->w0 - wt->w1;
+  wt->inv_g = 1.0 / wt->g;
+}
+
+/* exact int -> double on the fp64 add pipe (no I2F): 2^52 + 2^31 + k, minus the bias */
+SER_HD double ser_i2d(int k)
+{
+  return SER_SUB(ser_u2d(0x4330000000000000ull | (uint64_t)((uint32_t)k ^ 0x80000000u)), 4503601774854144.0);
+}
 
 /* exp(x) for x <= ~0 (weights relative to the maximum); 0 below -708.  FMA Horner, ~1 ulp. */
 SER_HD double ser_exp_weight(double x)
@@ -244,95 +275,135 @@ SER_HD double ser_exp_weight(double x)
   return ser_u2d(ser_d2u(p) + ((uint64_t)k << 52));
 }
 
-/* log-weight of candidate with `dn1` more ones / `dn0` more zeros below it than the reference point */
-SER_HD double ser_logw(const SerWeights &w, int dn1, int dn0)
+/* log-weight (up to a constant) of the candidate that has `dn1` more ones and `di` more cells
+ * below it than the reference point: -(dn1 w1 + (di - dn1) w0) = dn1 (w0 - w1) + di (-w0) */
+SER_HD double ser_logw(const SerWeights &w, int dn1, int di, double c0)
 {
-  return -ser_fma((double)dn1, w.w1, SER_MUL((double)dn0, w.w0));
+  return ser_fma(ser_i2d(dn1), w.A, ser_fma(ser_i2d(di), w.g, c0));
+}
+
+/*
+ * One run of candidates inside which only zeros are passed: n candidates whose log-weights rise
+ * by g per step and end at le (<= ~0, relative to the maximum).  The reference floors every
+ * weight at exp(LOGEPSILON) (mcmc.c:734); m = the candidates that stay above the floor (they
+ * are the LAST m of the run).  Returns the run's total weight.
+ */
+SER_HD double ser_run_sum(const SerWeights &w, int n, double le, int *m_out, double *ye_out)
+{
+  if (le < SER_LOGEPSILON) { *m_out = 0; *ye_out = 0.0; return SER_MUL(ser_i2d(n), w.eps); }
+  int m = (int)SER_MUL(SER_SUB(le, SER_LOGEPSILON), w.inv_g) + 1;
+  if (m > n) m = n;
+  if (m > w.hmax) m = w.hmax;
+  const double ye = ser_exp_weight(le);
+  *m_out = m; *ye_out = ye;
+  return ser_fma(ye, w.H[m], SER_MUL(ser_i2d(n - m), w.eps));
 }
 
 /*
  * Gibbs draw of one boundary (the a-step, or the b-step on the reversed column).
- * Logical string s (REV: s[k] = v[N-1-k]); candidates 0..bound; `cur` is the
- * current value; weight(i) ~ exp(-sum_{p<i} w(s_p)), floored at eps relative to
- * the maximum, summed in candidate order; pick = first i with cumsum >= U*total.
- * ck[] is caller-provided scratch of (bound>>5)+1 doubles.
+ * Logical string s (REV: s[k] = v[N-1-k]); candidates 0..bound; `cur` is the current value;
+ * weight(i) ~ exp(-sum_{p<i} w(s_p)) floored at eps relative to the maximum; the pick is the
+ * first candidate whose cumulative weight reaches U * total (mcmc_auxa + mcmc_logtop +
+ * mcmc_randompick, mcmc.c:828-915).
+ *
+ * Sparse formulation: between two ones the weights form a geometric sequence, so every maximal
+ * run of candidates that only passes zeros (cut at 32-bit word boundaries) is summed in closed
+ * form through the table H -- O(#ones + #words) work per column instead of O(#sites).
+ * ck[] is caller-provided scratch of (bound>>5)+1 doubles (cumulative weight per word).
  */
 template <bool REV>
 SER_HD int ser_gibbs_boundary(const uint32_t *col, int C, int W, int N, int cur, int bound, double U,
                               const SerWeights &wt, double *ck)
 {
   const int nw = (bound >> 5) + 1;
-  /* ones / zeros below the current boundary: the reference point of the log-weights */
+  /* ones below the current boundary: the reference point of the log-weights */
   int o_cur;
   if (!REV) o_cur = ser_col_popc(col, C, 0, cur);
   else o_cur = ser_col_popc(col, C, N - cur, N);
-  const int z_cur = cur - o_cur;
 
-  /* pass A: maximum log-weight; local maxima sit just below a one, or at `bound` */
+  /* pass A: maximum log-weight; local maxima sit on the candidate just below a one, or at `bound` */
   double lmax;
   {
-    int obase = 0;
+    int o = 0;
     lmax = -1.0e300;
     for (int j = 0; j < nw; j++) {
       uint32_t word = ser_logical_word<REV>(col, C, W, N, j) & ser_range_mask(j, 0, bound);
-      int o = obase;
-      obase += SER_POPC(word);
       while (word) {
         const int t = SER_FFS(word) - 1;
         word &= word - 1u;
-        const int i = 32 * j + t;
-        lmax = ser_fmax(lmax, ser_logw(wt, o - o_cur, (i - o) - z_cur));
+        lmax = ser_fmax(lmax, ser_logw(wt, o - o_cur, 32 * j + t - cur, 0.0));
         o++;
       }
     }
-    lmax = ser_fmax(lmax, ser_logw(wt, obase - o_cur, (bound - obase) - z_cur));
+    lmax = ser_fmax(lmax, ser_logw(wt, o - o_cur, bound - cur, 0.0));
   }
+  const double c0 = -lmax;
 
-  /* pass B: floored weights summed in candidate order, one checkpoint per word */
+  /* pass B: total weight, one cumulative checkpoint per word */
   double S = 0.0;
   {
-    int obase = 0;
+    int o = 0;
     for (int j = 0; j < nw; j++) {
-      const uint32_t word = ser_logical_word<REV>(col, C, W, N, j);
-      double y = ser_exp_weight(SER_SUB(ser_logw(wt, obase - o_cur, (32 * j - obase) - z_cur), lmax));
-      const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
-      if (cnt == 32) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int k = 0; k < 32; k++) {
-          S = SER_ADD(S, ser_fmax(y, wt.eps));
-          y = SER_MUL(y, ((word >> k) & 1u) ? wt.r1 : wt.r0);
-        }
-      } else {
-        for (int k = 0; k < cnt; k++) {
-          S = SER_ADD(S, ser_fmax(y, wt.eps));
-          y = SER_MUL(y, ((word >> k) & 1u) ? wt.r1 : wt.r0);
-        }
+      const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32; /* candidates in this word */
+      uint32_t cuts = ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1);
+      int ts = 0; /* first candidate (local index) of the current run */
+      for (;;) {
+        const int te = cuts ? SER_FFS(cuts) - 1 : cnt - 1; /* run ends on the candidate below the next one */
+        int m; double ye;
+        S = SER_ADD(S, ser_run_sum(wt, te - ts + 1, ser_logw(wt, o - o_cur, 32 * j + te - cur, c0), &m, &ye));
+        if (!cuts) break;
+        cuts &= cuts - 1u;
+        o++;
+        ts = te + 1;
       }
       ck[j] = S;
-      obase += SER_POPC(word);
+      /* the bit of the word's last candidate is passed when entering the next word */
+      if (cnt == 32) o += (int)((ser_logical_word<REV>(col, C, W, N, j) >> 31) & 1u);
     }
   }
 
-  /* pass C: inverse CDF (mcmc_randompick): first candidate whose cumulative weight >= U*S */
+  /* pass C: inverse CDF -- word, then run, then candidate inside the run */
   const double target = SER_MUL(U, S);
   int j = 0;
   while (j < nw - 1 && ck[j] < target) j++;
   double s = j ? ck[j - 1] : 0.0;
-  int obase;
-  if (!REV) obase = ser_col_popc(col, C, 0, 32 * j);
-  else obase = ser_col_popc(col, C, N - 32 * j, N);
-  const uint32_t word = ser_logical_word<REV>(col, C, W, N, j);
-  double y = ser_exp_weight(SER_SUB(ser_logw(wt, obase - o_cur, (32 * j - obase) - z_cur), lmax));
+  int o;
+  if (!REV) o = ser_col_popc(col, C, 0, 32 * j);
+  else o = ser_col_popc(col, C, N - 32 * j, N);
   const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
-  int k = 0;
-  for (; k < cnt - 1; k++) {
-    s = SER_ADD(s, ser_fmax(y, wt.eps));
-    if (s >= target) break;
-    y = SER_MUL(y, ((word >> k) & 1u) ? wt.r1 : wt.r0);
+  uint32_t cuts = ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1);
+  int ts = 0;
+  for (;;) {
+    const int te = cuts ? SER_FFS(cuts) - 1 : cnt - 1;
+    const int n = te - ts + 1;
+    int m; double ye;
+    const double snext = SER_ADD(s, ser_run_sum(wt, n, ser_logw(wt, o - o_cur, 32 * j + te - cur, c0), &m, &ye));
+    if (snext >= target || !cuts) {
+      /* inside this run: nf floored candidates of weight eps each, then m geometric ones */
+      const int nf = n - m;
+      const double sf = ser_fma(ser_i2d(nf), wt.eps, s);
+      int t;
+      if (nf > 0 && (sf >= target || m == 0)) {
+        const double td = SER_DIV(SER_SUB(target, s), wt.eps); /* ~ whole eps steps below the target */
+        t = !(td > 0.0) ? 0 : (td >= (double)(nf - 1) ? nf - 1 : (int)td);
+        while (t > 0 && ser_fma(ser_i2d(t), wt.eps, s) >= target) t--;
+        while (t < nf - 1 && ser_fma(ser_i2d(t + 1), wt.eps, s) < target) t++;
+      } else {
+        /* cumulative weight through geometric candidate k (k = 0..m-1): sf + ye (H[m] - H[m-1-k]) */
+        int lo = 0, hi = m - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (ser_fma(ye, SER_SUB(wt.H[m], wt.H[m - 1 - mid]), sf) >= target) hi = mid; else lo = mid + 1;
+        }
+        t = nf + lo;
+      }
+      return 32 * j + ts + t;
+    }
+    s = snext;
+    cuts &= cuts - 1u;
+    o++;
+    ts = te + 1;
   }
-  return 32 * j + k;
 }
 
 /* ------------------------------------------------------------------ pi proposals */

@@ -69,6 +69,7 @@ struct Smem {
   double *draws_pi; /* SER_PI_DRAWS */
   double *draws_cd; /* 8 */
   double *terms;    /* C */
+  double *H;        /* N + 2: geometric partial sums of the current sweep (ser_h_entry) */
   uint32_t *V;      /* W*C */
   int *red;         /* 2 * SER_MAX_WARPS * 4 */
   int *hcum;        /* W+1 */
@@ -80,11 +81,13 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
+  size_t o_H = take(sizeof(double) * (N + 2));
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_h = take(sizeof(int) * (W + 1));
   size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
   if (s) {
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
+    s->H = (double *)(base + o_H);
     s->V = (uint32_t *)(base + o_v); s->red = (int *)(base + o_r); s->hcum = (int *)(base + o_h);
     s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q); s->perm16 = (uint16_t *)(base + o_m);
   }
@@ -147,9 +150,7 @@ __device__ void init_ab(const KParams &p, const uint32_t *col, int *a, int *b)
 
 __device__ __forceinline__ void set_weights(SerWeights &wt, double c, double cc, double d, double dd)
 {
-  wt.c = c; wt.cc = cc; wt.d = d; wt.dd = dd;
-  wt.w1 = dd - c; wt.w0 = d - cc;
-  wt.r1 = exp(-wt.w1); wt.r0 = exp(-wt.w0);
+  ser_set_weights(&wt, c, cc, d, dd);
 }
 
 /* totals and log-likelihood from the block-reduced alive-ones / lifespan sums (mcmc.c:977-986) */
@@ -328,6 +329,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
 
   SerWeights wt;
   wt.eps = p.eps;
+  wt.H = sm.H;
+  wt.hmax = 0;
   set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
   SerHard hd;
   hd.hcol = sm.V + M; hd.hcum = sm.hcum; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh;
@@ -386,6 +389,10 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
       }
       set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
       sc.counters[0]++; sc.counters[1]++;
+      /* geometric partial sums for this sweep's g (shared by all taxa: c, d are scalar) */
+      wt.hmax = ser_hmax(wt.g, N);
+      for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
+      __syncthreads();
 
       /* ================= a/b Gibbs (mcmc_sampleab, mcmc.c:918-996) ================= */
       int t1 = 0, len = 0, changed = 0;

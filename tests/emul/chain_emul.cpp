@@ -42,10 +42,13 @@ struct Chain {
     if (cur >= tape_len) { fprintf(stderr, "emul: tape exhausted\n"); exit(3); }
     return tape[cur++];
   }
+  std::vector<double> H;
   void set_cd(double c, double cc, double d, double dd) {
-    wt.c = c; wt.cc = cc; wt.d = d; wt.dd = dd;
-    wt.w1 = dd - c; wt.w0 = d - cc;
-    wt.r1 = std::exp(-wt.w1); wt.r0 = std::exp(-wt.w0);
+    ser_set_weights(&wt, c, cc, d, dd);
+    wt.hmax = ser_hmax(wt.g, N);
+    H.resize(wt.hmax + 1);
+    for (int m = 0; m <= wt.hmax; m++) H[m] = ser_h_entry(wt.g, m);
+    wt.H = H.data();
   }
   void rebuild_hcum() {
     hcum[0] = 0;
