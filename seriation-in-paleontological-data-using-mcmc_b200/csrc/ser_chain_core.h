@@ -4,9 +4,11 @@
  * One chain = one CTA; one taxon = one thread.  Each thread owns one *column*
  * of the chain's bit matrix V: V[w][col] (word-major, stride C words) holds the
  * taxon's occurrences in POSITION order, bit p = X[rpi[p]][m].  Column M is
- * the hard-site mask in position order.  Everything the reference evaluates
- * cell by cell (mcmc.c:828-898, :1127-1682) becomes range popcounts on that
- * column.  The functions below are the per-thread pieces; the block-level
+ * the hard-site mask in position order.  Next to V lives the prefix table
+ * pre[w][col] = number of ones in words < w (w = 0..W), so every range
+ * popcount is two table reads + two POPCs, loop-free.  Everything the
+ * reference evaluates cell by cell (mcmc.c:828-898, :1127-1682) becomes range
+ * popcounts on that column.  The functions below are the per-thread pieces; the block-level
  * choreography (reductions, draws, accept) lives in ser_kernels.cu and, for
  * CPU-side testing of the same logic, in tests/emul/chain_emul.cpp.
  *
@@ -57,6 +59,9 @@ SER_HD double ser_fma(double a, double b, double c) { return fma(a, b, c); }
 SER_HD double ser_fmax(double a, double b) { return a > b ? a : b; }
 #endif
 
+/* bits [0,n), n in [0,31] -- the hot-path variant (n = p & 31) */
+SER_HD uint32_t ser_mask_lo(int n) { return (1u << n) - 1u; }
+
 /* bits [0,n), n in [0,32] */
 SER_HD uint32_t ser_mask_lt(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
 
@@ -97,13 +102,33 @@ SER_HD uint32_t ser_col_extract32(const uint32_t *col, int C, int W, int p)
 
 SER_HD int ser_col_bit(const uint32_t *col, int C, int p) { return (col[(p >> 5) * C] >> (p & 31)) & 1u; }
 
-/* popcount of bits [lo, hi) */
-SER_HD int ser_col_popc(const uint32_t *col, int C, int lo, int hi)
+/* ones in bits [0, p), p in [0, N]: prefix table + one POPC */
+SER_HD int ser_rank1(const uint32_t *col, const uint16_t *pre, int C, int p)
 {
-  int n = 0;
-  if (hi <= lo) return 0;
-  for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) n += SER_POPC(col[w * C] & ser_range_mask(w, lo, hi));
-  return n;
+  const int w = p >> 5;
+  return (int)pre[w * C] + SER_POPC(col[w * C] & ser_mask_lo(p & 31));
+}
+
+/* popcount of bits [lo, hi) */
+SER_HD int ser_col_popc(const uint32_t *col, const uint16_t *pre, int C, int lo, int hi)
+{
+  return hi <= lo ? 0 : ser_rank1(col, pre, C, hi) - ser_rank1(col, pre, C, lo);
+}
+
+/* (re)build pre[0..W] from the words */
+SER_HD void ser_col_build_pre(const uint32_t *col, uint16_t *pre, int C, int W)
+{
+  int acc = 0;
+  pre[0] = 0;
+  for (int w = 0; w < W; w++) { acc += SER_POPC(col[w * C]); pre[(w + 1) * C] = (uint16_t)acc; }
+}
+
+/* after a permutation of bits inside words w0..w1 (the multiset of bits there is unchanged)
+ * only pre[w0+1..w1] can differ */
+SER_HD void ser_col_fix_pre(const uint32_t *col, uint16_t *pre, int C, int w0, int w1)
+{
+  int acc = pre[w0 * C];
+  for (int w = w0; w < w1; w++) { acc += SER_POPC(col[w * C]); pre[(w + 1) * C] = (uint16_t)acc; }
 }
 
 /* word j of the logical string s: REV ? s[k] = v[N-1-k] : s = v */
@@ -183,31 +208,39 @@ SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uin
 }
 
 /* ------------------------------------------------------------------ hard sites */
-/* hcol = column M (hard mask in position order); hcum[w] = #hard positions in words < w */
+/* hcol = column M (hard mask in position order) and its prefix table */
 struct SerHard {
   const uint32_t *hcol;
-  const int *hcum; /* W + 1 entries */
+  const uint16_t *hpre; /* hpre[w * C] = #hard positions in words < w, w = 0..W */
+  const uint16_t *hp;   /* the nh hard positions, ascending */
   int C, W, N, nh;
 };
 
-/* number of hard positions < p, p in [0, N] */
-SER_HD int ser_hard_rank(const SerHard &h, int p)
+/* rebuild the sorted list of hard positions from the mask (owner thread, after a move) */
+SER_HD void ser_hard_list(const uint32_t *hcol, int C, int W, uint16_t *hp)
 {
-  const int w = p >> 5;
-  if (w >= h.W) return h.hcum[h.W];
-  return h.hcum[w] + SER_POPC(h.hcol[w * h.C] & ser_mask_lt(p & 31));
+  int k = 0;
+  for (int w = 0; w < W; w++) {
+    uint32_t v = hcol[w * C];
+    while (v) { hp[k++] = (uint16_t)(32 * w + SER_FFS(v) - 1); v &= v - 1u; }
+  }
 }
+
+/* number of hard positions < p, p in [0, N] */
+SER_HD int ser_hard_rank(const SerHard &h, int p) { return ser_rank1(h.hcol, h.hpre, h.C, p); }
 SER_HD int ser_is_hard(const SerHard &h, int p) { return (h.hcol[(p >> 5) * h.C] >> (p & 31)) & 1u; }
 /* number of hard positions in [lo, hi] */
 SER_HD int ser_hard_count(const SerHard &h, int lo, int hi) { return ser_hard_rank(h, hi + 1) - ser_hard_rank(h, lo); }
-/* position of the r-th (from 0) non-hard position; r < N - nh */
+/* position of the r-th (from 0) non-hard position; r < N - nh.  Binary search for the word
+ * (non-hard prefix 32w - hpre[w] is non-decreasing), then select inside it. */
 SER_HD int ser_select_nonhard(const SerHard &h, int r)
 {
-  for (int w = 0; w < h.W; w++) {
-    const int next = 32 * (w + 1) - h.hcum[w + 1];
-    if (r < next) return 32 * w + ser_select_bit(~h.hcol[w * h.C], r - (32 * w - h.hcum[w]));
+  int lo = 0, hi = h.W - 1; /* largest w with 32w - hpre[w] <= r */
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (32 * mid - (int)h.hpre[mid * h.C] <= r) lo = mid; else hi = mid - 1;
   }
-  return h.N - 1; /* unreachable for valid r */
+  return 32 * lo + ser_select_bit(~h.hcol[lo * h.C], r - (32 * lo - (int)h.hpre[lo * h.C]));
 }
 
 /* ------------------------------------------------------------------ likelihood weights */
@@ -299,6 +332,23 @@ SER_HD double ser_run_sum(const SerWeights &w, int n, double le, int *m_out, dou
   return ser_fma(ye, w.H[m], SER_MUL(ser_i2d(n - m), w.eps));
 }
 
+/* sum of the candidates t = 0..cnt-1 of logical word `word` (first candidate has log-weight
+ * `base`, `cuts` = the ones among bits 0..cnt-2): runs between ones in closed form */
+SER_HD double ser_word_sum(const SerWeights &wt, uint32_t cuts, int cnt, double base)
+{
+  double sum = 0.0, acc = base; /* acc = base + (#ones passed) * A */
+  int ts = 0;
+  for (;;) {
+    const int te = cuts ? SER_FFS(cuts) - 1 : cnt - 1; /* run ends on the candidate below the next one */
+    int m; double ye;
+    sum = SER_ADD(sum, ser_run_sum(wt, te - ts + 1, ser_fma(ser_i2d(te), wt.g, acc), &m, &ye));
+    if (!cuts) return sum;
+    cuts &= cuts - 1u;
+    acc = SER_ADD(acc, wt.A);
+    ts = te + 1;
+  }
+}
+
 /*
  * Gibbs draw of one boundary (the a-step, or the b-step on the reversed column).
  * Logical string s (REV: s[k] = v[N-1-k]); candidates 0..bound; `cur` is the current value;
@@ -306,78 +356,103 @@ SER_HD double ser_run_sum(const SerWeights &w, int n, double le, int *m_out, dou
  * first candidate whose cumulative weight reaches U * total (mcmc_auxa + mcmc_logtop +
  * mcmc_randompick, mcmc.c:828-915).
  *
- * Sparse formulation: between two ones the weights form a geometric sequence, so every maximal
- * run of candidates that only passes zeros (cut at 32-bit word boundaries) is summed in closed
- * form through the table H -- O(#ones + #words) work per column instead of O(#sites).
- * ck[] is caller-provided scratch of (bound>>5)+1 doubles (cumulative weight per word).
+ * Sparse formulation.  Passing a zero raises the log-weight by g, passing a one lowers it by w1,
+ * so (i) between two ones the weights are geometric and a whole run is summed through the table
+ * H, and (ii) a word whose zero-only upper bound stays below the floor contributes cnt * eps
+ * without looking at its bits.  Each lane first classifies its words with that bound (cheap,
+ * uniform loop), remembers the few "live" ones in a bitmask, and then works through its own live
+ * words -- so a warp runs the expensive run/exp path max-popcount(live) times, not once per word.
+ * ck[] is caller-provided scratch of (bound>>5)+1 doubles.
  */
 template <bool REV>
-SER_HD int ser_gibbs_boundary(const uint32_t *col, int C, int W, int N, int cur, int bound, double U,
-                              const SerWeights &wt, double *ck)
+SER_HD int ser_gibbs_boundary(const uint32_t *col, const uint16_t *pre, int C, int W, int N, int cur, int bound,
+                              double U, const SerWeights &wt, double *ck)
 {
   const int nw = (bound >> 5) + 1;
-  /* ones below the current boundary: the reference point of the log-weights */
-  int o_cur;
-  if (!REV) o_cur = ser_col_popc(col, C, 0, cur);
-  else o_cur = ser_col_popc(col, C, N - cur, N);
+  const int total = pre[W * C];
+  /* ones of the logical string below candidate k */
+#define SER_OBELOW(k) (REV ? total - ser_rank1(col, pre, C, N - (k)) : ser_rank1(col, pre, C, (k)))
+  const int o_cur = SER_OBELOW(cur);
+  const double gcur = SER_MUL(ser_i2d(cur), wt.g);
 
-  /* pass A: maximum log-weight; local maxima sit on the candidate just below a one, or at `bound` */
-  double lmax;
-  {
-    int o = 0;
-    lmax = -1.0e300;
-    for (int j = 0; j < nw; j++) {
-      uint32_t word = ser_logical_word<REV>(col, C, W, N, j) & ser_range_mask(j, 0, bound);
-      while (word) {
-        const int t = SER_FFS(word) - 1;
-        word &= word - 1u;
-        lmax = ser_fmax(lmax, ser_logw(wt, o - o_cur, 32 * j + t - cur, 0.0));
-        o++;
-      }
-    }
-    lmax = ser_fmax(lmax, ser_logw(wt, o - o_cur, bound - cur, 0.0));
+  /* pass A: maximum log-weight.  L(cur) = 0 is a candidate, so only words whose zero-only bound
+   * exceeds 0 can hold the maximum. */
+  double lmax = 0.0;
+  uint64_t live = 0;
+  for (int j = 0; j < nw; j++) {
+    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
+    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
+    const double ub = ser_fma(ser_i2d(ob), wt.A, SER_SUB(SER_MUL(ser_i2d(32 * j + cnt - 1), wt.g), gcur));
+    if (ub > 0.0) live |= 1ull << j;
   }
-  const double c0 = -lmax;
+  while (live) {
+#if defined(__CUDA_ARCH__)
+    const int j = __ffsll((long long)live) - 1;
+#else
+    const int j = __builtin_ffsll((long long)live) - 1;
+#endif
+    live &= live - 1ull;
+    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
+    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
+    double acc = ser_fma(ser_i2d(ob), wt.A, SER_SUB(SER_MUL(ser_i2d(32 * j), wt.g), gcur));
+    uint32_t cuts = ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1);
+    while (cuts) { /* candidate just below each one */
+      const int t = SER_FFS(cuts) - 1;
+      cuts &= cuts - 1u;
+      lmax = ser_fmax(lmax, ser_fma(ser_i2d(t), wt.g, acc));
+      acc = SER_ADD(acc, wt.A);
+    }
+    lmax = ser_fmax(lmax, ser_fma(ser_i2d(cnt - 1), wt.g, acc)); /* last candidate of the word */
+  }
+  const double c0 = SER_SUB(-lmax, gcur);
 
-  /* pass B: total weight, one cumulative checkpoint per word */
+  /* pass B: per-word weight.  Fully floored words by the bound; the rest run by run. */
+  live = 0;
+  for (int j = 0; j < nw; j++) {
+    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
+    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
+    const double ub = ser_fma(ser_i2d(ob), wt.A, ser_fma(ser_i2d(32 * j + cnt - 1), wt.g, c0));
+    if (ub < SER_LOGEPSILON) ck[j] = SER_MUL(ser_i2d(cnt), wt.eps);
+    else { ck[j] = 0.0; live |= 1ull << j; }
+  }
+  const uint64_t live_b = live;
+  while (live) {
+#if defined(__CUDA_ARCH__)
+    const int j = __ffsll((long long)live) - 1;
+#else
+    const int j = __builtin_ffsll((long long)live) - 1;
+#endif
+    live &= live - 1ull;
+    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
+    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
+    const double base = ser_fma(ser_i2d(ob), wt.A, ser_fma(ser_i2d(32 * j), wt.g, c0));
+    ck[j] = ser_word_sum(wt, ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1), cnt, base);
+  }
   double S = 0.0;
-  {
-    int o = 0;
-    for (int j = 0; j < nw; j++) {
-      const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32; /* candidates in this word */
-      uint32_t cuts = ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1);
-      int ts = 0; /* first candidate (local index) of the current run */
-      for (;;) {
-        const int te = cuts ? SER_FFS(cuts) - 1 : cnt - 1; /* run ends on the candidate below the next one */
-        int m; double ye;
-        S = SER_ADD(S, ser_run_sum(wt, te - ts + 1, ser_logw(wt, o - o_cur, 32 * j + te - cur, c0), &m, &ye));
-        if (!cuts) break;
-        cuts &= cuts - 1u;
-        o++;
-        ts = te + 1;
-      }
-      ck[j] = S;
-      /* the bit of the word's last candidate is passed when entering the next word */
-      if (cnt == 32) o += (int)((ser_logical_word<REV>(col, C, W, N, j) >> 31) & 1u);
-    }
-  }
+  for (int j = 0; j < nw; j++) { S = SER_ADD(S, ck[j]); ck[j] = S; } /* cumulative, candidate order */
 
   /* pass C: inverse CDF -- word, then run, then candidate inside the run */
   const double target = SER_MUL(U, S);
   int j = 0;
   while (j < nw - 1 && ck[j] < target) j++;
   double s = j ? ck[j - 1] : 0.0;
-  int o;
-  if (!REV) o = ser_col_popc(col, C, 0, 32 * j);
-  else o = ser_col_popc(col, C, N - 32 * j, N);
   const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
+  if (!((live_b >> j) & 1ull)) { /* a fully floored word: cnt candidates of weight eps each */
+    const double td = SER_DIV(SER_SUB(target, s), wt.eps);
+    int t = !(td > 0.0) ? 0 : (td >= (double)(cnt - 1) ? cnt - 1 : (int)td);
+    while (t > 0 && ser_fma(ser_i2d(t), wt.eps, s) >= target) t--;
+    while (t < cnt - 1 && ser_fma(ser_i2d(t + 1), wt.eps, s) < target) t++;
+    return 32 * j + t;
+  }
+  const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
+  double acc = ser_fma(ser_i2d(ob), wt.A, ser_fma(ser_i2d(32 * j), wt.g, c0));
   uint32_t cuts = ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1);
   int ts = 0;
   for (;;) {
     const int te = cuts ? SER_FFS(cuts) - 1 : cnt - 1;
     const int n = te - ts + 1;
     int m; double ye;
-    const double snext = SER_ADD(s, ser_run_sum(wt, n, ser_logw(wt, o - o_cur, 32 * j + te - cur, c0), &m, &ye));
+    const double snext = SER_ADD(s, ser_run_sum(wt, n, ser_fma(ser_i2d(te), wt.g, acc), &m, &ye));
     if (snext >= target || !cuts) {
       /* inside this run: nf floored candidates of weight eps each, then m geometric ones */
       const int nf = n - m;
@@ -401,9 +476,10 @@ SER_HD int ser_gibbs_boundary(const uint32_t *col, int C, int W, int N, int cur,
     }
     s = snext;
     cuts &= cuts - 1u;
-    o++;
+    acc = SER_ADD(acc, wt.A);
     ts = te + 1;
   }
+#undef SER_OBELOW
 }
 
 /* ------------------------------------------------------------------ pi proposals */
@@ -453,14 +529,15 @@ SER_HD void ser_pi1_apply_ab(int *a, int *b, int i, int j)
 }
 
 /* pi2: positions [i, j] reversed */
-SER_HD void ser_pi2_delta(const uint32_t *col, int C, int a, int b, int i, int j, int inc1, int inc2,
-                          int *dt0, int *dt1)
+SER_HD void ser_pi2_delta(const uint32_t *col, const uint16_t *pre, int C, int a, int b, int i, int j, int inc1,
+                          int inc2, int *dt0, int *dt1)
 {
   const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
   *dt0 = 0; *dt1 = 0;
   if (ain == bin) return;
   const int split = ain ? a : b;
-  const int oL = ser_col_popc(col, C, i, split), oR = ser_col_popc(col, C, split, j + 1);
+  const int r = ser_rank1(col, pre, C, split);
+  const int oL = r - ser_rank1(col, pre, C, i), oR = ser_rank1(col, pre, C, j + 1) - r;
   const int zL = (split - i) - oL, zR = (j + 1 - split) - oR;
   if (ain) { *dt1 = oL - oR; *dt0 = zR - zL; }  /* left part becomes alive, right part dies */
   else { *dt1 = oR - oL; *dt0 = zL - zR; }      /* left part dies, right part becomes alive */
@@ -495,8 +572,8 @@ SER_HD int ser_pi3_perm(const SerHard &h, const SerPi3 &g, int n)
 }
 
 /* pi3: only the non-hard sites of [i, j] are reversed; a/b mirror as in pi2 */
-SER_HD void ser_pi3_delta(const uint32_t *col, int C, const SerHard &h, const SerPi3 &g, int a, int b,
-                          int inc1, int inc2, int *dt0, int *dt1)
+SER_HD void ser_pi3_delta(const uint32_t *col, const uint16_t *pre, int C, const SerHard &h, const SerPi3 &g, int a,
+                          int b, int inc1, int inc2, int *dt0, int *dt1)
 {
   const int i = g.i, j = g.j;
   const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
@@ -508,19 +585,20 @@ SER_HD void ser_pi3_delta(const uint32_t *col, int C, const SerHard &h, const Se
   const int alo = a > i ? a : i, ahi = b < j + 1 ? b : j + 1;
   /* is alive afterwards, in OLD position coordinates:
    *   hard sites stay put            -> hard positions in [na,nb)
-   *   non-hard site of window rank r -> lands on rank K-1-r, alive iff that is in [R(na),R(nb)) */
+   *   non-hard site of window rank r -> lands on rank K-1-r, alive iff that is in [R(na),R(nb)),
+   *                                     i.e. non-hard positions in [lo2, hi2) */
   int nac = na < i ? i : (na > j + 1 ? j + 1 : na), nbc = nb < i ? i : (nb > j + 1 ? j + 1 : nb);
   if (nbc < nac) nbc = nac;
-  const int lo2 = ser_pi3_wpos(h, g, g.K - ser_pi3_wrank(h, g, nbc));
-  const int hi2 = ser_pi3_wpos(h, g, g.K - ser_pi3_wrank(h, g, nac));
-  int oA = 0, oB = 0, nA = 0, nB = 0;
-  for (int w = i >> 5; w <= j >> 5; w++) {
-    const uint32_t v = col[w * C], hw = h.hcol[w * h.C];
-    const uint32_t mA = ser_range_mask(w, alo, ahi);
-    const uint32_t mB = (hw & ser_range_mask(w, nac, nbc)) | (~hw & ser_range_mask(w, lo2, hi2));
-    oA += SER_POPC(v & mA); nA += SER_POPC(mA);
-    oB += SER_POPC(v & mB); nB += SER_POPC(mB);
-  }
+  const int hr_na = ser_hard_rank(h, nac), hr_nb = ser_hard_rank(h, nbc);
+  const int lo2 = ser_pi3_wpos(h, g, g.K - ((nbc - i) - (hr_nb - g.hr_i)));
+  const int hi2 = ser_pi3_wpos(h, g, g.K - ((nac - i) - (hr_na - g.hr_i)));
+  const int hr_lo2 = ser_hard_rank(h, lo2), hr_hi2 = ser_hard_rank(h, hi2);
+  const int nA = ahi > alo ? ahi - alo : 0, oA = ser_col_popc(col, pre, C, alo, ahi);
+  /* B = (hard in [nac,nbc)) + (non-hard in [lo2,hi2)) */
+  const int nB = (hr_nb - hr_na) + ((hi2 > lo2 ? hi2 - lo2 : 0) - (hr_hi2 - hr_lo2));
+  int oB = ser_col_popc(col, pre, C, lo2, hi2);
+  for (int k = hr_lo2; k < hr_hi2; k++) oB -= ser_col_bit(col, C, h.hp[k]); /* hard ones inside [lo2,hi2) do not count */
+  for (int k = hr_na; k < hr_nb; k++) oB += ser_col_bit(col, C, h.hp[k]);   /* hard ones in [nac,nbc) do */
   *dt1 = oB - oA;
   *dt0 = (nA - oA) - (nB - oB); /* true zeros = dead zeros: gain what the alive zeros lose */
 }
@@ -535,10 +613,10 @@ SER_HD double ser_term(const SerWeights &w, int dt0, int dt1)
 }
 
 /* per-taxon counts from the column: t1 = ones alive, the rest by difference (mcmc.c:651-708) */
-SER_HD void ser_counts(const uint32_t *col, int C, int N, int a, int b, int ones, int *t0, int *f0, int *t1,
-                       int *f1)
+SER_HD void ser_counts(const uint32_t *col, const uint16_t *pre, int C, int N, int a, int b, int ones, int *t0,
+                       int *f0, int *t1, int *f1)
 {
-  const int o = ser_col_popc(col, C, a, b);
+  const int o = ser_col_popc(col, pre, C, a, b);
   *t1 = o;
   *f1 = ones - o;
   *f0 = (b - a) - o;

@@ -72,7 +72,8 @@ struct Smem {
   double *H;        /* N + 2: geometric partial sums of the current sweep (ser_h_entry) */
   uint32_t *V;      /* W*C */
   int *red;         /* 2 * SER_MAX_WARPS * 4 */
-  int *hcum;        /* W+1 */
+  uint16_t *pre;    /* (W+1)*C: pre[w][col] = ones of the column in words < w */
+  uint16_t *hp;     /* N+1: hard positions, ascending */
   uint16_t *rpi, *tmp16, *perm16; /* N each */
 };
 
@@ -83,12 +84,12 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
   size_t o_H = take(sizeof(double) * (N + 2));
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
-  size_t o_h = take(sizeof(int) * (W + 1));
+  size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
   size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
   if (s) {
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
     s->H = (double *)(base + o_H);
-    s->V = (uint32_t *)(base + o_v); s->red = (int *)(base + o_r); s->hcum = (int *)(base + o_h);
+    s->V = (uint32_t *)(base + o_v); s->red = (int *)(base + o_r); s->pre = (uint16_t *)(base + o_h); s->hp = (uint16_t *)(base + o_hp);
     s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q); s->perm16 = (uint16_t *)(base + o_m);
   }
   return off;
@@ -128,14 +129,11 @@ __device__ void build_columns(const KParams &p, const Smem &sm)
     }
     sm.V[w * C + tid] = word;
   }
+  ser_col_build_pre(sm.V + tid, sm.pre + tid, C, p.W);
 }
 
-__device__ void rebuild_hcum(const KParams &p, const Smem &sm)
-{
-  int acc = 0;
-  sm.hcum[0] = 0;
-  for (int w = 0; w < p.W; w++) { acc += __popc(sm.V[w * p.C + p.M]); sm.hcum[w + 1] = acc; }
-}
+/* sorted hard positions from the hard-mask column (its owner thread, tid == M) */
+__device__ void rebuild_hard(const KParams &p, const Smem &sm) { ser_hard_list(sm.V + p.M, p.C, p.W, sm.hp); }
 
 /* mcmc_initab, mcmc.c:440-474, on the thread's own column */
 __device__ void init_ab(const KParams &p, const uint32_t *col, int *a, int *b)
@@ -237,7 +235,7 @@ __global__ void ser_init_kernel(KParams p)
   wt.eps = p.eps;
   set_weights(wt, p.c0, p.cc0, p.d0, p.dd0);
   int t1 = 0, len = 0;
-  if (tid < M) { t1 = ser_col_popc(col, C, a, b); len = b - a; }
+  if (tid < M) { t1 = ser_col_popc(col, sm.pre + tid, C, a, b); len = b - a; }
   int buf = 0, T1, LEN, dummy;
   block_sum3(t1, len, 0, sm.red, buf, &T1, &LEN, &dummy);
   int t0a, f0a, t1a, f1a;
@@ -303,6 +301,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
   const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
   uint32_t *col = sm.V + tid;
+  uint16_t *pre = sm.pre + tid;
   const bool is_taxon = tid < M, is_col = tid <= M;
 
   /* ---- load chain state */
@@ -317,7 +316,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   __syncthreads();
   build_columns(p, sm);
   __syncthreads();
-  if (tid == M) rebuild_hcum(p, sm);
+  if (tid == M) rebuild_hard(p, sm);
   __syncthreads();
 
   const double *tape = nullptr;
@@ -333,7 +332,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   wt.hmax = 0;
   set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
   SerHard hd;
-  hd.hcol = sm.V + M; hd.hcum = sm.hcum; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh;
+  hd.hcol = sm.V + M; hd.hpre = sm.pre + M; hd.hp = sm.hp; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh;
   PropState ps;
   ps.k = 0; ps.buf = 0;
   double ck[SER_MAXW + 1];
@@ -397,13 +396,13 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
       /* ================= a/b Gibbs (mcmc_sampleab, mcmc.c:918-996) ================= */
       int t1 = 0, len = 0, changed = 0;
       if (is_taxon) {
-        const int na = ser_gibbs_boundary<false>(col, C, W, N, a, b, ua, wt, ck);
+        const int na = ser_gibbs_boundary<false>(col, pre, C, W, N, a, b, ua, wt, ck);
         changed += na != a;
         a = na;
-        const int t = ser_gibbs_boundary<true>(col, C, W, N, N - b, N - a, ub, wt, ck);
+        const int t = ser_gibbs_boundary<true>(col, pre, C, W, N, N - b, N - a, ub, wt, ck);
         changed += (N - t) != b;
         b = N - t;
-        t1 = ser_col_popc(col, C, a, b);
+        t1 = ser_col_popc(col, pre, C, a, b);
         len = b - a;
       }
       {
@@ -430,12 +429,12 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
           if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
           if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
           if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
-          if (is_col) ser_col_rotate(col, C, W, i, j);
+          if (is_col) { ser_col_rotate(col, C, W, i, j); ser_col_fix_pre(col, pre, C, lo >> 5, hi >> 5); }
           for (int n = lo + tid; n <= hi; n += C)
             sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
           __syncthreads();
           for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
-          if (tid == M) rebuild_hcum(p, sm);
+          if (tid == M) rebuild_hard(p, sm);
           sc.counters[3]++;
         } else if (kind == 1 || kind == 3) { /* ---------------- mcmc_samplepi2, mcmc.c:1311-1486 */
           int i, j;
@@ -453,17 +452,17 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
           if (ser_hard_count(hd, i, j) > 1) continue;
           const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
           ps.k += 2;
-          if (is_taxon) ser_pi2_delta(col, C, a, b, i, j, inc1, inc2, &dt0, &dt1);
+          if (is_taxon) ser_pi2_delta(col, pre, C, a, b, i, j, inc1, inc2, &dt0, &dt1);
           if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
           if (is_taxon) {
             const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
           }
-          if (is_col) ser_col_reverse(col, C, W, i, j);
+          if (is_col) { ser_col_reverse(col, C, W, i, j); ser_col_fix_pre(col, pre, C, i >> 5, j >> 5); }
           for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
           __syncthreads();
           for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
-          if (tid == M) rebuild_hcum(p, sm);
+          if (tid == M) rebuild_hard(p, sm);
           sc.counters[kind == 1 ? 4 : 5]++;
         } else { /* ---------------- mcmc_samplepi3, mcmc.c:1489-1682 */
           const int nfree = N - p.nh;
@@ -475,7 +474,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
           const SerPi3 g = ser_pi3_window(hd, ir, jr);
           const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
           ps.k += 2;
-          if (is_taxon) ser_pi3_delta(col, C, hd, g, a, b, inc1, inc2, &dt0, &dt1);
+          if (is_taxon) ser_pi3_delta(col, pre, C, hd, g, a, b, inc1, inc2, &dt0, &dt1);
           if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
           for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
           __syncthreads();
@@ -483,6 +482,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
             const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
             ser_col_permute(col, C, W, g.i, g.j, sm.perm16);
+            ser_col_fix_pre(col, pre, C, g.i >> 5, g.j >> 5);
           }
           for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
           __syncthreads();
@@ -546,7 +546,7 @@ __global__ void ser_export_kernel(KParams p, int chain, int *out_a, int *out_b, 
   if (tid < p.M) {
     const int a = p.ab[(size_t)chain * 2 * p.Mpad + tid], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
     int t0, f0, t1, f1;
-    ser_counts(sm.V + tid, C, p.N, a, b, p.ones[tid], &t0, &f0, &t1, &f1);
+    ser_counts(sm.V + tid, sm.pre + tid, C, p.N, a, b, p.ones[tid], &t0, &f0, &t1, &f1);
     out_a[tid] = a; out_b[tid] = b;
     out_cnt[tid] = t0; out_cnt[p.M + tid] = f0; out_cnt[2 * p.M + tid] = t1; out_cnt[3 * p.M + tid] = f1;
   }
@@ -582,7 +582,7 @@ __global__ void ser_check_kernel(KParams p, int *bad_count)
   if (tid < M) {
     const int a = p.ab[(size_t)chain * 2 * p.Mpad + tid], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
     if (!(0 <= a && a <= b && b <= N)) atomicOr(&s_flags, 2);
-    else { t1 = ser_col_popc(sm.V + tid, C, a, b); len = b - a; }
+    else { t1 = ser_col_popc(sm.V + tid, sm.pre + tid, C, a, b); len = b - a; }
   }
   int buf = 0, T1, LEN, dummy;
   block_sum3(t1, len, 0, sm.red, buf, &T1, &LEN, &dummy);

@@ -27,7 +27,8 @@ struct Chain {
   int N, M, W, C, nh;
   std::vector<uint8_t> X, hard;
   std::vector<uint32_t> V; // [W][C], column M = hard mask
-  std::vector<int> a, b, ones, hcum;
+  std::vector<int> a, b, ones;
+  std::vector<uint16_t> pre, hp; // pre[(W+1)][C] prefix ones; hp = sorted hard positions
   std::vector<uint16_t> rpi;
   SerWeights wt;
   double loglik;
@@ -37,7 +38,8 @@ struct Chain {
   long long n_degenerate;
 
   uint32_t *col(int m) { return V.data() + m; }
-  SerHard hardinfo() const { return SerHard{V.data() + M, hcum.data(), C, W, N, nh}; }
+  uint16_t *pcol(int m) { return pre.data() + m; }
+  SerHard hardinfo() const { return SerHard{V.data() + M, pre.data() + M, hp.data(), C, W, N, nh}; }
   double next() {
     if (cur >= tape_len) { fprintf(stderr, "emul: tape exhausted\n"); exit(3); }
     return tape[cur++];
@@ -50,10 +52,8 @@ struct Chain {
     for (int m = 0; m <= wt.hmax; m++) H[m] = ser_h_entry(wt.g, m);
     wt.H = H.data();
   }
-  void rebuild_hcum() {
-    hcum[0] = 0;
-    for (int w = 0; w < W; w++) hcum[w + 1] = hcum[w] + SER_POPC(V[w * C + M]);
-  }
+  void rebuild_hard() { ser_hard_list(V.data() + M, C, W, hp.data()); }
+  void fix_pre(int p0, int p1) { for (int m = 0; m <= M; m++) ser_col_fix_pre(col(m), pcol(m), C, p0 >> 5, p1 >> 5); }
   void build_columns() {
     std::fill(V.begin(), V.end(), 0u);
     for (int p = 0; p < N; p++) {
@@ -62,7 +62,8 @@ struct Chain {
         if (X[(size_t)site * M + m]) V[(p >> 5) * C + m] |= 1u << (p & 31);
       if (hard[site]) V[(p >> 5) * C + M] |= 1u << (p & 31);
     }
-    rebuild_hcum();
+    for (int m = 0; m <= M; m++) ser_col_build_pre(col(m), pcol(m), C, W);
+    rebuild_hard();
   }
   void initab() {
     for (int m = 0; m < M; m++) {
@@ -76,7 +77,7 @@ struct Chain {
   }
   void totals() {
     long T1 = 0, LEN = 0, ONES = 0;
-    for (int m = 0; m < M; m++) { T1 += ser_col_popc(col(m), C, a[m], b[m]); LEN += b[m] - a[m]; ONES += ones[m]; }
+    for (int m = 0; m < M; m++) { T1 += ser_col_popc(col(m), pcol(m), C, a[m], b[m]); LEN += b[m] - a[m]; ONES += ones[m]; }
     t1a = (int)T1; f1a = (int)(ONES - T1); f0a = (int)(LEN - T1); t0a = (int)((long)N * M - LEN - f1a);
     loglik = t0a * wt.cc + f0a * wt.d + t1a * wt.dd + f1a * wt.c;
   }
@@ -126,7 +127,8 @@ int pi1(Chain &ch) {
   if (i < j) for (int n = i; n < j; n++) ch.rpi[n] = ch.rpi[n + 1];
   else for (int n = i; n > j; n--) ch.rpi[n] = ch.rpi[n - 1];
   ch.rpi[j] = t;
-  ch.rebuild_hcum();
+  ch.fix_pre(lo, hi);
+  ch.rebuild_hard();
   after_accept(ch, D0, D1, delta);
   return 1;
 }
@@ -142,7 +144,7 @@ int pi2(Chain &ch, int swap) {
   if (ser_hard_count(h, i, j) > 1) return 0;
   const int inc1 = ser_draw_int(ch.next(), 2), inc2 = ser_draw_int(ch.next(), 2);
   std::vector<int> dt0(M), dt1(M);
-  for (int m = 0; m < M; m++) ser_pi2_delta(ch.col(m), C, ch.a[m], ch.b[m], i, j, inc1, inc2, &dt0[m], &dt1[m]);
+  for (int m = 0; m < M; m++) ser_pi2_delta(ch.col(m), ch.pcol(m), C, ch.a[m], ch.b[m], i, j, inc1, inc2, &dt0[m], &dt1[m]);
   double delta;
   if (!decide(ch, dt0, dt1, &delta)) return 0;
   long D0 = 0, D1 = 0;
@@ -153,7 +155,8 @@ int pi2(Chain &ch, int swap) {
   }
   for (int m = 0; m <= M; m++) ser_col_reverse(ch.col(m), C, W, i, j);
   for (int l = i, r = j; l < r; l++, r--) { uint16_t t = ch.rpi[l]; ch.rpi[l] = ch.rpi[r]; ch.rpi[r] = t; }
-  ch.rebuild_hcum();
+  ch.fix_pre(i, j);
+  ch.rebuild_hard();
   after_accept(ch, D0, D1, delta);
   return 1;
 }
@@ -168,7 +171,7 @@ int pi3(Chain &ch) {
   const SerPi3 g = ser_pi3_window(h, ir, jr);
   const int inc1 = ser_draw_int(ch.next(), 2), inc2 = ser_draw_int(ch.next(), 2);
   std::vector<int> dt0(M), dt1(M);
-  for (int m = 0; m < M; m++) ser_pi3_delta(ch.col(m), C, h, g, ch.a[m], ch.b[m], inc1, inc2, &dt0[m], &dt1[m]);
+  for (int m = 0; m < M; m++) ser_pi3_delta(ch.col(m), ch.pcol(m), C, h, g, ch.a[m], ch.b[m], inc1, inc2, &dt0[m], &dt1[m]);
   double delta;
   if (!decide(ch, dt0, dt1, &delta)) return 0;
   long D0 = 0, D1 = 0;
@@ -182,6 +185,7 @@ int pi3(Chain &ch) {
   for (int m = 0; m < M; m++) ser_col_permute(ch.col(m), C, W, g.i, g.j, perm.data());
   std::vector<uint16_t> tmp(ch.rpi);
   for (int n = g.i; n <= g.j; n++) ch.rpi[n] = tmp[perm[n]];
+  ch.fix_pre(g.i, g.j);
   after_accept(ch, D0, D1, delta);
   return 1;
 }
@@ -200,10 +204,10 @@ int sample_ab(Chain &ch) {
   std::vector<double> ck(ch.W + 1);
   for (int m = 0; m < ch.M; m++) {
     const double ua = ch.next(), ub = ch.next();
-    const int na = ser_gibbs_boundary<false>(ch.col(m), ch.C, ch.W, ch.N, ch.a[m], ch.b[m], ua, ch.wt, ck.data());
+    const int na = ser_gibbs_boundary<false>(ch.col(m), ch.pcol(m), ch.C, ch.W, ch.N, ch.a[m], ch.b[m], ua, ch.wt, ck.data());
     changed += na != ch.a[m];
     ch.a[m] = na;
-    const int t = ser_gibbs_boundary<true>(ch.col(m), ch.C, ch.W, ch.N, ch.N - ch.b[m], ch.N - ch.a[m], ub, ch.wt, ck.data());
+    const int t = ser_gibbs_boundary<true>(ch.col(m), ch.pcol(m), ch.C, ch.W, ch.N, ch.N - ch.b[m], ch.N - ch.a[m], ub, ch.wt, ck.data());
     changed += (ch.N - t) != ch.b[m];
     ch.b[m] = ch.N - t;
   }
@@ -230,7 +234,8 @@ void *emul_create(int N, int M, const uint8_t *X, const uint8_t *hard, double c0
   ch->hard.assign(hard, hard + N);
   for (int n = 0; n < N; n++) ch->nh += hard[n] != 0;
   ch->V.assign((size_t)ch->W * ch->C, 0u);
-  ch->a.assign(M, 0); ch->b.assign(M, 0); ch->ones.assign(M, 0); ch->hcum.assign(ch->W + 1, 0);
+  ch->a.assign(M, 0); ch->b.assign(M, 0); ch->ones.assign(M, 0);
+  ch->pre.assign((size_t)(ch->W + 1) * ch->C, 0); ch->hp.assign(N + 1, 0);
   ch->rpi.resize(N);
   for (int n = 0; n < N; n++) ch->rpi[n] = (uint16_t)n;
   for (int m = 0; m < M; m++) for (int n = 0; n < N; n++) ch->ones[m] += X[(size_t)n * M + m] != 0;
@@ -291,7 +296,7 @@ void emul_get_state(void *p, int32_t *a, int32_t *b, int32_t *pi, int32_t *rpi, 
   for (int m = 0; m < ch.M; m++) {
     a[m] = ch.a[m]; b[m] = ch.b[m];
     int x0, y0, x1, y1;
-    ser_counts(ch.col(m), ch.C, ch.N, ch.a[m], ch.b[m], ch.ones[m], &x0, &y0, &x1, &y1);
+    ser_counts(ch.col(m), ch.pcol(m), ch.C, ch.N, ch.a[m], ch.b[m], ch.ones[m], &x0, &y0, &x1, &y1);
     t0[m] = x0; f0[m] = y0; t1[m] = x1; f1[m] = y1;
   }
   for (int n = 0; n < ch.N; n++) { rpi[n] = ch.rpi[n]; pi[ch.rpi[n]] = n; }
