@@ -332,154 +332,130 @@ SER_HD double ser_run_sum(const SerWeights &w, int n, double le, int *m_out, dou
   return ser_fma(ye, w.H[m], SER_MUL(ser_i2d(n - m), w.eps));
 }
 
-/* sum of the candidates t = 0..cnt-1 of logical word `word` (first candidate has log-weight
- * `base`, `cuts` = the ones among bits 0..cnt-2): runs between ones in closed form */
-SER_HD double ser_word_sum(const SerWeights &wt, uint32_t cuts, int cnt, double base)
+/*
+ * ---- Gibbs draw of one boundary, item formulation ---------------------------------------
+ * (the a-step, or the b-step on the reversed column: mcmc_auxa + mcmc_logtop +
+ * mcmc_randompick, mcmc.c:828-915)
+ *
+ * Logical string s (REV: s[q] = v[N-1-q]); candidates 0..bound; `cur` = current value;
+ * weight(i) ~ exp(L(i)) floored at eps relative to the maximum, L(i) = dn1 A + di g with dn1 /
+ * di the ones / cells between cur and i.  Passing a zero raises L by g, passing a one lowers it
+ * by w1, so the candidates split into RUNS that end on a local maximum: the candidate just
+ * below each one of s[0,bound) and the candidate `bound`.  One run = one ITEM; its weight is the
+ * closed form ser_run_sum().  A column with K ones below `bound` has K+1 items, so the whole
+ * step costs O(#ones) instead of O(#sites), and the items of all taxa of a chain are evaluated
+ * densely across the CTA (ser_kernels.cu) -- only a short scan over a taxon's own items stays
+ * with the taxon's thread.
+ */
+struct SerStep {
+  int cur, bound; /* logical coordinates */
+  int ocur;       /* ones of s below cur */
+  int kb;         /* ones of s below bound = number of one-items; item kb is the bound item */
+  int nones, N, rev;
+};
+
+/* ascending positions of the ones of a column */
+SER_HD int ser_expand_ones(const uint32_t *col, int C, int W, uint16_t *out)
 {
-  double sum = 0.0, acc = base; /* acc = base + (#ones passed) * A */
-  int ts = 0;
-  for (;;) {
-    const int te = cuts ? SER_FFS(cuts) - 1 : cnt - 1; /* run ends on the candidate below the next one */
-    int m; double ye;
-    sum = SER_ADD(sum, ser_run_sum(wt, te - ts + 1, ser_fma(ser_i2d(te), wt.g, acc), &m, &ye));
-    if (!cuts) return sum;
-    cuts &= cuts - 1u;
-    acc = SER_ADD(acc, wt.A);
-    ts = te + 1;
+  int k = 0;
+  for (int w = 0; w < W; w++) {
+    uint32_t v = col[w * C];
+    while (v) { out[k++] = (uint16_t)(32 * w + SER_FFS(v) - 1); v &= v - 1u; }
   }
+  return k;
 }
 
-/*
- * Gibbs draw of one boundary (the a-step, or the b-step on the reversed column).
- * Logical string s (REV: s[k] = v[N-1-k]); candidates 0..bound; `cur` is the current value;
- * weight(i) ~ exp(-sum_{p<i} w(s_p)) floored at eps relative to the maximum; the pick is the
- * first candidate whose cumulative weight reaches U * total (mcmc_auxa + mcmc_logtop +
- * mcmc_randompick, mcmc.c:828-915).
- *
- * Sparse formulation.  Passing a zero raises the log-weight by g, passing a one lowers it by w1,
- * so (i) between two ones the weights are geometric and a whole run is summed through the table
- * H, and (ii) a word whose zero-only upper bound stays below the floor contributes cnt * eps
- * without looking at its bits.  Each lane first classifies its words with that bound (cheap,
- * uniform loop), remembers the few "live" ones in a bitmask, and then works through its own live
- * words -- so a warp runs the expensive run/exp path max-popcount(live) times, not once per word.
- * ck[] is caller-provided scratch of (bound>>5)+1 doubles.
- */
-template <bool REV>
-SER_HD int ser_gibbs_boundary(const uint32_t *col, const uint16_t *pre, int C, int W, int N, int cur, int bound,
-                              double U, const SerWeights &wt, double *ck)
+SER_HD SerStep ser_step_a(const uint32_t *col, const uint16_t *pre, int C, int W, int N, int a, int b)
 {
-  const int nw = (bound >> 5) + 1;
-  const int total = pre[W * C];
-  /* ones of the logical string below candidate k */
-#define SER_OBELOW(k) (REV ? total - ser_rank1(col, pre, C, N - (k)) : ser_rank1(col, pre, C, (k)))
-  const int o_cur = SER_OBELOW(cur);
-  const double gcur = SER_MUL(ser_i2d(cur), wt.g);
+  SerStep st;
+  st.cur = a; st.bound = b; st.ocur = ser_rank1(col, pre, C, a); st.kb = ser_rank1(col, pre, C, b);
+  st.nones = pre[W * C]; st.N = N; st.rev = 0;
+  return st;
+}
+/* b-step on the reversed column: boundary t = N - b, candidates 0..N-a */
+SER_HD SerStep ser_step_b(const uint32_t *col, const uint16_t *pre, int C, int W, int N, int a, int b)
+{
+  SerStep st;
+  st.nones = pre[W * C]; st.N = N; st.rev = 1;
+  st.cur = N - b; st.bound = N - a;
+  st.ocur = st.nones - ser_rank1(col, pre, C, b); st.kb = st.nones - ser_rank1(col, pre, C, a);
+  return st;
+}
 
-  /* pass A: maximum log-weight.  L(cur) = 0 is a candidate, so only words whose zero-only bound
-   * exceeds 0 can hold the maximum. */
-  double lmax = 0.0;
-  uint64_t live = 0;
-  for (int j = 0; j < nw; j++) {
-    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
-    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
-    const double ub = ser_fma(ser_i2d(ob), wt.A, SER_SUB(SER_MUL(ser_i2d(32 * j + cnt - 1), wt.g), gcur));
-    if (ub > 0.0) live |= 1ull << j;
-  }
-  while (live) {
-#if defined(__CUDA_ARCH__)
-    const int j = __ffsll((long long)live) - 1;
-#else
-    const int j = __builtin_ffsll((long long)live) - 1;
-#endif
-    live &= live - 1ull;
-    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
-    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
-    double acc = ser_fma(ser_i2d(ob), wt.A, SER_SUB(SER_MUL(ser_i2d(32 * j), wt.g), gcur));
-    uint32_t cuts = ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1);
-    while (cuts) { /* candidate just below each one */
-      const int t = SER_FFS(cuts) - 1;
-      cuts &= cuts - 1u;
-      lmax = ser_fmax(lmax, ser_fma(ser_i2d(t), wt.g, acc));
-      acc = SER_ADD(acc, wt.A);
-    }
-    lmax = ser_fmax(lmax, ser_fma(ser_i2d(cnt - 1), wt.g, acc)); /* last candidate of the word */
-  }
-  const double c0 = SER_SUB(-lmax, gcur);
+/* logical position of the kk-th logical one (kk < kb); pos[] = ascending physical positions */
+SER_HD int ser_item_q(const SerStep &st, const uint16_t *pos, int kk)
+{
+  return st.rev ? st.N - 1 - (int)pos[st.nones - 1 - kk] : (int)pos[kk];
+}
 
-  /* pass B: per-word weight.  Fully floored words by the bound; the rest run by run. */
-  live = 0;
-  for (int j = 0; j < nw; j++) {
-    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
-    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
-    const double ub = ser_fma(ser_i2d(ob), wt.A, ser_fma(ser_i2d(32 * j + cnt - 1), wt.g, c0));
-    if (ub < SER_LOGEPSILON) ck[j] = SER_MUL(ser_i2d(cnt), wt.eps);
-    else { ck[j] = 0.0; live |= 1ull << j; }
-  }
-  const uint64_t live_b = live;
-  while (live) {
-#if defined(__CUDA_ARCH__)
-    const int j = __ffsll((long long)live) - 1;
-#else
-    const int j = __builtin_ffsll((long long)live) - 1;
-#endif
-    live &= live - 1ull;
-    const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
-    const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
-    const double base = ser_fma(ser_i2d(ob), wt.A, ser_fma(ser_i2d(32 * j), wt.g, c0));
-    ck[j] = ser_word_sum(wt, ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1), cnt, base);
-  }
-  double S = 0.0;
-  for (int j = 0; j < nw; j++) { S = SER_ADD(S, ck[j]); ck[j] = S; } /* cumulative, candidate order */
+/* item kk (0..kb): last candidate q, run length n, log-weight of q relative to cur */
+SER_HD double ser_item_eval(const SerWeights &wt, const SerStep &st, const uint16_t *pos, int kk, int *q_out, int *n_out)
+{
+  const int q = kk < st.kb ? ser_item_q(st, pos, kk) : st.bound;
+  const int qprev = kk > 0 ? ser_item_q(st, pos, kk - 1) : -1;
+  *q_out = q; *n_out = q - qprev;
+  return ser_fma(ser_i2d(kk - st.ocur), wt.A, SER_MUL(ser_i2d(q - st.cur), wt.g));
+}
 
-  /* pass C: inverse CDF -- word, then run, then candidate inside the run */
-  const double target = SER_MUL(U, S);
-  int j = 0;
-  while (j < nw - 1 && ck[j] < target) j++;
-  double s = j ? ck[j - 1] : 0.0;
-  const int cnt = (bound + 1 - 32 * j) < 32 ? (bound + 1 - 32 * j) : 32;
-  if (!((live_b >> j) & 1ull)) { /* a fully floored word: cnt candidates of weight eps each */
-    const double td = SER_DIV(SER_SUB(target, s), wt.eps);
-    int t = !(td > 0.0) ? 0 : (td >= (double)(cnt - 1) ? cnt - 1 : (int)td);
+/* maximum log-weight over the items (the reference's z, mcmc.c:727-730) */
+SER_HD double ser_step_lmax(const SerWeights &wt, const SerStep &st, const uint16_t *pos)
+{
+  double lmax = -1.0e300;
+  for (int kk = 0; kk <= st.kb; kk++) {
+    int q, n;
+    lmax = ser_fmax(lmax, ser_item_eval(wt, st, pos, kk, &q, &n));
+  }
+  return lmax;
+}
+
+/* weight of item kk given the step's maximum */
+SER_HD double ser_item_weight(const SerWeights &wt, const SerStep &st, const uint16_t *pos, int kk, double lmax)
+{
+  int q, n, m; double ye;
+  const double le = SER_SUB(ser_item_eval(wt, st, pos, kk, &q, &n), lmax);
+  return ser_run_sum(wt, n, le, &m, &ye);
+}
+
+/* inside one run: s = cumulative weight before it; returns t in [0,n): the first candidate of
+ * the run whose cumulative weight reaches target (the last one if none does) */
+SER_HD int ser_run_pick(const SerWeights &wt, int n, double le, double s, double target)
+{
+  int m; double ye;
+  ser_run_sum(wt, n, le, &m, &ye);
+  const int nf = n - m; /* nf floored candidates of weight eps each, then m geometric ones */
+  const double sf = ser_fma(ser_i2d(nf), wt.eps, s);
+  if (nf > 0 && (sf >= target || m == 0)) {
+    const double td = SER_DIV(SER_SUB(target, s), wt.eps); /* ~ whole eps steps below the target */
+    int t = !(td > 0.0) ? 0 : (td >= (double)(nf - 1) ? nf - 1 : (int)td);
     while (t > 0 && ser_fma(ser_i2d(t), wt.eps, s) >= target) t--;
-    while (t < cnt - 1 && ser_fma(ser_i2d(t + 1), wt.eps, s) < target) t++;
-    return 32 * j + t;
+    while (t < nf - 1 && ser_fma(ser_i2d(t + 1), wt.eps, s) < target) t++;
+    return t;
   }
-  const int ob = (REV ? total - ser_rank1(col, pre, C, N - 32 * j) : (int)pre[j * C]) - o_cur;
-  double acc = ser_fma(ser_i2d(ob), wt.A, ser_fma(ser_i2d(32 * j), wt.g, c0));
-  uint32_t cuts = ser_logical_word<REV>(col, C, W, N, j) & ser_mask_lt(cnt - 1);
-  int ts = 0;
-  for (;;) {
-    const int te = cuts ? SER_FFS(cuts) - 1 : cnt - 1;
-    const int n = te - ts + 1;
-    int m; double ye;
-    const double snext = SER_ADD(s, ser_run_sum(wt, n, ser_fma(ser_i2d(te), wt.g, acc), &m, &ye));
-    if (snext >= target || !cuts) {
-      /* inside this run: nf floored candidates of weight eps each, then m geometric ones */
-      const int nf = n - m;
-      const double sf = ser_fma(ser_i2d(nf), wt.eps, s);
-      int t;
-      if (nf > 0 && (sf >= target || m == 0)) {
-        const double td = SER_DIV(SER_SUB(target, s), wt.eps); /* ~ whole eps steps below the target */
-        t = !(td > 0.0) ? 0 : (td >= (double)(nf - 1) ? nf - 1 : (int)td);
-        while (t > 0 && ser_fma(ser_i2d(t), wt.eps, s) >= target) t--;
-        while (t < nf - 1 && ser_fma(ser_i2d(t + 1), wt.eps, s) < target) t++;
-      } else {
-        /* cumulative weight through geometric candidate k (k = 0..m-1): sf + ye (H[m] - H[m-1-k]) */
-        int lo = 0, hi = m - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (ser_fma(ye, SER_SUB(wt.H[m], wt.H[m - 1 - mid]), sf) >= target) hi = mid; else lo = mid + 1;
-        }
-        t = nf + lo;
-      }
-      return 32 * j + ts + t;
-    }
-    s = snext;
-    cuts &= cuts - 1u;
-    acc = SER_ADD(acc, wt.A);
-    ts = te + 1;
+  /* cumulative weight through geometric candidate k (k = 0..m-1): sf + ye (H[m] - H[m-1-k]) */
+  int lo = 0, hi = m - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (ser_fma(ye, SER_SUB(wt.H[m], wt.H[m - 1 - mid]), sf) >= target) hi = mid; else lo = mid + 1;
   }
-#undef SER_OBELOW
+  return nf + lo;
+}
+
+/* the taxon's own part: val[0..kb] holds the item weights; turns them into cumulative sums,
+ * inverts the CDF (mcmc_randompick) and returns the picked candidate (logical index) */
+SER_HD int ser_step_pick(const SerWeights &wt, const SerStep &st, const uint16_t *pos, double *val, double lmax,
+                         double U)
+{
+  double S = 0.0;
+  for (int kk = 0; kk <= st.kb; kk++) { S = SER_ADD(S, val[kk]); val[kk] = S; }
+  const double target = SER_MUL(U, S);
+  int lo = 0, hi = st.kb; /* first item whose cumulative weight reaches the target */
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (val[mid] >= target) hi = mid; else lo = mid + 1;
+  }
+  int q, n;
+  const double le = SER_SUB(ser_item_eval(wt, st, pos, lo, &q, &n), lmax);
+  return q - n + 1 + ser_run_pick(wt, n, le, lo ? val[lo - 1] : 0.0, target);
 }
 
 /* ------------------------------------------------------------------ pi proposals */

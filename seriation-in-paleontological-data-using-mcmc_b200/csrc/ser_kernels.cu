@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -48,7 +49,11 @@ struct KParams {
   int N, M, W, C, nh, Mw, Npad, Mpad;
   const uint32_t *Xs;  /* [N][Mw] site-major bits */
   const uint8_t *hard; /* [N] file order */
-  const int *ones;     /* [M] ones per taxon */
+  const int *ones;     /* [M] ones per column */
+  const uint16_t *order;    /* [M] column -> taxon (columns are sorted by ones, descending) */
+  const int *off;           /* [M+1] first item of each column; a column has ones+1 items */
+  const uint16_t *item_col; /* [I] item -> column */
+  int I;                    /* ones_total + M */
   uint16_t *ab;        /* [chain][2][Mpad] */
   uint16_t *rpi;       /* [chain][Npad] */
   ChainScalars *scal;  /* [chain] */
@@ -72,23 +77,31 @@ struct Smem {
   double *H;        /* N + 2: geometric partial sums of the current sweep (ser_h_entry) */
   uint32_t *V;      /* W*C */
   int *red;         /* 2 * SER_MAX_WARPS * 4 */
+  double *val;      /* I+1: item weights of the running Gibbs step */
+  double *lmax;     /* C: per-column maximum log-weight of the running step */
+  uint16_t *pos;    /* I+1: ascending positions of the ones of every column (postings) */
+  uint16_t *st4;    /* 4*C: per-column step geometry: cur, bound, ocur, kb */
   uint16_t *pre;    /* (W+1)*C: pre[w][col] = ones of the column in words < w */
   uint16_t *hp;     /* N+1: hard positions, ascending */
   uint16_t *rpi, *tmp16, *perm16; /* N each */
 };
 
-__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C)
+__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C, int I)
 {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
   size_t o_H = take(sizeof(double) * (N + 2));
+  size_t o_val = take(sizeof(double) * (I + 1)), o_lm = take(sizeof(double) * C);
+  size_t o_pos = take(sizeof(uint16_t) * (I + 1)), o_st = take(sizeof(uint16_t) * 4 * C);
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
   size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
   if (s) {
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
     s->H = (double *)(base + o_H);
+    s->val = (double *)(base + o_val); s->lmax = (double *)(base + o_lm);
+    s->pos = (uint16_t *)(base + o_pos); s->st4 = (uint16_t *)(base + o_st);
     s->V = (uint32_t *)(base + o_v); s->red = (int *)(base + o_r); s->pre = (uint16_t *)(base + o_h); s->hp = (uint16_t *)(base + o_hp);
     s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q); s->perm16 = (uint16_t *)(base + o_m);
   }
@@ -167,7 +180,7 @@ __global__ void ser_init_kernel(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
-  const size_t used = smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+  const size_t used = smem_layout(&sm, smem_raw, p.N, p.W, p.C, 0);
   /* extra scratch behind the common layout: 2N staged draws, pi / rest / chosen as u16 */
   double *stage = (double *)(smem_raw + used);
   uint16_t *pi16 = (uint16_t *)(stage + 2 * p.N);
@@ -279,7 +292,7 @@ __device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, cons
       /* The integer totals cancel but single taxa changed: the reference's sequential float sum
        * (mcmc.c:1214/1435/1630) may leave a residual whose SIGN decides whether a draw is
        * consumed.  Re-create that sum exactly: per-taxon terms in taxon order. */
-      if (threadIdx.x < p.M) sm.terms[threadIdx.x] = ser_term(wt, dt0, dt1);
+      if (threadIdx.x < p.M) sm.terms[p.order[threadIdx.x]] = ser_term(wt, dt0, dt1);
       __syncthreads();
       for (int m = 0; m < p.M; m++) delta = SER_ADD(delta, sm.terms[m]);
     }
@@ -296,7 +309,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
-  smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I);
 
   const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
   const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
@@ -307,11 +320,12 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   /* ---- load chain state */
   ChainScalars sc = p.scal[chain];
   for (int n = tid; n < N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
-  int a = 0, b = 0, ones = 0;
+  int a = 0, b = 0, taxon = 0, off_c = 0;
   if (is_taxon) {
     a = p.ab[(size_t)chain * 2 * p.Mpad + tid];
     b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
-    ones = p.ones[tid];
+    taxon = p.order[tid]; /* the taxon this column holds: indexes the tape, the samples, terms[] */
+    off_c = p.off[tid];
   }
   __syncthreads();
   build_columns(p, sm);
@@ -335,7 +349,6 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   hd.hcol = sm.V + M; hd.hpre = sm.pre + M; hd.hp = sm.hp; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh;
   PropState ps;
   ps.k = 0; ps.buf = 0;
-  double ck[SER_MAXW + 1];
 
   for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
     for (int s = 0; s < p.sweeps_per_call; s++) {
@@ -350,7 +363,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
           const long long idx = need + t;
           sm.draws_pi[t] = idx < tape_len ? tape[idx] : 0.5;
         }
-        if (is_taxon) { ua = tape[sc.cursor + 6 + 2 * tid]; ub = tape[sc.cursor + 7 + 2 * tid]; }
+        if (is_taxon) { ua = tape[sc.cursor + 6 + 2 * taxon]; ub = tape[sc.cursor + 7 + 2 * taxon]; }
       } else {
         if (tid < 4) { /* Beta(1+f1a,1+t0a) and Beta(1+f0a,1+t1a) as Gamma ratios (mcmc.c:790, :820) */
           const int cnt = tid == 0 ? sc.f1a : tid == 1 ? sc.t0a : tid == 2 ? sc.f0a : sc.t1a;
@@ -371,7 +384,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
           sm.draws_pi[t] = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
         if (is_taxon) {
           uint32_t o[4];
-          ser_philox4x32_10((uint32_t)tid, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+          ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
           ua = ser_u53(o[0], o[1]); ub = ser_u53(o[2], o[3]);
         }
       }
@@ -393,18 +406,41 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
       for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
       __syncthreads();
 
-      /* ================= a/b Gibbs (mcmc_sampleab, mcmc.c:918-996) ================= */
-      int t1 = 0, len = 0, changed = 0;
-      if (is_taxon) {
-        const int na = ser_gibbs_boundary<false>(col, pre, C, W, N, a, b, ua, wt, ck);
-        changed += na != a;
-        a = na;
-        const int t = ser_gibbs_boundary<true>(col, pre, C, W, N, N - b, N - a, ub, wt, ck);
-        changed += (N - t) != b;
-        b = N - t;
-        t1 = ser_col_popc(col, pre, C, a, b);
-        len = b - a;
+      /* ================= a/b Gibbs (mcmc_sampleab, mcmc.c:918-996) =================
+       * item formulation (ser_chain_core.h): postings of the column, then for the a-step and
+       * the b-step: per-column maximum (own thread), item weights (dense over the CTA),
+       * per-column scan + inverse CDF (own thread). */
+      if (is_taxon) ser_expand_ones(col, C, W, sm.pos + off_c);
+      int changed = 0;
+#pragma unroll 1
+      for (int step = 0; step < 2; step++) {
+        SerStep st;
+        double lmax = 0.0;
+        if (is_taxon) {
+          st = step == 0 ? ser_step_a(col, pre, C, W, N, a, b) : ser_step_b(col, pre, C, W, N, a, b);
+          lmax = ser_step_lmax(wt, st, sm.pos + off_c);
+          sm.lmax[tid] = lmax;
+          sm.st4[4 * tid + 0] = (uint16_t)st.cur; sm.st4[4 * tid + 1] = (uint16_t)st.bound;
+          sm.st4[4 * tid + 2] = (uint16_t)st.ocur; sm.st4[4 * tid + 3] = (uint16_t)st.kb;
+        }
+        __syncthreads();
+        for (int e = tid; e < p.I; e += C) {
+          const int c = p.item_col[e];
+          const int oc = p.off[c], kk = e - oc;
+          SerStep it;
+          it.cur = sm.st4[4 * c + 0]; it.bound = sm.st4[4 * c + 1]; it.ocur = sm.st4[4 * c + 2]; it.kb = sm.st4[4 * c + 3];
+          it.nones = p.off[c + 1] - oc - 1; it.N = N; it.rev = step;
+          if (kk <= it.kb) sm.val[e] = ser_item_weight(wt, it, sm.pos + oc, kk, sm.lmax[c]);
+        }
+        __syncthreads();
+        if (is_taxon) {
+          const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + off_c, lmax, step == 0 ? ua : ub);
+          if (step == 0) { changed += pick != a; a = pick; }
+          else { changed += (N - pick) != b; b = N - pick; }
+        }
       }
+      int t1 = 0, len = 0;
+      if (is_taxon) { t1 = ser_col_popc(col, pre, C, a, b); len = b - a; }
       {
         int T1, LEN, CH;
         block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
@@ -509,7 +545,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
         if (p.store >= SER_STORE_PI)
           for (int pos = tid; pos < N; pos += C) p.samp_pi[row * N + sm.rpi[pos]] = (uint16_t)pos;
         if (p.store >= SER_STORE_FULL) {
-          if (is_taxon) { p.samp_a[row * M + tid] = (uint16_t)a; p.samp_b[row * M + tid] = (uint16_t)b; }
+          if (is_taxon) { p.samp_a[row * M + taxon] = (uint16_t)a; p.samp_b[row * M + taxon] = (uint16_t)b; }
           if (tid == 0) { p.samp_cdl[row * 3 + 0] = sc.c; p.samp_cdl[row * 3 + 1] = sc.d; p.samp_cdl[row * 3 + 2] = sc.loglik; }
         }
       }
@@ -528,7 +564,6 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   }
   for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
   if (tid == 0) p.scal[chain] = sc;
-  (void)ones;
 }
 
 /* ------------------------------------------------------------------ export / check kernels */
@@ -537,7 +572,7 @@ __global__ void ser_export_kernel(KParams p, int chain, int *out_a, int *out_b, 
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
-  smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I);
   const int tid = threadIdx.x, C = p.C;
   for (int n = tid; n < p.N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
   __syncthreads();
@@ -547,8 +582,9 @@ __global__ void ser_export_kernel(KParams p, int chain, int *out_a, int *out_b, 
     const int a = p.ab[(size_t)chain * 2 * p.Mpad + tid], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
     int t0, f0, t1, f1;
     ser_counts(sm.V + tid, sm.pre + tid, C, p.N, a, b, p.ones[tid], &t0, &f0, &t1, &f1);
-    out_a[tid] = a; out_b[tid] = b;
-    out_cnt[tid] = t0; out_cnt[p.M + tid] = f0; out_cnt[2 * p.M + tid] = t1; out_cnt[3 * p.M + tid] = f1;
+    const int tx = p.order[tid];
+    out_a[tx] = a; out_b[tx] = b;
+    out_cnt[tx] = t0; out_cnt[p.M + tx] = f0; out_cnt[2 * p.M + tx] = t1; out_cnt[3 * p.M + tx] = f1;
   }
 }
 
@@ -558,7 +594,7 @@ __global__ void ser_check_kernel(KParams p, int *bad_count)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
-  smem_layout(&sm, smem_raw, p.N, p.W, p.C);
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I);
   const int chain = blockIdx.x, tid = threadIdx.x, C = p.C, N = p.N, M = p.M;
   __shared__ int s_flags;
   if (tid == 0) s_flags = 0;
@@ -751,7 +787,8 @@ struct ser_run {
   uint8_t *h_hard;
   uint32_t *d_Xs;
   uint8_t *d_hard;
-  int *d_ones;
+  int *d_ones, *d_off;
+  uint16_t *d_order, *d_item_col;
   uint16_t *d_ab, *d_rpi;
   ChainScalars *d_scal;
   double *d_tape;
@@ -765,7 +802,7 @@ struct ser_run {
   int timing_open;
   double elapsed_ms;
   long long launches;
-  size_t smem_sweep, smem_init;
+  size_t smem_sweep, smem_init, smem_small;
   int initialized, have_tapes;
 };
 
@@ -811,13 +848,29 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   kp.cc0 = log(1. - exp(kp.c0)); kp.dd0 = log(1. - exp(kp.d0));
   kp.eps = exp(-32.236191301916641); /* exp(LOGEPSILON), mcmc.h:26 */
 
-  /* site-major bit matrix + per-taxon ones */
-  std::vector<uint32_t> Xs((size_t)N * kp.Mw, 0u);
-  std::vector<int> ones(M, 0);
+  /* Columns = taxa sorted by number of occurrences (descending), so that the threads of a warp
+   * own taxa with similar item counts; `order` maps a column back to its taxon.  Site-major bit
+   * matrix over columns, ones per column, and the static item tables of the Gibbs step. */
+  std::vector<int> tones(M, 0);
   long long ones_total = 0;
   for (int n = 0; n < N; n++)
     for (int m = 0; m < M; m++)
-      if (ds->X[(size_t)n * M + m]) { Xs[(size_t)n * kp.Mw + (m >> 5)] |= 1u << (m & 31); ones[m]++; ones_total++; }
+      if (ds->X[(size_t)n * M + m]) { tones[m]++; ones_total++; }
+  std::vector<uint16_t> order(M);
+  for (int m = 0; m < M; m++) order[m] = (uint16_t)m;
+  std::stable_sort(order.begin(), order.end(), [&](uint16_t x, uint16_t y) { return tones[x] > tones[y]; });
+  std::vector<uint32_t> Xs((size_t)N * kp.Mw, 0u);
+  std::vector<int> ones(M, 0), off(M + 1, 0);
+  for (int c = 0; c < M; c++) {
+    ones[c] = tones[order[c]];
+    off[c + 1] = off[c] + ones[c] + 1;
+    for (int n = 0; n < N; n++)
+      if (ds->X[(size_t)n * M + order[c]]) Xs[(size_t)n * kp.Mw + (c >> 5)] |= 1u << (c & 31);
+  }
+  kp.I = off[M];
+  std::vector<uint16_t> item_col(kp.I);
+  for (int c = 0; c < M; c++)
+    for (int e = off[c]; e < off[c + 1]; e++) item_col[e] = (uint16_t)c;
   kp.ones_total = ones_total;
   run->h_hard = (uint8_t *)malloc(N);
   memcpy(run->h_hard, ds->hard, N);
@@ -826,6 +879,9 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   CUDA_TRY(cudaMalloc(&run->d_Xs, Xs.size() * 4));
   CUDA_TRY(cudaMalloc(&run->d_hard, N));
   CUDA_TRY(cudaMalloc(&run->d_ones, M * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&run->d_off, (M + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&run->d_order, M * sizeof(uint16_t)));
+  CUDA_TRY(cudaMalloc(&run->d_item_col, (size_t)kp.I * sizeof(uint16_t)));
   CUDA_TRY(cudaMalloc(&run->d_ab, nc * 2 * kp.Mpad * sizeof(uint16_t)));
   CUDA_TRY(cudaMalloc(&run->d_rpi, nc * kp.Npad * sizeof(uint16_t)));
   CUDA_TRY(cudaMalloc(&run->d_scal, nc * sizeof(ChainScalars)));
@@ -834,6 +890,9 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   CUDA_TRY(cudaMemcpyAsync(run->d_Xs, Xs.data(), Xs.size() * 4, cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemcpyAsync(run->d_hard, ds->hard, N, cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemcpyAsync(run->d_ones, ones.data(), M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(run->d_off, off.data(), (M + 1) * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(run->d_order, order.data(), M * sizeof(uint16_t), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(run->d_item_col, item_col.data(), (size_t)kp.I * sizeof(uint16_t), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemsetAsync(run->d_scal, 0, nc * sizeof(ChainScalars), run->stream));
   CUDA_TRY(cudaStreamSynchronize(run->stream));
   if (cfg->store >= SER_STORE_PI && cfg->max_samples > 0) {
@@ -845,12 +904,14 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     CUDA_TRY(cudaMalloc(&run->d_samp_cdl, nc * cfg->max_samples * 3 * sizeof(double)));
   }
   kp.Xs = run->d_Xs; kp.hard = run->d_hard; kp.ones = run->d_ones;
+  kp.order = run->d_order; kp.off = run->d_off; kp.item_col = run->d_item_col;
   kp.ab = run->d_ab; kp.rpi = run->d_rpi; kp.scal = run->d_scal;
   kp.samp_a = run->d_samp_a; kp.samp_b = run->d_samp_b; kp.samp_pi = run->d_samp_pi; kp.samp_cdl = run->d_samp_cdl;
 
-  run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C);
-  run->smem_init = run->smem_sweep + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
-  if (run->smem_init > 227 * 1024) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_init); return SER_E_ARG; }
+  run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
+  run->smem_small = smem_layout(nullptr, nullptr, N, run->W, run->C, 0);
+  run->smem_init = run->smem_small + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
+  if (run->smem_init > 227 * 1024 || run->smem_sweep > 227 * 1024) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_init); return SER_E_ARG; }
   CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
   CUDA_TRY(cudaFuncSetAttribute(ser_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_init));
   CUDA_TRY(cudaFuncSetAttribute(ser_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
@@ -864,7 +925,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   if (!run) return;
   cudaSetDevice(run->cfg.device);
   cudaStreamSynchronize(run->stream);
-  cudaFree(run->d_Xs); cudaFree(run->d_hard); cudaFree(run->d_ones); cudaFree(run->d_ab); cudaFree(run->d_rpi);
+  cudaFree(run->d_Xs); cudaFree(run->d_hard); cudaFree(run->d_ones); cudaFree(run->d_off); cudaFree(run->d_order); cudaFree(run->d_item_col); cudaFree(run->d_ab); cudaFree(run->d_rpi);
   cudaFree(run->d_scal); cudaFree(run->d_tape); cudaFree(run->d_tape_off); cudaFree(run->d_samp_a);
   cudaFree(run->d_samp_b); cudaFree(run->d_samp_pi); cudaFree(run->d_samp_cdl); cudaFree(run->d_scratch_i);
   cudaFree(run->d_bad);

@@ -200,16 +200,31 @@ void sample_cd(Chain &ch) {
 }
 
 int sample_ab(Chain &ch) {
+  // item formulation: (1) postings of every column, (2) per step: per-taxon maximum, dense item
+  // weights, per-taxon scan + pick -- the loops below are the kernel's phases run sequentially
   int changed = 0;
-  std::vector<double> ck(ch.W + 1);
-  for (int m = 0; m < ch.M; m++) {
-    const double ua = ch.next(), ub = ch.next();
-    const int na = ser_gibbs_boundary<false>(ch.col(m), ch.pcol(m), ch.C, ch.W, ch.N, ch.a[m], ch.b[m], ua, ch.wt, ck.data());
-    changed += na != ch.a[m];
-    ch.a[m] = na;
-    const int t = ser_gibbs_boundary<true>(ch.col(m), ch.pcol(m), ch.C, ch.W, ch.N, ch.N - ch.b[m], ch.N - ch.a[m], ub, ch.wt, ck.data());
-    changed += (ch.N - t) != ch.b[m];
-    ch.b[m] = ch.N - t;
+  const int M = ch.M, C = ch.C, W = ch.W, N = ch.N;
+  std::vector<int> off(M + 1, 0);
+  for (int m = 0; m < M; m++) off[m + 1] = off[m] + ch.ones[m] + 1;
+  std::vector<uint16_t> pos(off[M] + 1);
+  std::vector<double> val(off[M] + 1), lmax(M), ua(M), ub(M);
+  std::vector<SerStep> st(M);
+  for (int m = 0; m < M; m++) { ua[m] = ch.next(); ub[m] = ch.next(); }
+  for (int m = 0; m < M; m++) ser_expand_ones(ch.col(m), C, W, pos.data() + off[m]);
+  for (int step = 0; step < 2; step++) {
+    for (int m = 0; m < M; m++) {
+      st[m] = step == 0 ? ser_step_a(ch.col(m), ch.pcol(m), C, W, N, ch.a[m], ch.b[m])
+                        : ser_step_b(ch.col(m), ch.pcol(m), C, W, N, ch.a[m], ch.b[m]);
+      lmax[m] = ser_step_lmax(ch.wt, st[m], pos.data() + off[m]);
+    }
+    for (int m = 0; m < M; m++)          // dense over items in the kernel
+      for (int kk = 0; kk <= st[m].kb; kk++)
+        val[off[m] + kk] = ser_item_weight(ch.wt, st[m], pos.data() + off[m], kk, lmax[m]);
+    for (int m = 0; m < M; m++) {
+      const int pick = ser_step_pick(ch.wt, st[m], pos.data() + off[m], val.data() + off[m], lmax[m], step == 0 ? ua[m] : ub[m]);
+      if (step == 0) { changed += pick != ch.a[m]; ch.a[m] = pick; }
+      else { changed += (N - pick) != ch.b[m]; ch.b[m] = N - pick; }
+    }
   }
   ch.totals();
   return changed;
