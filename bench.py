@@ -269,14 +269,19 @@ def main():
     run.close()
 
     # end-to-end arm
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         step_e2e()
     barrier()
     t1 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         step_e2e()
+        e2e_steps.append(time.perf_counter() - ts)
     barrier()
     dt_e2e = time.perf_counter() - t1
+    if rank == 0:
+        print("e2e step times (ms): " + " ".join("%.1f" % (1e3 * v) for v in e2e_steps), file=sys.stderr)
 
     t = torch.tensor([dt, dt_e2e, sum(sweep_ms) / max(1, len(sweep_ms))], dtype=torch.float64, device=dev)
     if world > 1:

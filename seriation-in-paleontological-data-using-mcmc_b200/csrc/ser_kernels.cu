@@ -72,6 +72,7 @@ struct KParams {
 /* ------------------------------------------------------------------ shared-memory carve-up */
 struct Smem {
   double *draws_pi; /* SER_PI_DRAWS */
+  double *logdraw;  /* SER_PI_DRAWS: log of each staged draw (only read where a draw is a U+) */
   double *draws_cd; /* 8 */
   double *terms;    /* C */
   double *H;        /* N + 2: geometric partial sums of the current sweep (ser_h_entry) */
@@ -90,6 +91,7 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
 {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  size_t o_ld = take(sizeof(double) * SER_PI_DRAWS);
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
   size_t o_H = take(sizeof(double) * (N + 2));
   size_t o_val = take(sizeof(double) * (I + 1)), o_lm = take(sizeof(double) * C);
@@ -98,6 +100,7 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
   size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
   if (s) {
+    s->logdraw = (double *)(base + o_ld);
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
     s->H = (double *)(base + o_H);
     s->val = (double *)(base + o_val); s->lmax = (double *)(base + o_lm);
@@ -301,8 +304,7 @@ __device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, cons
   }
   *delta_out = delta;
   if (delta >= 0.0) return true;
-  const double u = sm.draws_pi[ps.k++];
-  return delta > log(u);
+  return delta > sm.logdraw[ps.k++];
 }
 
 __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
@@ -361,7 +363,9 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
         if (tid < 6) sm.draws_cd[tid] = tape[sc.cursor + tid];
         for (int t = tid; t < SER_PI_DRAWS; t += C) {
           const long long idx = need + t;
-          sm.draws_pi[t] = idx < tape_len ? tape[idx] : 0.5;
+          const double u = idx < tape_len ? tape[idx] : 0.5;
+          sm.draws_pi[t] = u;
+          sm.logdraw[t] = log(u);
         }
         if (is_taxon) { ua = tape[sc.cursor + 6 + 2 * taxon]; ub = tape[sc.cursor + 7 + 2 * taxon]; }
       } else {
@@ -380,8 +384,11 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
             sm.draws_cd[tid] = val; sm.draws_cd[tid + 1] = l1m;
           }
         }
-        for (int t = tid; t < SER_PI_DRAWS; t += C)
-          sm.draws_pi[t] = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+        for (int t = tid; t < SER_PI_DRAWS; t += C) {
+          const double u = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+          sm.draws_pi[t] = u;
+          sm.logdraw[t] = log(ser_pos(u));
+        }
         if (is_taxon) {
           uint32_t o[4];
           ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
