@@ -1,0 +1,194 @@
+/*
+ * mcmc_main.c -- the `mcmc` command line over the C ABI (host code stays in C).
+ *
+ * Drop-in for the reference binary's contract (C_Implementation/mcmc.c:102-210, called by
+ * script.py:44-45 as `./mcmc <chain_index> < dataset.txt` with GSL_RNG_SEED in the environment):
+ *   - argv[1] = chain index -> files go to Chains/chain_XX/ (two digits, like mcmc.c:148-178)
+ *   - stdin   = dataset in the reference's .txt format
+ *   - 1000 burn-in + 1000 sampling calls of 10 sweeps, one thinned sample per call
+ *   - writes chain_data.csv, exp_data.csv, taxa.csv, sites.csv, hard_sites.csv
+ *   - stderr echoes "GSL_RNG_SEED=<n>" like gsl_rng_env_setup(); exit 0 / 1
+ * Differences, all deliberate: the random stream is the structured Philox stream keyed by
+ * (GSL_RNG_SEED, chain index) instead of GSL's MT19937; Chains/chain_XX/ is created when missing
+ * (the reference dereferences a NULL FILE*); `mcmc` without arguments prints usage instead of
+ * crashing at atoi(NULL) (mcmc.c:153); `manycd=1` is refused (out of scope).
+ *
+ * Batch mode (replaces script.py's Pool over 100 processes by one launch):
+ *   mcmc --chains N [--first I] [--burn B] [--samples S] [--seed X] [--dataset file]
+ *        [--chains-dir DIR] [--select K] [--po file.csv] [--device D]
+ * Replay mode: SER_TAPE_IN=<file of raw doubles> mcmc <idx> < dataset.txt
+ */
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include "../../include/seriation_b200.h"
+
+static void die(const char *what)
+{
+  fprintf(stderr, "mcmc: %s: %s\n", what, ser_last_error());
+  exit(1);
+}
+
+static void usage(const char *argv0)
+{
+  fprintf(stderr,
+          "usage: %s <chain_index> < dataset.txt          (reference-compatible single chain)\n"
+          "       %s [manycd Tburnin T] < dataset.txt      (manycd must be 0; chain 0)\n"
+          "       %s --chains N [--first I] [--burn B] [--samples S] [--seed X] [--dataset F]\n"
+          "              [--chains-dir DIR] [--select K] [--po out.csv] [--device D]\n",
+          argv0, argv0, argv0);
+  exit(1);
+}
+
+static double *read_tape(const char *path, uint64_t *len)
+{
+  FILE *f = fopen(path, "rb");
+  long sz;
+  double *buf;
+  if (!f) { fprintf(stderr, "mcmc: cannot open tape %s\n", path); exit(1); }
+  fseek(f, 0, SEEK_END);
+  sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  buf = (double *)malloc((size_t)sz + 8);
+  if (!buf || fread(buf, 1, (size_t)sz, f) != (size_t)sz) { fprintf(stderr, "mcmc: cannot read tape %s\n", path); exit(1); }
+  fclose(f);
+  *len = (uint64_t)sz / sizeof(double);
+  return buf;
+}
+
+int main(int argc, char **argv)
+{
+  int n_chains = 1, first = 0, burn = 1000, samples = 1000, select_k = 0, device = 0, batch = 0, i;
+  unsigned long seed = 0;
+  const char *dataset = NULL, *chains_dir = "Chains", *po_path = NULL, *tape_path = getenv("SER_TAPE_IN");
+  const char *env_seed = getenv("GSL_RNG_SEED");
+  ser_dataset *ds = NULL;
+  ser_run *run = NULL;
+  ser_run_config cfg;
+  int32_t N, M, nh, bad = 0;
+
+  if (env_seed) {
+    seed = strtoul(env_seed, NULL, 0);
+    fprintf(stderr, "GSL_RNG_SEED=%lu\n", seed);
+  }
+  if (argc == 1) usage(argv[0]);
+  if (argv[1][0] == '-') {
+    batch = 1;
+    for (i = 1; i < argc; i++) {
+      const char *a = argv[i], *v = (i + 1 < argc) ? argv[i + 1] : NULL;
+      if (!v) usage(argv[0]);
+      if (!strcmp(a, "--chains")) n_chains = atoi(v);
+      else if (!strcmp(a, "--first")) first = atoi(v);
+      else if (!strcmp(a, "--burn")) burn = atoi(v);
+      else if (!strcmp(a, "--samples")) samples = atoi(v);
+      else if (!strcmp(a, "--seed")) seed = strtoul(v, NULL, 0);
+      else if (!strcmp(a, "--dataset")) dataset = v;
+      else if (!strcmp(a, "--chains-dir")) chains_dir = v;
+      else if (!strcmp(a, "--select")) select_k = atoi(v);
+      else if (!strcmp(a, "--po")) po_path = v;
+      else if (!strcmp(a, "--device")) device = atoi(v);
+      else usage(argv[0]);
+      i++;
+    }
+    if (n_chains < 1 || burn < 0 || samples < 0) usage(argv[0]);
+  } else if (argc == 2) {
+    first = atoi(argv[1]); /* mcmc.c:115,153 */
+  } else if (argc == 4) {
+    int manycd = 0;
+    if (!(sscanf(argv[1], "%d", &manycd) == 1 && sscanf(argv[2], "%d", &burn) == 1 && burn >= 0 &&
+          sscanf(argv[3], "%d", &samples) == 1 && samples >= 0))
+      usage(argv[0]);
+    if (manycd) { fprintf(stderr, "mcmc: manycd=1 (per-taxon c, d) is not supported by this build\n"); return 1; }
+  } else {
+    usage(argv[0]);
+  }
+
+  if (ser_dataset_read_txt(dataset, &ds)) { fprintf(stderr, "%s\n", ser_last_error()); return 1; } /* mcmc_readmodel's messages */
+  ser_dataset_dims(ds, &N, &M, &nh);
+
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.n_chains = n_chains;
+  cfg.chain_offset = first;
+  cfg.sweeps_per_call = 10;
+  cfg.mode = tape_path ? SER_MODE_REPLAY : SER_MODE_FREE;
+  cfg.seed = (uint32_t)seed;
+  cfg.store = (n_chains <= 100) ? SER_STORE_FULL : SER_STORE_PI;
+  cfg.max_samples = samples;
+  cfg.device = device;
+  if (ser_run_create(ds, &cfg, &run)) die("ser_run_create");
+  if (tape_path) {
+    uint64_t offs[2] = {0, 0};
+    double *tape;
+    if (n_chains != 1) { fprintf(stderr, "mcmc: SER_TAPE_IN drives exactly one chain\n"); return 1; }
+    tape = read_tape(tape_path, &offs[1]);
+    if (ser_run_set_tapes(run, tape, offs)) die("ser_run_set_tapes");
+    free(tape);
+  }
+  if (ser_run_init(run)) die("ser_run_init");
+  if (ser_run_advance(run, burn, 0)) die("burn-in");      /* mcmc.c:140-143 */
+  if (ser_run_advance(run, samples, 1)) die("sampling");  /* mcmc.c:180-185 */
+  if (ser_run_sync(run)) die("ser_run_sync");
+  if (ser_run_check(run, &bad)) { /* mcmc_consistent at exit, mcmc.c:199-204 */
+    fprintf(stderr, "main: error. (%s)\n", ser_last_error());
+    return 1;
+  }
+
+  /* Chains/chain_XX/ for the chains whose index has a two-digit directory */
+  if (cfg.store == SER_STORE_FULL) {
+    mkdir(chains_dir, 0777);
+    for (i = 0; i < n_chains; i++) {
+      char dir[1024];
+      const int idx = first + i;
+      if (idx < 0 || idx > 99) continue; /* the reference's directory name has two digits (mcmc.c:148-178) */
+      snprintf(dir, sizeof(dir), "%s/chain_%02d", chains_dir, idx);
+      if (mkdir(dir, 0777) && errno != EEXIST) { fprintf(stderr, "mcmc: cannot create %s\n", dir); return 1; }
+      if (ser_write_chain_files(run, i, dir)) die("ser_write_chain_files");
+    }
+  }
+
+  if (batch) {
+    double *e = (double *)malloc(sizeof(double) * (size_t)n_chains), *ec = (double *)malloc(sizeof(double) * (size_t)n_chains);
+    double *ed = (double *)malloc(sizeof(double) * (size_t)n_chains), ms = 0.0;
+    int32_t ns = 0;
+    if (ser_run_chain_stats(run, e, ec, ed, &ns)) die("ser_run_chain_stats");
+    ser_run_elapsed_ms(run, &ms, 0);
+    printf("chains %d  sites %d  taxa %d  hard %d  sweeps/chain %d  gpu_ms %.1f  sweeps/s %.0f\n", n_chains, N, M, nh,
+           (burn + samples) * 10, ms, ms > 0 ? (double)n_chains * (burn + samples) * 10 / (ms * 1e-3) : 0.0);
+    if (select_k > 0) {
+      int32_t *chosen = (int32_t *)malloc(sizeof(int32_t) * (size_t)select_k), nchosen = 0;
+      double mn, sd;
+      if (ser_select_chains(e, n_chains, select_k, chosen, &nchosen, &mn, &sd)) die("ser_select_chains");
+      printf("selection: min E[-logL] %.6f  sigma %.6f  chosen", mn, sd);
+      for (i = 0; i < nchosen; i++) printf(" %d", first + chosen[i]);
+      printf("\n");
+      if (nchosen > 0) {
+        double sc = 0.0, sdd = 0.0;
+        for (i = 0; i < nchosen; i++) { sc += ec[chosen[i]]; sdd += ed[chosen[i]]; }
+        printf("E[c] %.6f  E[d] %.6f over the chosen chains\n", sc / nchosen, sdd / nchosen);
+      }
+      if (po_path && nchosen > 0) {
+        int32_t *global = (int32_t *)malloc(sizeof(int32_t) * (size_t)nchosen);
+        int32_t *counts = (int32_t *)calloc((size_t)nchosen * N * N, sizeof(int32_t));
+        double *po = (double *)malloc(sizeof(double) * (size_t)N * N);
+        FILE *f;
+        int r, c;
+        for (i = 0; i < nchosen; i++) global[i] = first + chosen[i];
+        if (ser_run_po_counts(run, global, nchosen, counts)) die("ser_run_po_counts");
+        if (ser_po_finalize(counts, nchosen, N, select_k, 1, po)) die("ser_po_finalize");
+        if (!(f = fopen(po_path, "w"))) { fprintf(stderr, "mcmc: cannot open %s\n", po_path); return 1; }
+        for (r = 0; r < N; r++)
+          for (c = 0; c < N; c++) fprintf(f, "%.6f%c", po[(size_t)r * N + c], c + 1 < N ? ',' : '\n');
+        fclose(f);
+        free(global); free(counts); free(po);
+      }
+      free(chosen);
+    }
+    free(e); free(ec); free(ed);
+  }
+  ser_run_destroy(run);
+  ser_dataset_free(ds);
+  return 0;
+}

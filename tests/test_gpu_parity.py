@@ -226,3 +226,64 @@ def test_reference_file_writers(S, oracle_mod, tmp_path):
     assert sites[0] == "sites" and [int(v) for v in sites[1:N + 1]] == final.pi.tolist()
     hs = (tmp_path / "hard_sites.csv").read_text().split("\n")
     assert hs[0] == "i,pi_i" and len(hs) == int(hard.sum()) + 2
+
+
+def test_cli_drop_in_full_length_vs_reference_cli(S, oracle_mod, tmp_path):
+    """`mcmc 7 < g10s10.txt`, the call script.py:44-45 makes: the UNMODIFIED reference main()
+    (1000 + 1000 calls = 20 000 sweeps, files under Chains/chain_07/) against this repo's `mcmc`
+    replaying the tape the reference recorded.  Everything script.py reads is byte-identical;
+    only the printed log-likelihood may differ in its last digits (1e-9 relative bar)."""
+    import subprocess
+    from tools.datasets import write_txt
+    if not oracle_mod.ref_available():
+        pytest.skip("oracle/_ref/ref_mcmc not built")
+    X, hard = load_hex_dataset("g10s10")
+    ds = tmp_path / "g10s10.txt"
+    write_txt(str(ds), X, hard)
+    ref_dir, our_dir, tape = tmp_path / "ref", tmp_path / "ours", tmp_path / "tape.bin"
+    (ref_dir / "Chains" / "chain_07").mkdir(parents=True)
+    our_dir.mkdir()
+    env = dict(os.environ, GSL_RNG_SEED="5", SER_TAPE_OUT=str(tape))
+    with open(ds) as f:
+        subprocess.run([oracle_mod.REF_BIN, "cli", "7"], stdin=f, cwd=ref_dir, env=env, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    env = dict(os.environ, SER_TAPE_IN=str(tape))
+    env.pop("GSL_RNG_SEED", None)
+    with open(ds) as f:
+        subprocess.run([os.path.join(S.PKG_DIR, "mcmc"), "7"], stdin=f, cwd=our_dir, env=env, check=True)
+    r, o = ref_dir / "Chains" / "chain_07", our_dir / "Chains" / "chain_07"
+    for name in ("taxa.csv", "sites.csv", "hard_sites.csv"):
+        assert (r / name).read_bytes() == (o / name).read_bytes(), name
+    rl, ol = (r / "chain_data.csv").read_text().split("\n"), (o / "chain_data.csv").read_text().split("\n")
+    assert len(rl) == len(ol) == 1001
+    for a, b in zip(rl[:-1], ol[:-1]):
+        fa, fb = a.split(","), b.split(",")
+        assert fa[:5] == fb[:5]                                  # a, b, pi, exp(c), exp(d): byte-identical
+        assert abs(float(fa[5]) - float(fb[5])) <= LL_RTOL * abs(float(fa[5]))
+    re_, oe = (r / "exp_data.csv").read_text().split("\n"), (o / "exp_data.csv").read_text().split("\n")
+    assert re_[0] == oe[0]
+    rv, ov = [float(v) for v in re_[1].split(",")], [float(v) for v in oe[1].split(",")]
+    assert abs(rv[0] - ov[0]) <= LL_RTOL * abs(rv[0]) and abs(rv[1] - ov[1]) < 1e-13 and abs(rv[2] - ov[2]) < 1e-13
+
+
+def test_cli_batch_mode(S, tmp_path):
+    import subprocess
+    from tools.datasets import write_txt
+    X, hard = load_hex_dataset("g10s10")
+    ds = tmp_path / "g10s10.txt"
+    write_txt(str(ds), X, hard)
+    out = subprocess.run([os.path.join(S.PKG_DIR, "mcmc"), "--chains", "12", "--burn", "20", "--samples", "10", "--seed", "9",
+                          "--dataset", str(ds), "--chains-dir", str(tmp_path / "Chains"), "--select", "3",
+                          "--po", str(tmp_path / "po.csv")], check=True, capture_output=True, text=True).stdout
+    assert "selection:" in out and "sweeps/s" in out
+    assert sorted(os.listdir(tmp_path / "Chains")) == ["chain_%02d" % i for i in range(12)]
+    po = np.loadtxt(tmp_path / "po.csv", delimiter=",")
+    assert po.shape == (124, 124) and np.all(np.diag(po) < 0)
+    # the same chains through the Python mirror of script.py
+    batch = S.run_all_chains(str(ds), 12, 20, 10, seed=9)
+    e = batch.stats()["e_negloglik"]
+    first = float((tmp_path / "Chains" / "chain_00" / "exp_data.csv").read_text().split("\n")[1].split(",")[0])
+    assert abs(first - e[0] * 10 / 1000) < 1e-6   # print_exp_data divides by the literal 1000
+    chosen = S.choose_chains(batch, 3)
+    assert ("chosen " + " ".join(str(c) for c in chosen)) in out
+    assert np.allclose(S.compute_pair_order_matrix(batch, chosen, 3), po, atol=1e-6)
