@@ -813,6 +813,27 @@ struct ser_run {
   int initialized, have_tapes;
 };
 
+/* Stream-ordered pool allocation: cudaMalloc/cudaFree are synchronous driver calls with erratic
+ * latency (tens to hundreds of ms on shared hosts); the default memory pool with an unlimited
+ * release threshold keeps freed blocks cached, so creating / destroying runs and the temporary
+ * buffers of the cross-chain steps cost microseconds after the first use. */
+static cudaError_t pool_alloc(void **ptr, size_t bytes, cudaStream_t stream)
+{
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    configured[dev] = true;
+  }
+  return cudaMallocAsync(ptr, bytes ? bytes : 1, stream);
+}
+#define POOL_ALLOC(ptr, bytes) pool_alloc((void **)(ptr), (bytes), run->stream)
+
 static int set_device(const ser_run *run) { CUDA_TRY(cudaSetDevice(run->cfg.device)); return SER_OK; }
 
 static void mark_launch(ser_run *run)
@@ -883,17 +904,17 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   memcpy(run->h_hard, ds->hard, N);
 
   const size_t nc = (size_t)cfg->n_chains;
-  CUDA_TRY(cudaMalloc(&run->d_Xs, Xs.size() * 4));
-  CUDA_TRY(cudaMalloc(&run->d_hard, N));
-  CUDA_TRY(cudaMalloc(&run->d_ones, M * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&run->d_off, (M + 1) * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&run->d_order, M * sizeof(uint16_t)));
-  CUDA_TRY(cudaMalloc(&run->d_item_col, (size_t)kp.I * sizeof(uint16_t)));
-  CUDA_TRY(cudaMalloc(&run->d_ab, nc * 2 * kp.Mpad * sizeof(uint16_t)));
-  CUDA_TRY(cudaMalloc(&run->d_rpi, nc * kp.Npad * sizeof(uint16_t)));
-  CUDA_TRY(cudaMalloc(&run->d_scal, nc * sizeof(ChainScalars)));
-  CUDA_TRY(cudaMalloc(&run->d_scratch_i, (size_t)(2 * N + 6 * M + 16) * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&run->d_bad, sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&run->d_Xs, Xs.size() * 4));
+  CUDA_TRY(POOL_ALLOC(&run->d_hard, N));
+  CUDA_TRY(POOL_ALLOC(&run->d_ones, M * sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&run->d_off, (M + 1) * sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&run->d_order, M * sizeof(uint16_t)));
+  CUDA_TRY(POOL_ALLOC(&run->d_item_col, (size_t)kp.I * sizeof(uint16_t)));
+  CUDA_TRY(POOL_ALLOC(&run->d_ab, nc * 2 * kp.Mpad * sizeof(uint16_t)));
+  CUDA_TRY(POOL_ALLOC(&run->d_rpi, nc * kp.Npad * sizeof(uint16_t)));
+  CUDA_TRY(POOL_ALLOC(&run->d_scal, nc * sizeof(ChainScalars)));
+  CUDA_TRY(POOL_ALLOC(&run->d_scratch_i, (size_t)(2 * N + 6 * M + 16) * sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&run->d_bad, sizeof(int)));
   CUDA_TRY(cudaMemcpyAsync(run->d_Xs, Xs.data(), Xs.size() * 4, cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemcpyAsync(run->d_hard, ds->hard, N, cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemcpyAsync(run->d_ones, ones.data(), M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
@@ -903,12 +924,12 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   CUDA_TRY(cudaMemsetAsync(run->d_scal, 0, nc * sizeof(ChainScalars), run->stream));
   CUDA_TRY(cudaStreamSynchronize(run->stream));
   if (cfg->store >= SER_STORE_PI && cfg->max_samples > 0) {
-    CUDA_TRY(cudaMalloc(&run->d_samp_pi, nc * cfg->max_samples * N * sizeof(uint16_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_samp_pi, nc * cfg->max_samples * N * sizeof(uint16_t)));
   }
   if (cfg->store >= SER_STORE_FULL && cfg->max_samples > 0) {
-    CUDA_TRY(cudaMalloc(&run->d_samp_a, nc * cfg->max_samples * M * sizeof(uint16_t)));
-    CUDA_TRY(cudaMalloc(&run->d_samp_b, nc * cfg->max_samples * M * sizeof(uint16_t)));
-    CUDA_TRY(cudaMalloc(&run->d_samp_cdl, nc * cfg->max_samples * 3 * sizeof(double)));
+    CUDA_TRY(POOL_ALLOC(&run->d_samp_a, nc * cfg->max_samples * M * sizeof(uint16_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_samp_b, nc * cfg->max_samples * M * sizeof(uint16_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_samp_cdl, nc * cfg->max_samples * 3 * sizeof(double)));
   }
   kp.Xs = run->d_Xs; kp.hard = run->d_hard; kp.ones = run->d_ones;
   kp.order = run->d_order; kp.off = run->d_off; kp.item_col = run->d_item_col;
@@ -931,11 +952,11 @@ extern "C" void ser_run_destroy(ser_run *run)
 {
   if (!run) return;
   cudaSetDevice(run->cfg.device);
+  void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
+                  run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
+                  run->d_scratch_i, run->d_bad};
+  for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   cudaStreamSynchronize(run->stream);
-  cudaFree(run->d_Xs); cudaFree(run->d_hard); cudaFree(run->d_ones); cudaFree(run->d_off); cudaFree(run->d_order); cudaFree(run->d_item_col); cudaFree(run->d_ab); cudaFree(run->d_rpi);
-  cudaFree(run->d_scal); cudaFree(run->d_tape); cudaFree(run->d_tape_off); cudaFree(run->d_samp_a);
-  cudaFree(run->d_samp_b); cudaFree(run->d_samp_pi); cudaFree(run->d_samp_cdl); cudaFree(run->d_scratch_i);
-  cudaFree(run->d_bad);
   cudaEventDestroy(run->ev_start); cudaEventDestroy(run->ev_stop);
   cudaStreamDestroy(run->stream);
   free(run->h_hard);
@@ -959,10 +980,11 @@ extern "C" int ser_run_set_tapes(ser_run *run, const double *flat, const uint64_
   if (run->cfg.mode != SER_MODE_REPLAY) { ser_set_error("ser_run_set_tapes: run is not in replay mode"); return SER_E_STATE; }
   if (set_device(run)) return SER_E_CUDA;
   const size_t nc = (size_t)run->cfg.n_chains, total = (size_t)offsets[nc];
-  cudaFree(run->d_tape); cudaFree(run->d_tape_off);
+  if (run->d_tape) cudaFreeAsync(run->d_tape, run->stream);
+  if (run->d_tape_off) cudaFreeAsync(run->d_tape_off, run->stream);
   run->d_tape = nullptr; run->d_tape_off = nullptr;
-  CUDA_TRY(cudaMalloc(&run->d_tape, (total ? total : 1) * sizeof(double)));
-  CUDA_TRY(cudaMalloc(&run->d_tape_off, (nc + 1) * sizeof(unsigned long long)));
+  CUDA_TRY(POOL_ALLOC(&run->d_tape, (total ? total : 1) * sizeof(double)));
+  CUDA_TRY(POOL_ALLOC(&run->d_tape_off, (nc + 1) * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemcpyAsync(run->d_tape, flat, total * sizeof(double), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemcpyAsync(run->d_tape_off, offsets, (nc + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaStreamSynchronize(run->stream));
@@ -1211,8 +1233,8 @@ extern "C" int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k,
   if (set_device(run)) return SER_E_CUDA;
   int *d_ch = nullptr, *d_cnt = nullptr;
   const size_t nn = (size_t)k * run->N * run->N;
-  CUDA_TRY(cudaMalloc(&d_ch, k * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&d_cnt, nn * sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&d_ch, k * sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&d_cnt, nn * sizeof(int)));
   CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemsetAsync(d_cnt, 0, nn * sizeof(int), run->stream));
   int rc = ser_run_po_counts_device(run, d_ch, k, d_cnt);
@@ -1220,7 +1242,7 @@ extern "C" int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k,
     if (cudaMemcpyAsync(counts, d_cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, run->stream) != cudaSuccess ||
         cudaStreamSynchronize(run->stream) != cudaSuccess) { ser_set_error("ser_run_po_counts: copy back failed"); rc = SER_E_CUDA; }
   }
-  cudaFree(d_ch); cudaFree(d_cnt);
+  cudaFreeAsync(d_ch, run->stream); cudaFreeAsync(d_cnt, run->stream);
   return rc;
 }
 
