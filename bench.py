@@ -237,15 +237,8 @@ def main():
                     max_samples=args.sample_calls, device=local)
         run.init().advance(args.burn_calls, False).advance(args.sample_calls, True)
         st = run.chain_stats()                                    # D2H: per-chain scalars
-        if world > 1:
-            e_all = [None] * world
-            dist.all_gather_object(e_all, st["e_negloglik"])
-            e = np.concatenate(e_all)
-        else:
-            e = st["e_negloglik"]
-        chosen, _, _ = S.select_chains(e, k)
-        counts = run.po_counts(np.pad(chosen, (0, k - len(chosen)), constant_values=-1))  # D2H: k x N x N
-        po = S.po_finalize(counts, k)
+        # host buffers -> (all-gather) -> choose_chains -> PO counts (D2H k x N x N) -> (all-reduce) -> PO matrix
+        chosen, po = S.cross_chain_distributed(st["e_negloglik"], k, run.po_counts, N)
         run.close()
         return float(po[0, 1])
 

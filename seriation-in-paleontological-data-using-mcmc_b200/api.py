@@ -350,3 +350,39 @@ def compute_exp_cd(batch: ChainBatch, chains, chains_selected: int):
     st = batch.stats()
     return (float(np.sum(st["e_c"][list(chains)]) / chains_selected),
             float(np.sum(st["e_d"][list(chains)]) / chains_selected))
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-rank cross-chain step (host buffers; any torch.distributed backend)
+def cross_chain_distributed(e_local, k: int, po_counts_fn, n_sites: int, chains_selected: int | None = None,
+                            faithful: bool = True):
+    """Selection + pair-order matrix when the chains are sharded over ranks.
+
+    ``e_local``: this rank's E[-logL] (global chain id = rank * len(e_local) + i);
+    ``po_counts_fn(chosen_global_ids) -> int32 [k][N][N]`` fills the slabs of the chains this rank
+    owns and leaves the others zero (Run.po_counts does exactly that).
+    The exchange is what the path needs and nothing more: one all-gather of 8 bytes per chain, one
+    all-reduce(sum) of the count slabs.  Without an initialised process group it degrades to the
+    single-rank case.  Returns (chosen global ids, po matrix)."""
+    import torch
+    import torch.distributed as dist
+    e_local = np.ascontiguousarray(e_local, dtype=np.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        world = dist.get_world_size()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.from_numpy(e_local).to(dev)
+        allv = torch.empty(world * e_local.size, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allv, mine)
+        e_all = allv.cpu().numpy()
+    else:
+        dev, e_all = "cpu", e_local
+    chosen, _, _ = select_chains(e_all, k)
+    padded = np.full(k, -1, np.int32)
+    padded[:len(chosen)] = chosen
+    counts = np.ascontiguousarray(po_counts_fn(padded), dtype=np.int32)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.from_numpy(counts).to(dev)
+        dist.all_reduce(t)
+        counts = t.cpu().numpy()
+    po = po_finalize(counts[:max(1, len(chosen))], chains_selected or k, faithful) if len(chosen) else np.zeros((n_sites, n_sites))
+    return [int(c) for c in chosen], po
