@@ -54,6 +54,14 @@ struct KParams {
   const int *off;           /* [M+1] first item of each column; a column has ones+1 items */
   const uint16_t *item_col; /* [I] item -> column */
   int I;                    /* ones_total + M */
+  /* large-shape path (ser_sweep_kernel_big): per-CTA-slot scratch in global memory */
+  int Cs;                   /* column stride of the scratch bit matrix (>= M+1) */
+  uint32_t *gV;             /* [slot][W][Cs] */
+  uint16_t *gpre;           /* [slot][W+1][Cs] */
+  uint16_t *gpos;           /* [slot][I+1] */
+  double *gval;             /* [slot][I+1] */
+  double *gterms;           /* [slot][M] */
+  int n_chains;
   uint16_t *ab;        /* [chain][2][Mpad] */
   uint16_t *rpi;       /* [chain][Npad] */
   ChainScalars *scal;  /* [chain] */
@@ -151,17 +159,6 @@ __device__ void build_columns(const KParams &p, const Smem &sm)
 /* sorted hard positions from the hard-mask column (its owner thread, tid == M) */
 __device__ void rebuild_hard(const KParams &p, const Smem &sm) { ser_hard_list(sm.V + p.M, p.C, p.W, sm.hp); }
 
-/* mcmc_initab, mcmc.c:440-474, on the thread's own column */
-__device__ void init_ab(const KParams &p, const uint32_t *col, int *a, int *b)
-{
-  int first = -1, last = -1;
-  for (int w = 0; w < p.W; w++) {
-    const uint32_t v = col[w * p.C];
-    if (v) { if (first < 0) first = 32 * w + __ffs(v) - 1; last = 32 * w + 31 - __clz(v); }
-  }
-  if (first < 0) { *a = 0; *b = p.N; } else { *a = first; *b = last + 1; }
-}
-
 __device__ __forceinline__ void set_weights(SerWeights &wt, double c, double cc, double d, double dd)
 {
   ser_set_weights(&wt, c, cc, d, dd);
@@ -177,19 +174,54 @@ __device__ __forceinline__ void totals_from(const KParams &p, const SerWeights &
                     SER_MUL((double)f1, wt.c));
 }
 
+/* ------------------------------------------------------------------ V-free helpers
+ * The init / export / check kernels do not need the bit columns: a thread walks its taxa's cells in
+ * position order straight from the site-major matrix.  They work for every shape. */
+__device__ __forceinline__ int cell(const KParams &p, const uint16_t *rpi, int pos, int c)
+{
+  return (p.Xs[(size_t)rpi[pos] * p.Mw + (c >> 5)] >> (c & 31)) & 1u;
+}
+__device__ int taxon_count(const KParams &p, const uint16_t *rpi, int c, int lo, int hi)
+{
+  int n = 0;
+  for (int pos = lo; pos < hi; pos++) n += cell(p, rpi, pos, c);
+  return n;
+}
+/* mcmc_initab, mcmc.c:440-474 */
+__device__ void taxon_init_ab(const KParams &p, const uint16_t *rpi, int c, int *a, int *b)
+{
+  int first = -1, last = -1;
+  for (int pos = 0; pos < p.N; pos++)
+    if (cell(p, rpi, pos, c)) { if (first < 0) first = pos; last = pos; }
+  if (first < 0) { *a = 0; *b = p.N; } else { *a = first; *b = last + 1; }
+}
+
+struct AuxSmem { /* init / export / check kernels */
+  int *red;
+  uint16_t *rpi, *tmp16;
+};
+__host__ __device__ inline size_t aux_layout(AuxSmem *s, unsigned char *base, int N)
+{
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  size_t o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4), o_p = take(sizeof(uint16_t) * N), o_t = take(sizeof(uint16_t) * N);
+  if (s) { s->red = (int *)(base + o_r); s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_t); }
+  return off;
+}
+
 /* ------------------------------------------------------------------ init kernel */
 /* mcmc_readmodel's initial state + mcmc_randomize (mcmc.c:405-433, :477-578) */
 __global__ void ser_init_kernel(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem sm;
-  const size_t used = smem_layout(&sm, smem_raw, p.N, p.W, p.C, 0);
-  /* extra scratch behind the common layout: 2N staged draws, pi / rest / chosen as u16 */
+  AuxSmem sm;
+  const size_t used = aux_layout(&sm, smem_raw, p.N);
+  /* behind the common layout: 2N staged draws, pi / rest / chosen as u16 */
   double *stage = (double *)(smem_raw + used);
   uint16_t *pi16 = (uint16_t *)(stage + 2 * p.N);
   uint16_t *rest16 = pi16 + p.N, *chosen16 = rest16 + p.N;
 
-  const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, nh = p.nh;
+  const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, nh = p.nh;
   const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
   const double *tape = nullptr;
   long long tape_len = 0;
@@ -204,11 +236,13 @@ __global__ void ser_init_kernel(KParams p)
   for (int n = tid; n < N; n += C) sm.rpi[n] = (uint16_t)n;
   __syncthreads();
 
-  int a = 0, b = 0;
-  const uint32_t *col = sm.V + tid;
+  uint16_t *ab = p.ab + (size_t)chain * 2 * p.Mpad;
   if (nh == 0) { /* identity-order a/b are kept although pi is shuffled (mcmc.c:486-494) */
-    build_columns(p, sm);
-    if (tid < M) init_ab(p, col, &a, &b);
+    for (int c = tid; c < M; c += C) {
+      int a, b;
+      taxon_init_ab(p, sm.rpi, c, &a, &b);
+      ab[c] = (uint16_t)a; ab[p.Mpad + c] = (uint16_t)b;
+    }
     __syncthreads();
   }
 
@@ -243,25 +277,24 @@ __global__ void ser_init_kernel(KParams p)
   __syncthreads();
   for (int n = tid; n < N; n += C) sm.rpi[pi16[n]] = (uint16_t)n;
   __syncthreads();
-  build_columns(p, sm);
-  if (nh != 0 && tid < M) init_ab(p, col, &a, &b);
-  __syncthreads();
 
   SerWeights wt;
   wt.eps = p.eps;
   set_weights(wt, p.c0, p.cc0, p.d0, p.dd0);
   int t1 = 0, len = 0;
-  if (tid < M) { t1 = ser_col_popc(col, sm.pre + tid, C, a, b); len = b - a; }
+  for (int c = tid; c < M; c += C) {
+    int a, b;
+    if (nh != 0) { taxon_init_ab(p, sm.rpi, c, &a, &b); ab[c] = (uint16_t)a; ab[p.Mpad + c] = (uint16_t)b; }
+    else { a = ab[c]; b = ab[p.Mpad + c]; }
+    t1 += taxon_count(p, sm.rpi, c, a, b);
+    len += b - a;
+  }
   int buf = 0, T1, LEN, dummy;
   block_sum3(t1, len, 0, sm.red, buf, &T1, &LEN, &dummy);
   int t0a, f0a, t1a, f1a;
   double loglik;
   totals_from(p, wt, T1, LEN, &t0a, &f0a, &t1a, &f1a, &loglik);
 
-  if (tid < M) {
-    p.ab[(size_t)chain * 2 * p.Mpad + tid] = (uint16_t)a;
-    p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid] = (uint16_t)b;
-  }
   for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
   if (tid == 0) {
     ChainScalars sc;
@@ -573,25 +606,353 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
   if (tid == 0) p.scal[chain] = sc;
 }
 
+/* ------------------------------------------------------------------ the sweep kernel, large shapes
+ * Same algorithm and building blocks as ser_sweep_kernel, for matrices whose bit columns, prefix
+ * tables and item buffers exceed shared memory (e.g. 1024 sites x 4096 taxa: 0.7 MB + 0.3 MB +
+ * 3.2 MB per chain).  A CTA owns a slot of L2-resident global scratch and walks over chains
+ * (persistent grid); every thread owns the columns tid, tid+C, ...; a/b live in shared memory. */
+struct BigSmem {
+  double *draws_pi, *logdraw, *draws_cd, *H, *lmax;
+  int *red;
+  uint16_t *a16, *b16, *st4, *hp, *rpi, *tmp16, *perm16;
+};
+__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M)
+{
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  size_t o_dp = take(8 * SER_PI_DRAWS), o_ld = take(8 * SER_PI_DRAWS), o_dc = take(8 * 8), o_H = take(8 * (size_t)(N + 2));
+  size_t o_lm = take(8 * (size_t)M), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
+  size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)M), o_hp = take(2 * (size_t)(N + 1));
+  size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N);
+  if (s) {
+    s->draws_pi = (double *)(base + o_dp); s->logdraw = (double *)(base + o_ld); s->draws_cd = (double *)(base + o_dc);
+    s->H = (double *)(base + o_H); s->lmax = (double *)(base + o_lm); s->red = (int *)(base + o_r);
+    s->a16 = (uint16_t *)(base + o_a); s->b16 = (uint16_t *)(base + o_b); s->st4 = (uint16_t *)(base + o_st);
+    s->hp = (uint16_t *)(base + o_hp); s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q);
+    s->perm16 = (uint16_t *)(base + o_m);
+  }
+  return off;
+}
+
+/* MH tail for the large-shape kernel: the thread's deltas are already summed over its columns;
+ * the degenerate case re-evaluates the per-taxon deltas through `redo` (a lambda) */
+template <typename Redo>
+__device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &sm, const SerWeights &wt, PropState &ps,
+                                              double *terms, int dt0, int dt1, int nz, int *D0, int *D1, double *delta_out,
+                                              Redo redo)
+{
+  int NZ;
+  block_sum3(dt0, dt1, nz, sm.red, ps.buf, D0, D1, &NZ);
+  double delta;
+  if (*D0 == 0 && *D1 == 0) {
+    delta = 0.0;
+    if (NZ) { /* see mh_decide: re-create the reference's sequential per-taxon sum */
+      for (int c = threadIdx.x; c < p.M; c += blockDim.x) {
+        int x0, x1;
+        redo(c, &x0, &x1);
+        terms[p.order[c]] = ser_term(wt, x0, x1);
+      }
+      __syncthreads();
+      for (int m = 0; m < p.M; m++) delta = SER_ADD(delta, terms[m]);
+    }
+  } else {
+    delta = ser_term(wt, *D0, *D1);
+  }
+  *delta_out = delta;
+  if (delta >= 0.0) return true;
+  return delta > sm.logdraw[ps.k++];
+}
+
+__global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BigSmem sm;
+  big_layout(&sm, smem_raw, p.N, p.M);
+  const int tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, W = p.W, Cs = p.Cs;
+  uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
+  uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
+  uint16_t *POS = p.gpos + (size_t)blockIdx.x * (p.I + 1);
+  double *VAL = p.gval + (size_t)blockIdx.x * (p.I + 1);
+  double *TERMS = p.gterms + (size_t)blockIdx.x * M;
+
+  for (int chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
+    const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+    __syncthreads(); /* previous chain's state fully saved before the scratch is reused */
+    ChainScalars sc = p.scal[chain];
+    for (int n = tid; n < N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
+    for (int c = tid; c < M; c += C) {
+      sm.a16[c] = p.ab[(size_t)chain * 2 * p.Mpad + c];
+      sm.b16[c] = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c];
+    }
+    __syncthreads();
+    /* position-ordered columns + prefix tables of the owned columns */
+    for (int c = tid; c <= M; c += C) {
+      for (int w = 0; w < W; w++) {
+        uint32_t word = 0;
+        const int pend = min(32 * w + 32, N);
+        if (c < M) { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)cell(p, sm.rpi, pos, c) << (pos & 31); }
+        else { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)(p.hard[sm.rpi[pos]] != 0) << (pos & 31); }
+        V[w * Cs + c] = word;
+      }
+      ser_col_build_pre(V + c, PRE + c, Cs, W);
+      if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+    }
+    __syncthreads();
+
+    const double *tape = nullptr;
+    long long tape_len = 0;
+    if (p.mode == SER_MODE_REPLAY) {
+      tape = p.tape + p.tape_off[chain];
+      tape_len = (long long)(p.tape_off[chain + 1] - p.tape_off[chain]);
+    }
+    SerWeights wt;
+    wt.eps = p.eps; wt.H = sm.H; wt.hmax = 0;
+    set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+    SerHard hd;
+    hd.hcol = V + M; hd.hpre = PRE + M; hd.hp = sm.hp; hd.C = Cs; hd.W = W; hd.N = N; hd.nh = p.nh;
+    PropState ps;
+    ps.k = 0; ps.buf = 0;
+
+    for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
+      for (int s = 0; s < p.sweeps_per_call; s++) {
+        /* ================= stage this sweep's draws ================= */
+        __syncthreads();
+        if (p.mode == SER_MODE_REPLAY) {
+          const long long need = sc.cursor + 6 + 2 * (long long)M;
+          if (need > tape_len) { sc.flags |= 1; break; }
+          if (tid < 6) sm.draws_cd[tid] = tape[sc.cursor + tid];
+          for (int t = tid; t < SER_PI_DRAWS; t += C) {
+            const long long idx = need + t;
+            const double u = idx < tape_len ? tape[idx] : 0.5;
+            sm.draws_pi[t] = u; sm.logdraw[t] = log(u);
+          }
+        } else {
+          if (tid < 4) {
+            const int cnt = tid == 0 ? sc.f1a : tid == 1 ? sc.t0a : tid == 2 ? sc.f0a : sc.t1a;
+            const double g = ser_gamma_ge1(1.0 + (double)cnt, p.seed, gchain, sc.sweep, (uint32_t)tid);
+            const double go = __shfl_xor_sync(0xfu, g, 1);
+            if (tid == 0 || tid == 2) {
+              const double y = ser_beta_from_gammas(g, go);
+              double val = tid == 0 ? sc.c : sc.d, l1m = tid == 0 ? sc.cc : sc.dd;
+              const double lo = tid == 0 ? SER_MINC : SER_MIND, hi = tid == 0 ? SER_MAXC : SER_MAXD;
+              if (y > 0.0) {
+                const double ly = ser_log(y);
+                if (lo <= ly && ly <= hi) { val = ly; l1m = ser_log(SER_SUB(1.0, ser_exp(ly))); }
+              }
+              sm.draws_cd[tid] = val; sm.draws_cd[tid + 1] = l1m;
+            }
+          }
+          for (int t = tid; t < SER_PI_DRAWS; t += C) {
+            const double u = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+            sm.draws_pi[t] = u; sm.logdraw[t] = log(ser_pos(u));
+          }
+        }
+        __syncthreads();
+        if (p.mode == SER_MODE_REPLAY) {
+          const double yc = sm.draws_cd[0], lyc = sm.draws_cd[1], l1c = sm.draws_cd[2];
+          const double yd = sm.draws_cd[3], lyd = sm.draws_cd[4], l1d = sm.draws_cd[5];
+          if (yc > 0.0 && SER_MINC <= lyc && lyc <= SER_MAXC) { sc.c = lyc; sc.cc = l1c; }
+          if (yd > 0.0 && SER_MIND <= lyd && lyd <= SER_MAXD) { sc.d = lyd; sc.dd = l1d; }
+        } else {
+          sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3];
+        }
+        set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+        sc.counters[0]++; sc.counters[1]++;
+        wt.hmax = ser_hmax(wt.g, N);
+        for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
+
+        /* ================= a/b Gibbs, item formulation ================= */
+        for (int c = tid; c < M; c += C) ser_expand_ones(V + c, Cs, W, POS + p.off[c]);
+        int changed = 0;
+#pragma unroll 1
+        for (int step = 0; step < 2; step++) {
+          for (int c = tid; c < M; c += C) {
+            const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
+                                         : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
+            sm.lmax[c] = ser_step_lmax(wt, st, POS + p.off[c]);
+            sm.st4[4 * c + 0] = (uint16_t)st.cur; sm.st4[4 * c + 1] = (uint16_t)st.bound;
+            sm.st4[4 * c + 2] = (uint16_t)st.ocur; sm.st4[4 * c + 3] = (uint16_t)st.kb;
+          }
+          __syncthreads(); /* also publishes H and POS */
+          for (int e = tid; e < p.I; e += C) {
+            const int c = p.item_col[e];
+            const int oc = p.off[c], kk = e - oc;
+            SerStep it;
+            it.cur = sm.st4[4 * c + 0]; it.bound = sm.st4[4 * c + 1]; it.ocur = sm.st4[4 * c + 2]; it.kb = sm.st4[4 * c + 3];
+            it.nones = p.off[c + 1] - oc - 1; it.N = N; it.rev = step;
+            if (kk <= it.kb) VAL[e] = ser_item_weight(wt, it, POS + oc, kk, sm.lmax[c]);
+          }
+          __syncthreads();
+          for (int c = tid; c < M; c += C) {
+            SerStep st;
+            st.cur = sm.st4[4 * c + 0]; st.bound = sm.st4[4 * c + 1]; st.ocur = sm.st4[4 * c + 2]; st.kb = sm.st4[4 * c + 3];
+            st.nones = p.off[c + 1] - p.off[c] - 1; st.N = N; st.rev = step;
+            const int taxon = p.order[c];
+            double u;
+            if (p.mode == SER_MODE_REPLAY) u = tape[sc.cursor + 6 + 2 * taxon + step];
+            else {
+              uint32_t o[4];
+              ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+              u = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
+            }
+            const int pick = ser_step_pick(wt, st, POS + p.off[c], VAL + p.off[c], sm.lmax[c], u);
+            if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
+            else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
+          }
+        }
+        {
+          int t1 = 0, len = 0, T1, LEN, CH;
+          for (int c = tid; c < M; c += C) { t1 += ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]); len += sm.b16[c] - sm.a16[c]; }
+          block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
+          totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
+          sc.counters[2] += CH;
+        }
+
+        /* ================= 16 proposals for pi ================= */
+        ps.k = 0;
+        for (int prop = 0; prop < 16; prop++) {
+          const int kind = prop == 0 ? 3 : ((prop - 1) % 3);
+          int dt0 = 0, dt1 = 0, nz = 0, D0, D1;
+          double delta;
+          if (kind == 0) { /* pi1 */
+            const int i = ser_draw_int(sm.draws_pi[ps.k], N);
+            int j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+            ps.k += 2;
+            if (j >= i) j++;
+            const int lo = min(i, j), hi = max(i, j);
+            if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
+            auto redo = [&](int c, int *x0, int *x1) { ser_pi1_delta(V + c, Cs, sm.a16[c], sm.b16[c], i, j, x0, x1); };
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, &D0, &D1, &delta, redo)) continue;
+            for (int c = tid; c <= M; c += C) {
+              if (c < M) { int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b; }
+              ser_col_rotate(V + c, Cs, W, i, j);
+              ser_col_fix_pre(V + c, PRE + c, Cs, lo >> 5, hi >> 5);
+              if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+            }
+            for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
+            __syncthreads();
+            for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
+            sc.counters[3]++;
+          } else if (kind == 1 || kind == 3) { /* pi2 */
+            int i, j;
+            if (kind == 1) {
+              i = ser_draw_int(sm.draws_pi[ps.k], N);
+              j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+              ps.k += 2;
+              if (j >= i) j++;
+              else { const int t = i; i = j; j = t; }
+            } else {
+              i = ser_draw_int(sm.draws_pi[ps.k], N - 1);
+              ps.k += 1;
+              j = i + 1;
+            }
+            if (ser_hard_count(hd, i, j) > 1) continue;
+            const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+            ps.k += 2;
+            auto redo = [&](int c, int *x0, int *x1) { ser_pi2_delta(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c], i, j, inc1, inc2, x0, x1); };
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, &D0, &D1, &delta, redo)) continue;
+            for (int c = tid; c <= M; c += C) {
+              if (c < M) {
+                int a = sm.a16[c], b = sm.b16[c];
+                const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
+                ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
+                sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
+              }
+              ser_col_reverse(V + c, Cs, W, i, j);
+              ser_col_fix_pre(V + c, PRE + c, Cs, i >> 5, j >> 5);
+              if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+            }
+            for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
+            __syncthreads();
+            for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
+            sc.counters[kind == 1 ? 4 : 5]++;
+          } else { /* pi3 */
+            const int nfree = N - p.nh;
+            if (nfree < 2) continue;
+            const int r1 = ser_draw_int(sm.draws_pi[ps.k], nfree), r2 = ser_draw_int(sm.draws_pi[ps.k + 1], nfree - 1);
+            ps.k += 2;
+            int ir, jr;
+            if (r1 <= r2) { ir = r1; jr = r2 + 1; } else { ir = r2; jr = r1; }
+            const SerPi3 g = ser_pi3_window(hd, ir, jr);
+            const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+            ps.k += 2;
+            auto redo = [&](int c, int *x0, int *x1) { ser_pi3_delta(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1); };
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, &D0, &D1, &delta, redo)) continue;
+            for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
+            __syncthreads();
+            for (int c = tid; c < M; c += C) {
+              int a = sm.a16[c], b = sm.b16[c];
+              const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
+              ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
+              sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
+              ser_col_permute(V + c, Cs, W, g.i, g.j, sm.perm16);
+              ser_col_fix_pre(V + c, PRE + c, Cs, g.i >> 5, g.j >> 5);
+            }
+            for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
+            __syncthreads();
+            for (int n = g.i + tid; n <= g.j; n += C) sm.rpi[n] = sm.tmp16[n];
+            sc.counters[6]++;
+          }
+          sc.t0a += D0; sc.f0a -= D0; sc.t1a += D1; sc.f1a -= D1;
+          sc.loglik = SER_ADD(sc.loglik, delta);
+          __syncthreads();
+        }
+
+        if (p.mode == SER_MODE_REPLAY) sc.cursor += 6 + 2 * (long long)M + ps.k;
+        else sc.sweep++;
+        sc.counters[7]++;
+      }
+      if (sc.flags & 1) break;
+
+      if (p.sampling) {
+        const int sidx = sc.n_samples;
+        if (sidx < p.max_samples) {
+          const size_t row = (size_t)chain * p.max_samples + sidx;
+          if (p.store >= SER_STORE_PI)
+            for (int pos = tid; pos < N; pos += C) p.samp_pi[row * N + sm.rpi[pos]] = (uint16_t)pos;
+          if (p.store >= SER_STORE_FULL) {
+            for (int c = tid; c < M; c += C) { p.samp_a[row * M + p.order[c]] = sm.a16[c]; p.samp_b[row * M + p.order[c]] = sm.b16[c]; }
+            if (tid == 0) { p.samp_cdl[row * 3 + 0] = sc.c; p.samp_cdl[row * 3 + 1] = sc.d; p.samp_cdl[row * 3 + 2] = sc.loglik; }
+          }
+        }
+        sc.sum_negll = SER_ADD(sc.sum_negll, -sc.loglik);
+        sc.sum_ec = SER_ADD(sc.sum_ec, exp(sc.c));
+        sc.sum_ed = SER_ADD(sc.sum_ed, exp(sc.d));
+        sc.n_samples++;
+      }
+    }
+
+    __syncthreads();
+    for (int c = tid; c < M; c += C) {
+      p.ab[(size_t)chain * 2 * p.Mpad + c] = sm.a16[c];
+      p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c] = sm.b16[c];
+    }
+    for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
+    if (tid == 0) p.scal[chain] = sc;
+  }
+}
+
 /* ------------------------------------------------------------------ export / check kernels */
 /* int32 view of one chain's state incl. the derived per-taxon counts (mcmc_count01) */
 __global__ void ser_export_kernel(KParams p, int chain, int *out_a, int *out_b, int *out_pi, int *out_rpi, int *out_cnt)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem sm;
-  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I);
-  const int tid = threadIdx.x, C = p.C;
+  AuxSmem sm;
+  aux_layout(&sm, smem_raw, p.N);
+  const int tid = threadIdx.x, C = blockDim.x;
   for (int n = tid; n < p.N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
   __syncthreads();
-  build_columns(p, sm);
   for (int n = tid; n < p.N; n += C) { out_rpi[n] = sm.rpi[n]; out_pi[sm.rpi[n]] = n; }
-  if (tid < p.M) {
-    const int a = p.ab[(size_t)chain * 2 * p.Mpad + tid], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
-    int t0, f0, t1, f1;
-    ser_counts(sm.V + tid, sm.pre + tid, C, p.N, a, b, p.ones[tid], &t0, &f0, &t1, &f1);
-    const int tx = p.order[tid];
+  for (int c = tid; c < p.M; c += C) {
+    const int a = p.ab[(size_t)chain * 2 * p.Mpad + c], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c];
+    const int t1 = taxon_count(p, sm.rpi, c, a, b), ones = p.ones[c];
+    const int tx = p.order[c];
     out_a[tx] = a; out_b[tx] = b;
-    out_cnt[tx] = t0; out_cnt[p.M + tx] = f0; out_cnt[2 * p.M + tx] = t1; out_cnt[3 * p.M + tx] = f1;
+    out_cnt[tx] = p.N - (b - a) - (ones - t1); out_cnt[p.M + tx] = (b - a) - t1;
+    out_cnt[2 * p.M + tx] = t1; out_cnt[3 * p.M + tx] = ones - t1;
   }
 }
 
@@ -600,16 +961,16 @@ __global__ void ser_export_kernel(KParams p, int chain, int *out_a, int *out_b, 
 __global__ void ser_check_kernel(KParams p, int *bad_count)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem sm;
-  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I);
-  const int chain = blockIdx.x, tid = threadIdx.x, C = p.C, N = p.N, M = p.M;
+  AuxSmem sm;
+  aux_layout(&sm, smem_raw, p.N);
+  const int chain = blockIdx.x, tid = threadIdx.x, C = blockDim.x, N = p.N, M = p.M;
   __shared__ int s_flags;
   if (tid == 0) s_flags = 0;
   for (int n = tid; n < N; n += C) { sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n]; sm.tmp16[n] = 0xffff; }
   __syncthreads();
   for (int n = tid; n < N; n += C) {
     const int site = sm.rpi[n];
-    if (site >= N) atomicOr(&s_flags, 4);
+    if (site >= N) { atomicOr(&s_flags, 4); sm.rpi[n] = 0; }
     else sm.tmp16[site] = (uint16_t)n; /* pi */
   }
   __syncthreads();
@@ -620,12 +981,11 @@ __global__ void ser_check_kernel(KParams p, int *bad_count)
       if (p.hard[n]) { cnt++; if (last >= 0 && (int)sm.tmp16[n] < last) s_flags |= 8; last = sm.tmp16[n]; }
     if (cnt != p.nh) atomicOr(&s_flags, 8);
   }
-  build_columns(p, sm);
   int t1 = 0, len = 0;
-  if (tid < M) {
-    const int a = p.ab[(size_t)chain * 2 * p.Mpad + tid], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
+  for (int c = tid; c < M; c += C) {
+    const int a = p.ab[(size_t)chain * 2 * p.Mpad + c], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c];
     if (!(0 <= a && a <= b && b <= N)) atomicOr(&s_flags, 2);
-    else { t1 = ser_col_popc(sm.V + tid, sm.pre + tid, C, a, b); len = b - a; }
+    else { t1 += taxon_count(p, sm.rpi, c, a, b); len += b - a; }
   }
   int buf = 0, T1, LEN, dummy;
   block_sum3(t1, len, 0, sm.red, buf, &T1, &LEN, &dummy);
@@ -809,7 +1169,11 @@ struct ser_run {
   int timing_open;
   double elapsed_ms;
   long long launches;
-  size_t smem_sweep, smem_init, smem_small;
+  size_t smem_sweep, smem_init, smem_small, smem_big;
+  int Caux, big, big_threads, big_slots;
+  uint32_t *d_gV;
+  uint16_t *d_gpre, *d_gpos;
+  double *d_gval, *d_gterms;
   int initialized, have_tapes;
 };
 
@@ -847,7 +1211,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   if (!ds || !cfg || !out) { ser_set_error("ser_run_create: null argument"); return SER_E_ARG; }
   const int N = ds->N, M = ds->M;
   if (N < 2 || N > SER_MAX_SITES) { ser_set_error("ser_run_create: N=%d outside [2,%d]", N, SER_MAX_SITES); return SER_E_ARG; }
-  if (M < 1 || M + 1 > 1024) { ser_set_error("ser_run_create: M=%d: this build maps one taxon per thread, M <= 1023", M); return SER_E_ARG; }
+  if (M < 1 || M > SER_MAX_TAXA) { ser_set_error("ser_run_create: M=%d outside [1,%d]", M, SER_MAX_TAXA); return SER_E_ARG; }
   if (cfg->n_chains < 1 || cfg->sweeps_per_call < 1) { ser_set_error("ser_run_create: n_chains and sweeps_per_call must be >= 1"); return SER_E_ARG; }
   if (cfg->mode != SER_MODE_FREE && cfg->mode != SER_MODE_REPLAY) { ser_set_error("ser_run_create: bad mode"); return SER_E_ARG; }
   int ndev = 0;
@@ -860,6 +1224,12 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   run->N = N; run->M = M; run->nh = ds->nh;
   run->W = N / 32 + 1;
   run->C = ((M + 1) + 31) / 32 * 32;
+  run->Caux = std::min(1024, (M + 31) / 32 * 32);
+  /* large-shape path when one thread per column does not fit a CTA or its shared memory;
+   * SER_FORCE_BIG=<threads> forces it (tests run the whole parity suite through it) */
+  run->big_threads = 1024;
+  if (const char *fb = getenv("SER_FORCE_BIG")) { run->big = 1; if (atoi(fb) >= 32) run->big_threads = std::min(1024, atoi(fb) / 32 * 32); }
+  if (run->C > 1024) { run->big = 1; run->C = 1024; }
   CUDA_TRY(cudaSetDevice(cfg->device));
   CUDA_TRY(cudaStreamCreateWithFlags(&run->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&run->ev_start));
@@ -936,14 +1306,32 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   kp.ab = run->d_ab; kp.rpi = run->d_rpi; kp.scal = run->d_scal;
   kp.samp_a = run->d_samp_a; kp.samp_b = run->d_samp_b; kp.samp_pi = run->d_samp_pi; kp.samp_cdl = run->d_samp_cdl;
 
-  run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
-  run->smem_small = smem_layout(nullptr, nullptr, N, run->W, run->C, 0);
+  run->smem_small = aux_layout(nullptr, nullptr, N);
   run->smem_init = run->smem_small + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
-  if (run->smem_init > 227 * 1024 || run->smem_sweep > 227 * 1024) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_init); return SER_E_ARG; }
-  CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
   CUDA_TRY(cudaFuncSetAttribute(ser_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_init));
-  CUDA_TRY(cudaFuncSetAttribute(ser_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
-  CUDA_TRY(cudaFuncSetAttribute(ser_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+  if (!run->big) {
+    run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
+    if (run->smem_sweep > 227 * 1024) run->big = 1; /* columns + items do not fit: use the L2-resident variant */
+    else CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+  }
+  if (run->big) {
+    run->smem_big = big_layout(nullptr, nullptr, N, M);
+    if (run->smem_big > 227 * 1024) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_big); return SER_E_ARG; }
+    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_big));
+    int per_sm = 1, n_sm = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big, run->big_threads, run->smem_big));
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    run->big_slots = std::max(1, std::min(cfg->n_chains, per_sm * n_sm));
+    kp.Cs = ((M + 1) + 31) / 32 * 32;
+    const size_t sl = (size_t)run->big_slots;
+    CUDA_TRY(POOL_ALLOC(&run->d_gV, sl * run->W * kp.Cs * sizeof(uint32_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_gpre, sl * (run->W + 1) * kp.Cs * sizeof(uint16_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_gpos, sl * (kp.I + 1) * sizeof(uint16_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_gval, sl * (kp.I + 1) * sizeof(double)));
+    CUDA_TRY(POOL_ALLOC(&run->d_gterms, sl * M * sizeof(double)));
+    kp.gV = run->d_gV; kp.gpre = run->d_gpre; kp.gpos = run->d_gpos; kp.gval = run->d_gval; kp.gterms = run->d_gterms;
+  }
+  kp.n_chains = cfg->n_chains;
   *out = run;
   return SER_OK;
 }
@@ -954,7 +1342,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   cudaSetDevice(run->cfg.device);
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
-                  run->d_scratch_i, run->d_bad};
+                  run->d_scratch_i, run->d_bad, run->d_gV, run->d_gpre, run->d_gpos, run->d_gval, run->d_gterms};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   cudaStreamSynchronize(run->stream);
   cudaEventDestroy(run->ev_start); cudaEventDestroy(run->ev_stop);
@@ -999,7 +1387,7 @@ extern "C" int ser_run_init(ser_run *run)
   if (run->cfg.mode == SER_MODE_REPLAY && !run->have_tapes) { ser_set_error("ser_run_init: replay mode needs ser_run_set_tapes first"); return SER_E_TAPE; }
   if (set_device(run)) return SER_E_CUDA;
   mark_launch(run);
-  ser_init_kernel<<<run->cfg.n_chains, run->C, run->smem_init, run->stream>>>(run->kp);
+  ser_init_kernel<<<run->cfg.n_chains, run->Caux, run->smem_init, run->stream>>>(run->kp);
   CUDA_TRY(cudaGetLastError());
   run->initialized = 1;
   return SER_OK;
@@ -1014,7 +1402,8 @@ extern "C" int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling)
   KParams kp = run->kp;
   kp.n_calls = n_calls; kp.sampling = sampling;
   mark_launch(run);
-  ser_sweep_kernel<<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
+  if (run->big) ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+  else ser_sweep_kernel<<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
   CUDA_TRY(cudaGetLastError());
   return SER_OK;
 }
@@ -1068,7 +1457,7 @@ extern "C" int ser_run_get_state(ser_run *run, int32_t chain, int32_t *a, int32_
   int *d = run->d_scratch_i;
   int *d_a = d, *d_b = d + M, *d_pi = d + 2 * M, *d_rpi = d + 2 * M + N, *d_cnt = d + 2 * M + 2 * N;
   mark_launch(run);
-  ser_export_kernel<<<1, run->C, run->smem_sweep, run->stream>>>(run->kp, chain, d_a, d_b, d_pi, d_rpi, d_cnt);
+  ser_export_kernel<<<1, run->Caux, run->smem_small, run->stream>>>(run->kp, chain, d_a, d_b, d_pi, d_rpi, d_cnt);
   CUDA_TRY(cudaGetLastError());
   std::vector<int> h(2 * N + 6 * M);
   ChainScalars sc;
@@ -1109,7 +1498,7 @@ extern "C" int ser_run_check(ser_run *run, int32_t *n_bad)
   if (set_device(run)) return SER_E_CUDA;
   CUDA_TRY(cudaMemsetAsync(run->d_bad, 0, sizeof(int), run->stream));
   mark_launch(run);
-  ser_check_kernel<<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(run->kp, run->d_bad);
+  ser_check_kernel<<<run->cfg.n_chains, run->Caux, run->smem_small, run->stream>>>(run->kp, run->d_bad);
   CUDA_TRY(cudaGetLastError());
   int bad = 0;
   CUDA_TRY(cudaMemcpyAsync(&bad, run->d_bad, sizeof(int), cudaMemcpyDeviceToHost, run->stream));

@@ -194,7 +194,7 @@ def test_error_paths(S):
         short.state(0)                                      # tape exhausted mid-run
     assert "tape" in str(e.value)
     with pytest.raises(S.SeriationError):
-        S.Run(S.Dataset.from_bits(np.ones((4, 2000), np.uint8)), 1)  # unsupported shape says so
+        S.Run(S.Dataset.from_bits(np.ones((4, 5000), np.uint8)), 1)  # unsupported shape says so
 
 
 def test_reference_file_writers(S, oracle_mod, tmp_path):
@@ -287,3 +287,53 @@ def test_cli_batch_mode(S, tmp_path):
     chosen = S.choose_chains(batch, 3)
     assert ("chosen " + " ".join(str(c) for c in chosen)) in out
     assert np.allclose(S.compute_pair_order_matrix(batch, chosen, 3), po, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# large-shape path (ser_sweep_kernel_big): several columns per thread, bit columns / items in
+# L2-resident global scratch.  SER_FORCE_BIG=<threads> routes small shapes through it.
+@pytest.mark.parametrize("threads", ["64", "1024"])
+@pytest.mark.parametrize("name,burn,samp", [("g10s10", 8, 8), ("g2s2", 2, 2)])
+def test_big_path_replay_bit_exact(S, oracle_mod, monkeypatch, name, burn, samp, threads):
+    monkeypatch.setenv("SER_FORCE_BIG", threads)
+    X, hard = load_hex_dataset(name)
+    _replay_case(S, oracle_mod, X, hard, [5, 6, 7], burn, samp)
+
+
+@pytest.mark.parametrize("shape", EDGE_SHAPES[::2])
+def test_big_path_edge_shapes(S, oracle_mod, monkeypatch, shape):
+    monkeypatch.setenv("SER_FORCE_BIG", "32")
+    rng = np.random.default_rng(hash(shape) & 0xffff)
+    X, hard = random_dataset(rng, *shape)
+    _replay_case(S, oracle_mod, X, hard, [1, 2], 6, 6)
+
+
+def test_big_path_many_chains_share_slots(S, oracle_mod, monkeypatch):
+    """more chains than resident CTA slots: the persistent grid walks over chains"""
+    monkeypatch.setenv("SER_FORCE_BIG", "1024")
+    X, hard = load_hex_dataset("g10s10")
+    run = S.Run(S.Dataset.from_bits(X, hard), 700, seed=3, store=S.STORE_PI, max_samples=2)
+    run.init().advance(2, False).advance(2, True).sync()
+    assert run.check() == 0
+    monkeypatch.delenv("SER_FORCE_BIG")
+    ref = S.Run(S.Dataset.from_bits(X, hard), 700, seed=3, store=S.STORE_PI, max_samples=2)
+    ref.init().advance(2, False).advance(2, True).sync()
+    for i in (0, 1, 147, 148, 149, 400, 699):
+        a, b = run.state(i), ref.state(i)
+        for k in ("a", "b", "pi", "tot"):
+            assert np.array_equal(a[k], b[k]), (i, k)
+        assert a["loglik"] == b["loglik"]
+
+
+def test_wide_matrix_uses_big_path_replay(S, oracle_mod):
+    """M > 1023 (more taxa than threads in a CTA): synthetic 200 x 1500"""
+    X, hard = S.Dataset.synthetic(200, 1500, 6, 11).arrays()
+    _replay_case(S, oracle_mod, X, hard, [1, 2], 2, 2)
+
+
+def test_synthetic_1024x4096_replay(S, oracle_mod):
+    """BASELINE.json config 5 shape: 1024 sites x 4096 taxa, one chain, 10 + 10 sweeps vs the oracle"""
+    X, hard = S.Dataset.synthetic(1024, 4096, 16).arrays()
+    _replay_case(S, oracle_mod, X, hard, [42], 1, 1)
+    run = S.Run(S.Dataset.from_bits(X, hard), 300, seed=1).init().advance(1, False).advance(1, True).sync()
+    assert run.check() == 0
