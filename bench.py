@@ -37,7 +37,18 @@ ALGO = {
     "g10s2": dict(N=501, M=139, C=301352, B=37669, F=69917, hbm_sample=1582, k=2),
     "g5s5": dict(N=273, M=202, C=238360, B=29795, F=55550, hbm_sample=1378, k=2),
     "g2s2": dict(N=526, M=296, C=673301, B=84163, F=156288, hbm_sample=2260, k=4),
+    "synthetic": dict(N=1024, M=4096, C=18149376, B=2268672, F=4202496, hbm_sample=18456, k=2),
 }
+
+
+def load_dataset(name):
+    """(X, hard): a NOW subset from the committed fixtures, or the deterministic 1024 x 4096 synthetic
+    matrix of BASELINE.json config 5 (generator: ser_dataset_synthetic)"""
+    if name == "synthetic":
+        import seriation_b200 as S
+        return S.Dataset.synthetic(1024, 4096, 16).arrays()
+    from tools.datasets import load_hex_dataset
+    return load_hex_dataset(name)
 METRIC = "mcmc_sweeps_per_s_aggregate"
 UNIT = "sweeps/s"
 
@@ -48,10 +59,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dataset", default="g2s2")
-    ap.add_argument("--chains", type=int, default=16384, help="chains per GPU")
-    ap.add_argument("--burn-calls", type=int, default=5)
-    ap.add_argument("--sample-calls", type=int, default=5)
+    ap.add_argument("--dataset", default="g2s2", choices=sorted(ALGO))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (0: 16384; synthetic: 8192)")
+    ap.add_argument("--burn-calls", type=int, default=0, help="0: 5 (synthetic: 1)")
+    ap.add_argument("--sample-calls", type=int, default=0, help="0: 5 (synthetic: 1)")
+    ap.add_argument("--no-synthetic-probe", action="store_true")
     ap.add_argument("--cpu-calls", type=int, default=0, help="mcmc_sample() calls per CPU process (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -62,14 +74,15 @@ def cpu_reference_run(dataset, calls, procs):
     """`procs` concurrent processes of the reference sampler (script.py's Pool, :60-62), each doing
     `calls` mcmc_sample() calls (= 10 sweeps each) on `dataset`.  Returns (sweeps/s aggregate, kind)."""
     from oracle import oracle as O
-    from tools.datasets import load_hex_dataset, write_txt
-    X, hard = load_hex_dataset(dataset)
-    if O.ref_available():
+    from tools.datasets import write_txt
+    X, hard = load_dataset(dataset)
+    ref_bin = O.REF_BIN + ("_big" if X.shape[1] > 900 else "")  # rows > 1999 chars need the MAXS-patched build
+    if O.ref_available() and os.access(ref_bin, os.X_OK):
         with tempfile.TemporaryDirectory() as td:
             path = os.path.join(td, dataset + ".txt")
             write_txt(path, X, hard)
             t0 = time.perf_counter()
-            ps = [subprocess.Popen([O.REF_BIN, "bench", path, str(calls)], env=dict(os.environ, GSL_RNG_SEED=str(i + 1)),
+            ps = [subprocess.Popen([ref_bin, "bench", path, str(calls)], env=dict(os.environ, GSL_RNG_SEED=str(i + 1)),
                                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(procs)]
             rcs = [p.wait() for p in ps]
             dt = time.perf_counter() - t0
@@ -77,8 +90,8 @@ def cpu_reference_run(dataset, calls, procs):
             raise RuntimeError("reference binary failed: %r" % rcs)
         return procs * calls * 10 / dt, "reference"
     # no prebuilt reference binary: time the restatement (one process per core)
-    code = ("import sys; sys.path.insert(0, %r); from oracle import oracle as O; from tools.datasets import load_hex_dataset;"
-            "X,h=load_hex_dataset(%r); o=O.Oracle(X,h).source_mt(int(sys.argv[1])); o.randomize();"
+    code = ("import sys; sys.path.insert(0, %r); from oracle import oracle as O; import bench;"
+            "X,h=bench.load_dataset(%r); o=O.Oracle(X,h).source_mt(int(sys.argv[1])); o.randomize();"
             "[o.sample() for _ in range(%d)]" % (ROOT, dataset, calls))
     O.build()
     t0 = time.perf_counter()
@@ -93,7 +106,7 @@ def cpu_reference_run(dataset, calls, procs):
 def auto_cpu_calls(dataset):
     # ~10 s of CPU work per process: the survey measured 24-26 ns per canonical cell
     per_sweep = ALGO[dataset]["C"] * 25e-9
-    return max(2, int(10.0 / (per_sweep * 10)))
+    return max(1, int(10.0 / (per_sweep * 10)))
 
 
 def run_reference_arm(args):
@@ -167,8 +180,11 @@ def main():
     import torch
     import torch.distributed as dist
     import seriation_b200 as S
-    from tools.datasets import load_hex_dataset
 
+    big = args.dataset == "synthetic"
+    args.chains = args.chains or (8192 if big else 16384)
+    args.burn_calls = args.burn_calls or (1 if big else 5)
+    args.sample_calls = args.sample_calls or (1 if big else 5)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -179,7 +195,7 @@ def main():
     S.lib()  # fails loudly if the CUDA library is missing
 
     algo = ALGO[args.dataset]
-    X, hard = load_hex_dataset(args.dataset)
+    X, hard = load_dataset(args.dataset)
     N, M, k = X.shape[0], X.shape[1], algo["k"]
     n_local, n_total = args.chains, args.chains * world
     calls = args.burn_calls + args.sample_calls
@@ -292,7 +308,7 @@ def main():
             "bound": "fp64", "achieved": achieved, "peak": mb["fp64_tflops"], "unit": "TFLOP/s",
             "frac": achieved / mb["fp64_tflops"], "traffic": None,
             "peak_source": "ser_microbench fp64 FMA on this GPU, measured live (MEASURED_PEAKS.json holds only HBM and bf16)",
-            "kernel": "ser_sweep_kernel", "kernel_ms_per_step": sweep_kernel_ms,
+            "kernel": "ser_sweep_kernel_big" if big else "ser_sweep_kernel", "kernel_ms_per_step": sweep_kernel_ms,
             "kernel_sweeps_per_s_per_gpu": kernel_sweeps_per_s,
             "smem": {"achieved_gbs": algo["B"] * kernel_sweeps_per_s / 1e9, "peak_gbs": mb["lds_gbs"],
                      "frac": algo["B"] * kernel_sweeps_per_s / 1e9 / mb["lds_gbs"]},
@@ -308,19 +324,35 @@ def main():
             v, kind = cpu_reference_run(args.dataset, ccalls, procs)
             cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": kind,
                    "sample": "%d processes x %d sweeps of %s (unmodified mcmc.c, -O2, GSL-API shim)" % (procs, ccalls * 10, args.dataset)}
+        also = None
+        if world == 1 and not big and not args.no_synthetic_probe:
+            # BASELINE.json's metric also names the 1024 x 4096 synthetic matrix: a short probe of its
+            # sweep kernel (large-shape path), CUDA-event timed, so both shapes appear in one line
+            sds = S.Dataset.synthetic(1024, 4096, 16)
+            srun = S.Run(sds, 1184, seed=20060206, store=S.STORE_PI, max_samples=1, device=local)
+            srun.init().advance(1, False).sync()
+            srun.elapsed_ms(reset=True)
+            srun.advance(1, True)
+            sms = srun.elapsed_ms(reset=True)
+            sv = 1184 * 10 / (sms * 1e-3)
+            srun.close()
+            also = {"synthetic_1024x4096": {"value": sv, "unit": UNIT, "chains": 1184, "sweeps_per_chain": 10, "kernel_ms": sms,
+                                             "fp64_frac": 10.0 * ALGO["synthetic"]["F"] * sv / 1e12 / mb["fp64_tflops"],
+                                             "note": "sweep kernel only (ser_sweep_kernel_big); full line: --dataset synthetic"}}
         h2d = int(X.shape[0] * ((M + 31) // 32) * 4 + N + 4 * M)
         d2h = int(n_local * 200 + k * N * N * 4)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "NOW subset %s (committed fixture of the reference's Dataset/), Philox free-running chains" % args.dataset,
+            "dtype": "f64", "data": ("synthetic 1024 x 4096 occurrence matrix (ser_dataset_synthetic), Philox free-running chains" if big else
+                                     "NOW subset %s (committed fixture of the reference's Dataset/), Philox free-running chains" % args.dataset),
             "config": {"workload": "%s %dx%d, %d chains per GPU x (%d burn + %d sampling) calls x 10 sweeps, thin 10, "
                                    "on-device selection (k=%d) + pair-order counts" % (args.dataset, N, M, n_local, args.burn_calls, args.sample_calls, k),
                        "chains_total": n_total, "sweeps_per_step": sweeps_per_step, "parallelism": "chains sharded x%d" % world,
                        "l2": "256 MB flush buffer written between timed steps"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                    "ms_per_step": dt_e2e / args.steps * 1e3},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "also": also,
         }))
     if world > 1:
         dist.destroy_process_group()
