@@ -231,16 +231,17 @@ SER_HD int ser_hard_rank(const SerHard &h, int p) { return ser_rank1(h.hcol, h.h
 SER_HD int ser_is_hard(const SerHard &h, int p) { return (h.hcol[(p >> 5) * h.C] >> (p & 31)) & 1u; }
 /* number of hard positions in [lo, hi] */
 SER_HD int ser_hard_count(const SerHard &h, int lo, int hi) { return ser_hard_rank(h, hi + 1) - ser_hard_rank(h, lo); }
-/* position of the r-th (from 0) non-hard position; r < N - nh.  Binary search for the word
- * (non-hard prefix 32w - hpre[w] is non-decreasing), then select inside it. */
+/* position of the r-th (from 0) non-hard position; r < N - nh.  hp[k] - k = number of non-hard
+ * positions before hard site k (non-decreasing), so the answer is r + #{k : hp[k] - k <= r}:
+ * an upper-bound search over the sorted hard list. */
 SER_HD int ser_select_nonhard(const SerHard &h, int r)
 {
-  int lo = 0, hi = h.W - 1; /* largest w with 32w - hpre[w] <= r */
+  int lo = 0, hi = h.nh; /* first k with hp[k] - k > r */
   while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (32 * mid - (int)h.hpre[mid * h.C] <= r) lo = mid; else hi = mid - 1;
+    const int mid = (lo + hi) >> 1;
+    if ((int)h.hp[mid] - mid <= r) lo = mid + 1; else hi = mid;
   }
-  return 32 * lo + ser_select_bit(~h.hcol[lo * h.C], r - (32 * lo - (int)h.hpre[lo * h.C]));
+  return r + lo;
 }
 
 /* ------------------------------------------------------------------ likelihood weights */

@@ -131,8 +131,12 @@ __device__ __forceinline__ void block_sum3(int v0, int v1, int v2, int *red, int
   int *r = red + buf * (SER_MAX_WARPS * 4);
   if (lane == 0) { r[warp * 4 + 0] = v0; r[warp * 4 + 1] = v1; r[warp * 4 + 2] = v2; }
   __syncthreads();
+  /* second level: lane w picks up warp w's partials, one more REDUX per value */
   int s0 = 0, s1 = 0, s2 = 0;
-  for (int w = 0; w < nwarp; w++) { s0 += r[w * 4 + 0]; s1 += r[w * 4 + 1]; s2 += r[w * 4 + 2]; }
+  if (lane < nwarp) { s0 = r[lane * 4 + 0]; s1 = r[lane * 4 + 1]; s2 = r[lane * 4 + 2]; }
+  s0 = __reduce_add_sync(0xffffffffu, s0);
+  s1 = __reduce_add_sync(0xffffffffu, s1);
+  s2 = __reduce_add_sync(0xffffffffu, s2);
   buf ^= 1;
   *o0 = s0; *o1 = s1; *o2 = s2;
 }
@@ -340,7 +344,10 @@ __device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, cons
   return delta > sm.logdraw[ps.k++];
 }
 
-__global__ void __launch_bounds__(1024, 1) ser_sweep_kernel(KParams p)
+/* MAXT = largest block the instantiation is launched with: the small-block instantiation may use
+ * more registers per thread (shared memory, not registers, limits residency there) */
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
@@ -1170,7 +1177,7 @@ struct ser_run {
   double elapsed_ms;
   long long launches;
   size_t smem_sweep, smem_init, smem_small, smem_big;
-  int Caux, big, big_threads, big_slots;
+  int Caux, big, big_threads, big_slots, variant;
   uint32_t *d_gV;
   uint16_t *d_gpre, *d_gpos;
   double *d_gval, *d_gterms;
@@ -1312,7 +1319,17 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   if (!run->big) {
     run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
     if (run->smem_sweep > 227 * 1024) run->big = 1; /* columns + items do not fit: use the L2-resident variant */
-    else CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+    else {
+      /* two register budgets: 64 regs (any block size) and 85 regs (blocks <= 384 threads, two of
+       * them resident); take the one with more resident CTAs, the roomier one on a tie */
+      CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+      CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
+      int occ64 = 0, occ85 = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel<1024, 1>, run->C, run->smem_sweep));
+      if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel<384, 2>, run->C, run->smem_sweep));
+      run->variant = (occ85 >= occ64 && occ85 > 0) ? 1 : 0;
+      if (const char *v = getenv("SER_SWEEP_VARIANT")) run->variant = (atoi(v) == 1 && run->C <= 384) ? 1 : 0;
+    }
   }
   if (run->big) {
     run->smem_big = big_layout(nullptr, nullptr, N, M);
@@ -1403,7 +1420,8 @@ extern "C" int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling)
   kp.n_calls = n_calls; kp.sampling = sampling;
   mark_launch(run);
   if (run->big) ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
-  else ser_sweep_kernel<<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
+  else if (run->variant == 1) ser_sweep_kernel<384, 2><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
+  else ser_sweep_kernel<1024, 1><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
   CUDA_TRY(cudaGetLastError());
   return SER_OK;
 }
