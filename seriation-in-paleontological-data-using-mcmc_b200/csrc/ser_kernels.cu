@@ -52,7 +52,7 @@ struct KParams {
   const int *ones;     /* [M] ones per column */
   const uint16_t *order;    /* [M] column -> taxon (columns are sorted by ones, descending) */
   const int *off;           /* [M+1] first item of each column; a column has ones+1 items */
-  const uint16_t *item_col; /* [I] item -> column */
+  const uint32_t *item_col; /* [I] item -> (column << 16) | index of the item inside its column */
   int I;                    /* ones_total + M */
   /* large-shape path (ser_sweep_kernel_big): per-CTA-slot scratch in global memory */
   int Cs;                   /* column stride of the scratch bit matrix (>= M+1) */
@@ -472,12 +472,15 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
         }
         __syncthreads();
         for (int e = tid; e < p.I; e += C) {
-          const int c = p.item_col[e];
-          const int oc = p.off[c], kk = e - oc;
+          const uint32_t ck = p.item_col[e];
+          const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
+          const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c); /* cur, bound | ocur, kb */
           SerStep it;
-          it.cur = sm.st4[4 * c + 0]; it.bound = sm.st4[4 * c + 1]; it.ocur = sm.st4[4 * c + 2]; it.kb = sm.st4[4 * c + 3];
-          it.nones = p.off[c + 1] - oc - 1; it.N = N; it.rev = step;
-          if (kk <= it.kb) sm.val[e] = ser_item_weight(wt, it, sm.pos + oc, kk, sm.lmax[c]);
+          it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
+          if (kk <= it.kb) {
+            it.nones = p.ones[c]; it.N = N; it.rev = step;
+            sm.val[e] = ser_item_weight(wt, it, sm.pos + (e - kk), kk, sm.lmax[c]);
+          }
         }
         __syncthreads();
         if (is_taxon) {
@@ -782,12 +785,15 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           }
           __syncthreads(); /* also publishes H and POS */
           for (int e = tid; e < p.I; e += C) {
-            const int c = p.item_col[e];
-            const int oc = p.off[c], kk = e - oc;
+            const uint32_t ck = p.item_col[e];
+            const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
+            const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c);
             SerStep it;
-            it.cur = sm.st4[4 * c + 0]; it.bound = sm.st4[4 * c + 1]; it.ocur = sm.st4[4 * c + 2]; it.kb = sm.st4[4 * c + 3];
-            it.nones = p.off[c + 1] - oc - 1; it.N = N; it.rev = step;
-            if (kk <= it.kb) VAL[e] = ser_item_weight(wt, it, POS + oc, kk, sm.lmax[c]);
+            it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
+            if (kk <= it.kb) {
+              it.nones = p.ones[c]; it.N = N; it.rev = step;
+              VAL[e] = ser_item_weight(wt, it, POS + (e - kk), kk, sm.lmax[c]);
+            }
           }
           __syncthreads();
           for (int c = tid; c < M; c += C) {
@@ -1162,7 +1168,8 @@ struct ser_run {
   uint32_t *d_Xs;
   uint8_t *d_hard;
   int *d_ones, *d_off;
-  uint16_t *d_order, *d_item_col;
+  uint16_t *d_order;
+  uint32_t *d_item_col;
   uint16_t *d_ab, *d_rpi;
   ChainScalars *d_scal;
   double *d_tape;
@@ -1273,9 +1280,9 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
       if (ds->X[(size_t)n * M + order[c]]) Xs[(size_t)n * kp.Mw + (c >> 5)] |= 1u << (c & 31);
   }
   kp.I = off[M];
-  std::vector<uint16_t> item_col(kp.I);
+  std::vector<uint32_t> item_col(kp.I);
   for (int c = 0; c < M; c++)
-    for (int e = off[c]; e < off[c + 1]; e++) item_col[e] = (uint16_t)c;
+    for (int e = off[c]; e < off[c + 1]; e++) item_col[e] = ((uint32_t)c << 16) | (uint32_t)(e - off[c]);
   kp.ones_total = ones_total;
   run->h_hard = (uint8_t *)malloc(N);
   memcpy(run->h_hard, ds->hard, N);
@@ -1286,7 +1293,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   CUDA_TRY(POOL_ALLOC(&run->d_ones, M * sizeof(int)));
   CUDA_TRY(POOL_ALLOC(&run->d_off, (M + 1) * sizeof(int)));
   CUDA_TRY(POOL_ALLOC(&run->d_order, M * sizeof(uint16_t)));
-  CUDA_TRY(POOL_ALLOC(&run->d_item_col, (size_t)kp.I * sizeof(uint16_t)));
+  CUDA_TRY(POOL_ALLOC(&run->d_item_col, (size_t)kp.I * sizeof(uint32_t)));
   CUDA_TRY(POOL_ALLOC(&run->d_ab, nc * 2 * kp.Mpad * sizeof(uint16_t)));
   CUDA_TRY(POOL_ALLOC(&run->d_rpi, nc * kp.Npad * sizeof(uint16_t)));
   CUDA_TRY(POOL_ALLOC(&run->d_scal, nc * sizeof(ChainScalars)));
@@ -1297,7 +1304,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   CUDA_TRY(cudaMemcpyAsync(run->d_ones, ones.data(), M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemcpyAsync(run->d_off, off.data(), (M + 1) * sizeof(int), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemcpyAsync(run->d_order, order.data(), M * sizeof(uint16_t), cudaMemcpyHostToDevice, run->stream));
-  CUDA_TRY(cudaMemcpyAsync(run->d_item_col, item_col.data(), (size_t)kp.I * sizeof(uint16_t), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(run->d_item_col, item_col.data(), (size_t)kp.I * sizeof(uint32_t), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(cudaMemsetAsync(run->d_scal, 0, nc * sizeof(ChainScalars), run->stream));
   CUDA_TRY(cudaStreamSynchronize(run->stream));
   if (cfg->store >= SER_STORE_PI && cfg->max_samples > 0) {
