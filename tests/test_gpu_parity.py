@@ -337,3 +337,48 @@ def test_synthetic_1024x4096_replay(S, oracle_mod):
     _replay_case(S, oracle_mod, X, hard, [42], 1, 1)
     run = S.Run(S.Dataset.from_bits(X, hard), 300, seed=1).init().advance(1, False).advance(1, True).sync()
     assert run.check() == 0
+
+
+def test_config3_g5s5_4096_chains_selection_and_po(S, oracle_mod):
+    """BASELINE.json config 3 at reduced length: g5s5, 4096 chains, k = 2 (script.py:455-456).
+    Device selection == script.py's choose_chains on the same E[-logL]; PO counts == numpy on the
+    chosen chains' pi history; and two of the 4096 chains are re-run on the CPU oracle (same Philox
+    stream) to tie the batch back to the reference algorithm."""
+    X, hard = load_hex_dataset("g5s5")
+    n, burn, samp, k, seed = 4096, 6, 8, 2, 20060206
+    run = S.Run(S.Dataset.from_bits(X, hard), n, seed=seed, store=S.STORE_PI, max_samples=samp)
+    run.init().advance(burn, False).advance(samp, True).sync()
+    assert run.check() == 0
+    st = run.chain_stats()
+    e = st["e_negloglik"]
+    want = oracle_mod.choose_chains(e, k)
+    assert list(S.select_chains(e, k)[0]) == want and len(want) == k
+    counts = run.po_counts(want)
+    for c, ch in enumerate(want):
+        assert np.array_equal(counts[c], oracle_mod.pair_order_counts(run.fetch_samples(ch, full=False)["pi"]))
+    po = S.po_finalize(counts, k)
+    assert po.shape == (273, 273) and np.all(np.diag(po) < 0)
+    for ch in (want[0], 4095):
+        o, init, res, final, tape = _oracle_chain(oracle_mod, X, hard, 0, burn, samp, philox=(seed, ch), detmath=True)
+        assert np.array_equal(run.fetch_samples(ch, full=False)["pi"], res["pi"])
+        assert abs(e[ch] - res["sums"][0] / samp) <= LL_RTOL * e[ch]
+
+
+def test_free_running_reproduces_report_table1_g10s10(S):
+    """End-to-end statistical check against the reference's published result (Docs/Report.pdf
+    Table 1, g10s10: E[c] = 0.0119, E[d] = 0.5127 over the 8 best of 100 chains; 10k burn-in +
+    10k sampling sweeps, thin 10).  Free-running Philox chains, full length."""
+    X, hard = load_hex_dataset("g10s10")
+    run = S.Run(S.Dataset.from_bits(X, hard), 100, seed=12345, store=S.STORE_PI, max_samples=1000)
+    run.init().advance(1000, False).advance(1000, True).sync()
+    assert run.check() == 0
+    st = run.chain_stats()
+    chosen, mn, sd = S.select_chains(st["e_negloglik"], 8)
+    assert len(chosen) == 8
+    e_c, e_d = st["e_c"][chosen].mean(), st["e_d"][chosen].mean()
+    assert abs(e_c - 0.0119) < 0.003, e_c
+    assert abs(e_d - 0.5127) < 0.05, e_d
+    # the seriation itself: expected correlation of the order with the file order (MN age order), 0.94 in the report
+    pis = np.concatenate([run.fetch_samples(int(c), full=False)["pi"] for c in chosen])
+    corr = np.mean([abs(np.corrcoef(p, np.arange(p.size))[0, 1]) for p in pis[::50]])
+    assert corr > 0.85, corr
