@@ -321,27 +321,36 @@ struct PropState { /* thread-uniform bookkeeping of the pi part */
 /* MH tail shared by the three proposals (mcmc.c:1261/:1441/:1636): block-reduce the integer
  * deltas, form delta, accept.  Every thread computes the same decision. */
 __device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, const SerWeights &wt, PropState &ps, int dt0,
-                                          int dt1, int *D0, int *D1, double *delta_out)
+                                          int dt1, bool exact, int *D0, int *D1, double *delta_out)
 {
   int nz;
   block_sum3(dt0, dt1, (dt0 | dt1) != 0, sm.red, ps.buf, D0, D1, &nz);
+  /* the reference's own delta: per-taxon terms in its operand order, added in taxon order */
+  auto reference_sum = [&]() {
+    double acc = 0.0;
+    __syncthreads(); /* terms[] may still be read from an earlier call */
+    if (threadIdx.x < p.M) sm.terms[p.order[threadIdx.x]] = ser_term(wt, dt0, dt1);
+    __syncthreads();
+    for (int m = 0; m < p.M; m++) acc = SER_ADD(acc, sm.terms[m]);
+    return acc;
+  };
   double delta;
+  bool seq = false;
   if (*D0 == 0 && *D1 == 0) {
+    /* The integer totals cancel.  If single taxa changed, the reference's sequential float sum
+     * (mcmc.c:1214/1435/1630) may leave a residual whose SIGN decides whether a draw is
+     * consumed: re-create that sum exactly. */
     delta = 0.0;
-    if (nz) {
-      /* The integer totals cancel but single taxa changed: the reference's sequential float sum
-       * (mcmc.c:1214/1435/1630) may leave a residual whose SIGN decides whether a draw is
-       * consumed.  Re-create that sum exactly: per-taxon terms in taxon order. */
-      if (threadIdx.x < p.M) sm.terms[p.order[threadIdx.x]] = ser_term(wt, dt0, dt1);
-      __syncthreads();
-      for (int m = 0; m < p.M; m++) delta = SER_ADD(delta, sm.terms[m]);
-    }
+    if (nz) { delta = reference_sum(); seq = true; }
   } else {
     delta = ser_term(wt, *D0, *D1);
   }
+  bool accept = delta >= 0.0;
+  if (!accept) accept = delta > sm.logdraw[ps.k++];
+  /* on a sampled sweep the saved log-likelihood must carry the reference's bits */
+  if (accept && exact && !seq && nz) delta = reference_sum();
   *delta_out = delta;
-  if (delta >= 0.0) return true;
-  return delta > sm.logdraw[ps.k++];
+  return accept;
 }
 
 /* MAXT = largest block the instantiation is launched with: the small-block instantiation may use
@@ -491,11 +500,26 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
       }
       int t1 = 0, len = 0;
       if (is_taxon) { t1 = ser_col_popc(col, pre, C, a, b); len = b - a; }
+      /* the log-likelihood is only ever observed after the last sweep of a sampling call
+       * (mcmc_save_chain); there it is formed with the reference's own sequential sums */
+      const bool exact = p.sampling && s == p.sweeps_per_call - 1;
       {
         int T1, LEN, CH;
         block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
         totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
         sc.counters[2] += CH;
+        if (exact) { /* mcmc_logl, mcmc.c:625-648: sum over taxa of t0*cc + f0*d + t1*dd + f1*c */
+          if (is_taxon) {
+            const int ones_c = p.ones[tid];
+            const int f1 = ones_c - t1, f0 = len - t1, t0 = N - len - f1;
+            sm.terms[taxon] = SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)t0, wt.cc), SER_MUL((double)f0, wt.d)), SER_MUL((double)t1, wt.dd)),
+                                      SER_MUL((double)f1, wt.c));
+          }
+          __syncthreads();
+          double acc = 0.0;
+          for (int m = 0; m < M; m++) acc = SER_ADD(acc, sm.terms[m]);
+          sc.loglik = acc;
+        }
       }
 
       /* ================= 16 proposals for pi (mcmc.c:237-243) ================= */
@@ -513,7 +537,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           const int lo = min(i, j), hi = max(i, j);
           if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
           if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
-          if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
+          if (!mh_decide(p, sm, wt, ps, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
           if (is_col) { ser_col_rotate(col, C, W, i, j); ser_col_fix_pre(col, pre, C, lo >> 5, hi >> 5); }
           for (int n = lo + tid; n <= hi; n += C)
@@ -539,7 +563,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
           ps.k += 2;
           if (is_taxon) ser_pi2_delta(col, pre, C, a, b, i, j, inc1, inc2, &dt0, &dt1);
-          if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
+          if (!mh_decide(p, sm, wt, ps, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           if (is_taxon) {
             const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
@@ -561,7 +585,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
           ps.k += 2;
           if (is_taxon) ser_pi3_delta(col, pre, C, hd, g, a, b, inc1, inc2, &dt0, &dt1);
-          if (!mh_decide(p, sm, wt, ps, dt0, dt1, &D0, &D1, &delta)) continue;
+          if (!mh_decide(p, sm, wt, ps, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
           __syncthreads();
           if (is_taxon) {
@@ -648,29 +672,36 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
  * the degenerate case re-evaluates the per-taxon deltas through `redo` (a lambda) */
 template <typename Redo>
 __device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &sm, const SerWeights &wt, PropState &ps,
-                                              double *terms, int dt0, int dt1, int nz, int *D0, int *D1, double *delta_out,
-                                              Redo redo)
+                                              double *terms, int dt0, int dt1, int nz, bool exact, int *D0, int *D1,
+                                              double *delta_out, Redo redo)
 {
   int NZ;
   block_sum3(dt0, dt1, nz, sm.red, ps.buf, D0, D1, &NZ);
+  auto reference_sum = [&]() { /* see mh_decide */
+    double acc = 0.0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.M; c += blockDim.x) {
+      int x0, x1;
+      redo(c, &x0, &x1);
+      terms[p.order[c]] = ser_term(wt, x0, x1);
+    }
+    __syncthreads();
+    for (int m = 0; m < p.M; m++) acc = SER_ADD(acc, terms[m]);
+    return acc;
+  };
   double delta;
+  bool seq = false;
   if (*D0 == 0 && *D1 == 0) {
     delta = 0.0;
-    if (NZ) { /* see mh_decide: re-create the reference's sequential per-taxon sum */
-      for (int c = threadIdx.x; c < p.M; c += blockDim.x) {
-        int x0, x1;
-        redo(c, &x0, &x1);
-        terms[p.order[c]] = ser_term(wt, x0, x1);
-      }
-      __syncthreads();
-      for (int m = 0; m < p.M; m++) delta = SER_ADD(delta, terms[m]);
-    }
+    if (NZ) { delta = reference_sum(); seq = true; }
   } else {
     delta = ser_term(wt, *D0, *D1);
   }
+  bool accept = delta >= 0.0;
+  if (!accept) accept = delta > sm.logdraw[ps.k++];
+  if (accept && exact && !seq && NZ) delta = reference_sum();
   *delta_out = delta;
-  if (delta >= 0.0) return true;
-  return delta > sm.logdraw[ps.k++];
+  return accept;
 }
 
 __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
@@ -813,12 +844,26 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
           }
         }
+        const bool exact = p.sampling && s == p.sweeps_per_call - 1;
         {
           int t1 = 0, len = 0, T1, LEN, CH;
-          for (int c = tid; c < M; c += C) { t1 += ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]); len += sm.b16[c] - sm.a16[c]; }
+          for (int c = tid; c < M; c += C) {
+            const int t1c = ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), lenc = sm.b16[c] - sm.a16[c];
+            t1 += t1c; len += lenc;
+            if (exact) { /* mcmc_logl's per-taxon term, mcmc.c:643-644 */
+              const int f1 = p.ones[c] - t1c, f0 = lenc - t1c, t0 = N - lenc - f1;
+              TERMS[p.order[c]] = SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)t0, wt.cc), SER_MUL((double)f0, wt.d)), SER_MUL((double)t1c, wt.dd)),
+                                          SER_MUL((double)f1, wt.c));
+            }
+          }
           block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
           totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
           sc.counters[2] += CH;
+          if (exact) {
+            double acc = 0.0;
+            for (int m = 0; m < M; m++) acc = SER_ADD(acc, TERMS[m]);
+            sc.loglik = acc;
+          }
         }
 
         /* ================= 16 proposals for pi ================= */
@@ -836,7 +881,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
             auto redo = [&](int c, int *x0, int *x1) { ser_pi1_delta(V + c, Cs, sm.a16[c], sm.b16[c], i, j, x0, x1); };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
-            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, &D0, &D1, &delta, redo)) continue;
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
             for (int c = tid; c <= M; c += C) {
               if (c < M) { int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b; }
               ser_col_rotate(V + c, Cs, W, i, j);
@@ -865,7 +910,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             ps.k += 2;
             auto redo = [&](int c, int *x0, int *x1) { ser_pi2_delta(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c], i, j, inc1, inc2, x0, x1); };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
-            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, &D0, &D1, &delta, redo)) continue;
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
             for (int c = tid; c <= M; c += C) {
               if (c < M) {
                 int a = sm.a16[c], b = sm.b16[c];
@@ -893,7 +938,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             ps.k += 2;
             auto redo = [&](int c, int *x0, int *x1) { ser_pi3_delta(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1); };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
-            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, &D0, &D1, &delta, redo)) continue;
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
             for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
             __syncthreads();
             for (int c = tid; c < M; c += C) {
