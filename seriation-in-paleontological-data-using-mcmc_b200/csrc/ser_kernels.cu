@@ -670,62 +670,6 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
 
 /* MH tail for the large-shape kernel: the thread's deltas are already summed over its columns;
  * the degenerate case re-evaluates the per-taxon deltas through `redo` (a lambda) */
-/* ---- warp-per-column versions of the per-column Gibbs phases (large-shape kernel): the lanes of
- * a warp stride over one column's words / items, so postings and item values are read and written
- * coalesced and the serial loops become warp scans */
-__device__ __forceinline__ void warp_expand_ones(const uint32_t *col, int Cs, int W, uint16_t *out, int lane)
-{
-  int base = 0;
-  for (int w0 = 0; w0 < W; w0 += 32) {
-    const int w = w0 + lane;
-    uint32_t v = w < W ? col[w * Cs] : 0u;
-    const int cnt = __popc(v);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    int k = base + incl - cnt;
-    while (v) { out[k++] = (uint16_t)(32 * w + __ffs(v) - 1); v &= v - 1u; }
-    base += __shfl_sync(0xffffffffu, incl, 31);
-  }
-}
-
-__device__ __forceinline__ double warp_step_lmax(const SerWeights &wt, const SerStep &st, const uint16_t *pos, int lane)
-{
-  double m = -1.0e300;
-  for (int kk = lane; kk <= st.kb; kk += 32) { int q, n; m = fmax(m, ser_item_eval(wt, st, pos, kk, &q, &n)); }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  return m;
-}
-
-/* cumulative scan of the item weights (in place), inverse CDF, pick inside the run; every lane
- * returns the picked candidate */
-__device__ __forceinline__ int warp_step_pick(const SerWeights &wt, const SerStep &st, const uint16_t *pos, double *val, double lmax,
-                                              double U, int lane)
-{
-  double carry = 0.0;
-  for (int base = 0; base <= st.kb; base += 32) {
-    const int kk = base + lane;
-    double v = kk <= st.kb ? val[kk] : 0.0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = SER_ADD(v, t); }
-    v = SER_ADD(v, carry);
-    if (kk <= st.kb) val[kk] = v;
-    carry = __shfl_sync(0xffffffffu, v, 31);
-  }
-  __syncwarp();
-  const double target = SER_MUL(U, carry);
-  int found = st.kb;
-  for (int base = 0; base <= st.kb; base += 32) {
-    const int kk = base + lane;
-    const unsigned hit = __ballot_sync(0xffffffffu, kk <= st.kb && val[kk] >= target);
-    if (hit) { found = base + __ffs(hit) - 1; break; }
-  }
-  int q, n;
-  const double le = SER_SUB(ser_item_eval(wt, st, pos, found, &q, &n), lmax);
-  return q - n + 1 + ser_run_pick(wt, n, le, found ? val[found - 1] : 0.0, target);
-}
-
 template <typename Redo>
 __device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &sm, const SerWeights &wt, PropState &ps,
                                               double *terms, int dt0, int dt1, int nz, bool exact, int *D0, int *D1,
@@ -859,21 +803,16 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
 
         /* ================= a/b Gibbs, item formulation ================= */
-        const int lane = tid & 31, wid = tid >> 5, nwarps = C >> 5;
-        for (int c = wid; c < M; c += nwarps) warp_expand_ones(V + c, Cs, W, POS + p.off[c], lane);
-        __syncthreads(); /* postings complete (and H) before any column reads them */
+        for (int c = tid; c < M; c += C) ser_expand_ones(V + c, Cs, W, POS + p.off[c]);
         int changed = 0;
 #pragma unroll 1
         for (int step = 0; step < 2; step++) {
-          for (int c = wid; c < M; c += nwarps) {
+          for (int c = tid; c < M; c += C) {
             const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
                                          : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
-            const double lm = warp_step_lmax(wt, st, POS + p.off[c], lane);
-            if (lane == 0) {
-              sm.lmax[c] = lm;
-              sm.st4[4 * c + 0] = (uint16_t)st.cur; sm.st4[4 * c + 1] = (uint16_t)st.bound;
-              sm.st4[4 * c + 2] = (uint16_t)st.ocur; sm.st4[4 * c + 3] = (uint16_t)st.kb;
-            }
+            sm.lmax[c] = ser_step_lmax(wt, st, POS + p.off[c]);
+            sm.st4[4 * c + 0] = (uint16_t)st.cur; sm.st4[4 * c + 1] = (uint16_t)st.bound;
+            sm.st4[4 * c + 2] = (uint16_t)st.ocur; sm.st4[4 * c + 3] = (uint16_t)st.kb;
           }
           __syncthreads(); /* also publishes H and POS */
           for (int e = tid; e < p.I; e += C) {
@@ -888,10 +827,10 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             }
           }
           __syncthreads();
-          for (int c = wid; c < M; c += nwarps) {
+          for (int c = tid; c < M; c += C) {
             SerStep st;
             st.cur = sm.st4[4 * c + 0]; st.bound = sm.st4[4 * c + 1]; st.ocur = sm.st4[4 * c + 2]; st.kb = sm.st4[4 * c + 3];
-            st.nones = p.ones[c]; st.N = N; st.rev = step;
+            st.nones = p.off[c + 1] - p.off[c] - 1; st.N = N; st.rev = step;
             const int taxon = p.order[c];
             double u;
             if (p.mode == SER_MODE_REPLAY) u = tape[sc.cursor + 6 + 2 * taxon + step];
@@ -900,13 +839,10 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
               u = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
             }
-            const int pick = warp_step_pick(wt, st, POS + p.off[c], VAL + p.off[c], sm.lmax[c], u, lane);
-            if (lane == 0) {
-              if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
-              else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
-            }
+            const int pick = ser_step_pick(wt, st, POS + p.off[c], VAL + p.off[c], sm.lmax[c], u);
+            if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
+            else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
           }
-          __syncthreads(); /* a16/b16 of every column final before the next step / the totals */
         }
         const bool exact = p.sampling && s == p.sweeps_per_call - 1;
         {
