@@ -377,3 +377,37 @@ def test_free_running_reproduces_report_table1_g10s10(S):
     pis = np.concatenate([run.fetch_samples(int(c), full=False)["pi"] for c in chosen])
     corr = np.mean([abs(np.corrcoef(p, np.arange(p.size))[0, 1]) for p in pis[::50]])
     assert corr > 0.85, corr
+
+
+def test_launch_splitting_is_invisible(S):
+    """advance(n) == n x advance(1): the chain state carried through HBM between launches is complete"""
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    one = S.Run(ds, 5, seed=77, store=S.STORE_FULL, max_samples=6).init().advance(4, False).advance(6, True).sync()
+    many = S.Run(ds, 5, seed=77, store=S.STORE_FULL, max_samples=6).init()
+    for c in range(10):
+        many.advance(1, c >= 4)
+    many.sync()
+    for i in range(5):
+        a, b = one.state(i), many.state(i)
+        for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+            assert np.array_equal(a[k], b[k]), (i, k)
+        assert (a["c"], a["d"], a["loglik"]) == (b["c"], b["d"], b["loglik"])
+        sa, sb = one.fetch_samples(i), many.fetch_samples(i)
+        assert all(np.array_equal(sa[k], sb[k]) for k in sa)
+    assert np.array_equal(one.chain_stats()["e_negloglik"], many.chain_stats()["e_negloglik"])
+    assert np.array_equal(one.counters(0), many.counters(0)) and one.counters(0)[7] == 100
+
+
+def test_sample_store_capacity_and_modes(S):
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    run = S.Run(ds, 2, seed=1, store=S.STORE_PI, max_samples=3).init().advance(5, True).sync()
+    assert run.chain_stats()["n_samples"] == 5              # the exp_data sums keep running ...
+    assert run.fetch_samples(0, full=False)["pi"].shape == (3, 124)   # ... the store keeps the first max_samples
+    with pytest.raises(S.SeriationError):
+        run.fetch_samples(0, full=True)                      # a, b, c, d were not stored
+    none = S.Run(ds, 2, seed=1).init().advance(2, True).sync()
+    with pytest.raises(S.SeriationError):
+        none.po_counts([0])                                  # no pi history without SER_STORE_PI
+    assert none.chain_stats()["n_samples"] == 2
