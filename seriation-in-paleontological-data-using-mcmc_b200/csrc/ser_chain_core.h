@@ -13,7 +13,8 @@
  * CPU-side testing of the same logic, in tests/emul/chain_emul.cpp.
  *
  * Reference (file:line under /root/reference/C_Implementation):
- *   ser_gibbs_boundary  mcmc_auxa :828-898 + mcmc_logtop :711-748 + mcmc_randompick :901-915
+ *   ser_step_a/_b, ser_item_eval/_weight, ser_run_sum/_pick, ser_step_lmax/_pick
+ *                       mcmc_auxa :828-898 + mcmc_logtop :711-748 + mcmc_randompick :901-915
  *   ser_pi1_delta       mcmc_samplepi1 :1171-1256
  *   ser_pi2_delta       mcmc_samplepi2 :1363-1436 (with mcmc_ininterval :1097-1124)
  *   ser_pi3_delta       mcmc_samplepi3 :1564-1631
@@ -75,31 +76,8 @@ SER_HD uint32_t ser_range_mask(int w, int lo, int hi)
   return ser_mask_lt(h) & ~ser_mask_lt(l);
 }
 
-/* position of the (k+1)-th set bit of mask (k from 0); mask must have > k bits set */
-SER_HD int ser_select_bit(uint32_t mask, int k)
-{
-#if defined(__CUDA_ARCH__)
-  return (int)__fns(mask, 0u, k + 1);
-#else
-  for (int i = 0; i < k; i++) mask &= mask - 1u;
-  return SER_FFS(mask) - 1;
-#endif
-}
-
 /* ------------------------------------------------------------------ columns */
-/* A column is addressed as col[w * C]; words >= W and < 0 read as zero. */
-SER_HD uint32_t ser_col_word(const uint32_t *col, int C, int W, int w)
-{
-  return (w >= 0 && w < W) ? col[w * C] : 0u;
-}
-
-/* 32 bits of the column starting at bit position p (p may be negative / beyond the end) */
-SER_HD uint32_t ser_col_extract32(const uint32_t *col, int C, int W, int p)
-{
-  const int w = p >> 5; /* arithmetic shift: floor */
-  return ser_funnel_r(ser_col_word(col, C, W, w), ser_col_word(col, C, W, w + 1), p & 31);
-}
-
+/* A column is addressed as col[w * C] (word w of the column, stride C words). */
 SER_HD int ser_col_bit(const uint32_t *col, int C, int p) { return (col[(p >> 5) * C] >> (p & 31)) & 1u; }
 
 /* ones in bits [0, p), p in [0, N]: prefix table + one POPC */
@@ -129,14 +107,6 @@ SER_HD void ser_col_fix_pre(const uint32_t *col, uint16_t *pre, int C, int w0, i
 {
   int acc = pre[w0 * C];
   for (int w = w0; w < w1; w++) { acc += SER_POPC(col[w * C]); pre[(w + 1) * C] = (uint16_t)acc; }
-}
-
-/* word j of the logical string s: REV ? s[k] = v[N-1-k] : s = v */
-template <bool REV>
-SER_HD uint32_t ser_logical_word(const uint32_t *col, int C, int W, int N, int j)
-{
-  if (!REV) return col[j * C];
-  return SER_BREV(ser_col_extract32(col, C, W, N - 32 - 32 * j));
 }
 
 /* in-place: reverse bits [i, j] (new[p] = old[i+j-p]) */
@@ -307,13 +277,6 @@ SER_HD double ser_exp_weight(double x)
   p = ser_fma(p, r, 1.0);
   const int64_t k = (int64_t)(int32_t)(uint32_t)ser_d2u(t); /* low word of the magic sum = k */
   return ser_u2d(ser_d2u(p) + ((uint64_t)k << 52));
-}
-
-/* log-weight (up to a constant) of the candidate that has `dn1` more ones and `di` more cells
- * below it than the reference point: -(dn1 w1 + (di - dn1) w0) = dn1 (w0 - w1) + di (-w0) */
-SER_HD double ser_logw(const SerWeights &w, int dn1, int di, double c0)
-{
-  return ser_fma(ser_i2d(dn1), w.A, ser_fma(ser_i2d(di), w.g, c0));
 }
 
 /*
