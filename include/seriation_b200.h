@@ -21,6 +21,8 @@
  *   ser_write_chain_files     main's five fopen()s      mcmc.c:148-197, :261-294
  *   ser_select_chains*        choose_chains             script.py:70-99
  *   ser_run_po_counts*        compute_pair_order_matrix script.py:155-189
+ *   ser_run_posterior_sums    compute_exp_ages / compute_exp_pi / compute_exp_a
+ *                                                       script.py:129-152, :230-276
  *   run_all_chains' Pool(8) over 100 processes (script.py:48-67) is replaced by
  *   n_chains in ser_run_config: one CTA per chain in one launch.
  */
@@ -143,6 +145,16 @@ int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *c
 /* script.py:155-175 finalisation incl. the reference's carry-over between chains when faithful != 0 */
 int ser_po_finalize(const int32_t *counts, int32_t k, int32_t N, int32_t chains_selected, int32_t faithful,
                     double *po);
+
+/* per-chain sums over the stored thinned samples of the chosen chains owned by this run
+ * (GLOBAL ids; others / -1 leave their slab untouched; zero the buffers first; host memory):
+ *   corr_num[c]  = sum_t sum_i i * pi_t(i)   -> mean Pearson r of pi with 0..N-1 (script.py:129-152):
+ *                  r = (corr_num/(T*N) - ((N-1)/2)^2) / ((N^2-1)/12), exact because pi_t is a permutation
+ *   pi_sum[c][i] = sum_t pi_t(i)   (script.py:230-252)      needs SER_STORE_PI
+ *   a_sum[c][m]  = sum_t a_t(m), b_sum likewise (script.py:255-276)   need SER_STORE_FULL; may be NULL
+ * n_samples receives T. */
+int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32_t k, int64_t *corr_num, int32_t *pi_sum,
+                           int32_t *a_sum, int32_t *b_sum, int32_t *n_samples);
 
 /* ---------------------------------------------------------------- reference-compatible files */
 /* Writes Chains-style files for one local chain into `dir` (which must exist, like the

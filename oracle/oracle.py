@@ -327,3 +327,41 @@ def pair_order_matrix(per_chain_counts, chains_selected: int, faithful: bool = T
         po += acc
         carry = acc
     return po / chains_selected
+
+
+def exp_ages(pi_samples_per_chain, chains_selected: int) -> float:
+    """script.py:129-152 verbatim in numpy: per chain sum_t pearsonr(pi_t, arange(N)) / 1000, summed, / chains_selected"""
+    total = 0.0
+    for pis in pi_samples_per_chain:
+        pis = np.asarray(pis, dtype=np.float64)
+        ref = np.arange(pis.shape[1], dtype=np.float64)
+        s = 0.0
+        for p in pis:
+            s += np.corrcoef(p, ref)[0, 1]
+        total += s / 1000
+    return total / chains_selected
+
+
+def exp_pi(pi_samples_per_chain, chains_selected: int) -> np.ndarray:
+    """script.py:230-252 verbatim: pi_sum reset inside the loop (:243), pi_sum_chain never reset"""
+    pi_sum = 0
+    pi_sum_chain = np.zeros(np.asarray(pi_samples_per_chain[0]).shape[1])
+    for pis in pi_samples_per_chain:
+        pi_sum = 0
+        for p in np.asarray(pis):
+            pi_sum_chain += p
+        pi_sum_chain /= 1000
+        pi_sum += pi_sum_chain
+    return pi_sum / chains_selected
+
+
+def exp_a(a_samples_per_chain, chains_selected: int) -> np.ndarray:
+    """script.py:255-276 verbatim: a_sum accumulates, a_sum_chain never reset"""
+    a_sum = np.zeros(np.asarray(a_samples_per_chain[0]).shape[1])
+    a_sum_chain = np.zeros_like(a_sum)
+    for a_s in a_samples_per_chain:
+        for a in np.asarray(a_s):
+            a_sum_chain += a
+        a_sum_chain /= 1000
+        a_sum += a_sum_chain
+    return a_sum / chains_selected

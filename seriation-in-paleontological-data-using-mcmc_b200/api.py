@@ -68,6 +68,7 @@ SYMBOLS = [
     ("ser_run_po_counts_device", C.c_int, [_vp, _vp, C.c_int32, _vp]),
     ("ser_run_po_counts", C.c_int, [_vp, _i32p, C.c_int32, _i32p]),
     ("ser_po_finalize", C.c_int, [_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]),
+    ("ser_run_posterior_sums", C.c_int, [_vp, _i32p, C.c_int32, _i64p, _i32p, _i32p, _i32p, _i32p]),
     ("ser_write_chain_files", C.c_int, [_vp, C.c_int32, C.c_char_p]),
     ("ser_microbench", C.c_int, [C.c_int32, _dp]),
 ]
@@ -262,6 +263,18 @@ class Run:
         _check(lib().ser_run_po_counts(self._h, _p(chosen, C.c_int32), len(chosen), _p(out, C.c_int32)))
         return out
 
+    def posterior_sums(self, chosen, with_ab: bool = False) -> dict:
+        """per chosen chain: sum_t sum_i i*pi_t(i), sum_t pi_t, (sum_t a_t, sum_t b_t) over the stored samples"""
+        chosen = np.ascontiguousarray(chosen, dtype=np.int32)
+        k = len(chosen)
+        corr, pi_sum = np.zeros(k, np.int64), np.zeros((k, self.N), np.int32)
+        a_sum = np.zeros((k, self.M), np.int32) if with_ab else None
+        b_sum = np.zeros((k, self.M), np.int32) if with_ab else None
+        n = C.c_int32()
+        _check(lib().ser_run_posterior_sums(self._h, _p(chosen, C.c_int32), k, _p(corr, C.c_int64), _p(pi_sum, C.c_int32),
+                                            _p(a_sum, C.c_int32), _p(b_sum, C.c_int32), C.byref(n)))
+        return dict(corr_num=corr, pi_sum=pi_sum, a_sum=a_sum, b_sum=b_sum, n_samples=n.value)
+
     def po_counts_device(self, chosen_ptr: int, k: int, counts_ptr: int):
         _check(lib().ser_run_po_counts_device(self._h, chosen_ptr, k, counts_ptr))
 
@@ -350,6 +363,48 @@ def compute_exp_cd(batch: ChainBatch, chains, chains_selected: int):
     st = batch.stats()
     return (float(np.sum(st["e_c"][list(chains)]) / chains_selected),
             float(np.sum(st["e_d"][list(chains)]) / chains_selected))
+
+
+def pearson_from_corr_num(corr_num, n_samples: int, n_sites: int):
+    """mean over samples of pearsonr(pi_t, arange(N)) from sum_t sum_i i*pi_t(i): pi_t is a permutation of
+    0..N-1, so both series have mean (N-1)/2 and variance (N^2-1)/12"""
+    N = float(n_sites)
+    mean, var = (N - 1.0) / 2.0, (N * N - 1.0) / 12.0
+    return (np.asarray(corr_num, dtype=np.float64) / (n_samples * N) - mean * mean) / var
+
+
+def carry_over_mean(per_chain_sums, chains_selected: int, keep_total: bool, faithful: bool = True):
+    """The accumulation pattern of compute_exp_pi / compute_exp_a (script.py:230-276): the per-chain
+    accumulator is divided by 1000 but never reset, so chain c starts from chain c-1's scaled values
+    (``faithful``); compute_exp_a adds every chain's accumulator into the total (``keep_total``), while
+    compute_exp_pi resets the total inside the loop (:243), so only the LAST chain's accumulator survives."""
+    carry = np.zeros_like(np.asarray(per_chain_sums[0], dtype=np.float64))
+    total = np.zeros_like(carry)
+    for sums in per_chain_sums:
+        acc = ((carry if faithful else 0.0) + np.asarray(sums, dtype=np.float64)) / 1000
+        total = total + acc if (keep_total or not faithful) else acc
+        carry = acc
+    return total / chains_selected
+
+
+def compute_exp_ages(batch: ChainBatch, chains, chains_selected: int, sites: int | None = None):
+    """script.py:129-152: expected Pearson correlation of pi with the file order, per-chain means (divided by the
+    literal 1000) summed over the chosen chains and divided by ``chains_selected``."""
+    ps = batch.run.posterior_sums(np.asarray(chains, dtype=np.int32))
+    r = pearson_from_corr_num(ps["corr_num"], ps["n_samples"], batch.run.N)   # mean over the T stored samples
+    return float(np.sum(r * ps["n_samples"] / 1000) / chains_selected)
+
+
+def compute_exp_pi(batch: ChainBatch, chains, sites: int | None, chains_selected: int, faithful: bool = True):
+    """script.py:230-252 (with its reset/carry-over quirks when ``faithful``)"""
+    ps = batch.run.posterior_sums(np.asarray(chains, dtype=np.int32))
+    return carry_over_mean(list(ps["pi_sum"]), chains_selected, keep_total=False, faithful=faithful)
+
+
+def compute_exp_a(batch: ChainBatch, chains, chains_selected: int, taxa: int | None = None, faithful: bool = True):
+    """script.py:255-276; needs a batch created with the full sample store"""
+    ps = batch.run.posterior_sums(np.asarray(chains, dtype=np.int32), with_ab=True)
+    return carry_over_mean(list(ps["a_sum"]), chains_selected, keep_total=True, faithful=faithful)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1157,6 +1157,31 @@ __global__ void ser_po_kernel(const uint16_t *samp_pi, int N, int max_samples, i
   counts[((size_t)blockIdx.z * N + i) * N + j] = (i == j) ? -n_samples : c;
 }
 
+/* posterior sums over the stored samples of one chosen chain per block (script.py:129-152, :230-276) */
+__global__ void ser_posterior_kernel(const uint16_t *samp_pi, const uint16_t *samp_a, const uint16_t *samp_b, int N, int M,
+                                     int max_samples, int n_samples, const int *chosen, int chain_offset, int n_local,
+                                     long long *corr_num, int *pi_sum, int *a_sum, int *b_sum)
+{
+  const int g = chosen[blockIdx.x];
+  if (g < chain_offset || g >= chain_offset + n_local) return;
+  const size_t base = (size_t)(g - chain_offset) * max_samples;
+  long long s = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    int acc = 0;
+    for (int t = 0; t < n_samples; t++) acc += samp_pi[(base + t) * N + i];
+    pi_sum[(size_t)blockIdx.x * N + i] = acc;
+    s += (long long)i * acc;
+  }
+  if (a_sum && samp_a)
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+      int sa = 0, sb = 0;
+      for (int t = 0; t < n_samples; t++) { sa += samp_a[(base + t) * M + m]; sb += samp_b[(base + t) * M + m]; }
+      a_sum[(size_t)blockIdx.x * M + m] = sa;
+      if (b_sum) b_sum[(size_t)blockIdx.x * M + m] = sb;
+    }
+  atomicAdd((unsigned long long *)&corr_num[blockIdx.x], (unsigned long long)s);
+}
+
 /* ------------------------------------------------------------------ micro-benchmarks */
 __global__ void mb_fp64_kernel(double *out, int iters)
 {
@@ -1703,6 +1728,48 @@ extern "C" int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k,
   }
   cudaFreeAsync(d_ch, run->stream); cudaFreeAsync(d_cnt, run->stream);
   return rc;
+}
+
+extern "C" int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32_t k, int64_t *corr_num, int32_t *pi_sum,
+                                      int32_t *a_sum, int32_t *b_sum, int32_t *n_samples)
+{
+  if (!run || !chosen || !corr_num || !pi_sum || k < 1) { ser_set_error("ser_run_posterior_sums: bad argument"); return SER_E_ARG; }
+  if (run->cfg.store < SER_STORE_PI) { ser_set_error("ser_run_posterior_sums: run has no pi sample store"); return SER_E_STATE; }
+  if ((a_sum || b_sum) && run->cfg.store < SER_STORE_FULL) { ser_set_error("ser_run_posterior_sums: a/b sums need SER_STORE_FULL"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples, N = run->N, M = run->M;
+  int *d_ch = nullptr, *d_pi = nullptr, *d_a = nullptr, *d_b = nullptr;
+  long long *d_corr = nullptr;
+  CUDA_TRY(POOL_ALLOC(&d_ch, k * sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&d_corr, k * sizeof(long long)));
+  CUDA_TRY(POOL_ALLOC(&d_pi, (size_t)k * N * sizeof(int)));
+  if (a_sum) { CUDA_TRY(POOL_ALLOC(&d_a, (size_t)k * M * sizeof(int))); CUDA_TRY(POOL_ALLOC(&d_b, (size_t)k * M * sizeof(int))); }
+  CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_corr, corr_num, k * sizeof(long long), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_pi, pi_sum, (size_t)k * N * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  if (a_sum) {
+    CUDA_TRY(cudaMemcpyAsync(d_a, a_sum, (size_t)k * M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+    if (b_sum) CUDA_TRY(cudaMemcpyAsync(d_b, b_sum, (size_t)k * M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  }
+  mark_launch(run);
+  ser_posterior_kernel<<<k, 256, 0, run->stream>>>(run->d_samp_pi, run->d_samp_a, run->d_samp_b, N, M, run->cfg.max_samples, ns, d_ch,
+                                                   run->cfg.chain_offset, run->cfg.n_chains, d_corr, d_pi, d_a, b_sum ? d_b : nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(corr_num, d_corr, k * sizeof(long long), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(pi_sum, d_pi, (size_t)k * N * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+  if (a_sum) {
+    CUDA_TRY(cudaMemcpyAsync(a_sum, d_a, (size_t)k * M * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+    if (b_sum) CUDA_TRY(cudaMemcpyAsync(b_sum, d_b, (size_t)k * M * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  cudaFreeAsync(d_ch, run->stream); cudaFreeAsync(d_corr, run->stream); cudaFreeAsync(d_pi, run->stream);
+  if (d_a) cudaFreeAsync(d_a, run->stream);
+  if (d_b) cudaFreeAsync(d_b, run->stream);
+  if (n_samples) *n_samples = ns;
+  return SER_OK;
 }
 
 extern "C" int ser_microbench(int32_t device, double out[3])

@@ -128,3 +128,24 @@ def test_po_finalize_matches_script_semantics(S, oracle_mod):
         want = oracle_mod.pair_order_matrix(per_chain, 3, faithful)
         got = S.po_finalize(counts, 3, faithful)
         assert np.allclose(got, want, rtol=0, atol=1e-15)
+
+
+def test_posterior_summary_finalisers_match_script_semantics(S, oracle_mod):
+    """compute_exp_ages / compute_exp_pi / compute_exp_a (script.py:129-152, :230-276) incl. their
+    reset / carry-over quirks, from per-chain sums (the GPU produces the sums)."""
+    rng = np.random.default_rng(9)
+    N, M, T, k = 19, 11, 30, 3
+    pis = [np.array([rng.permutation(N) for _ in range(T)]) for _ in range(k)]
+    a_s = [rng.integers(0, N, size=(T, M)) for _ in range(k)]
+    corr_num = np.array([int((p * np.arange(N)).sum()) for p in pis])
+    r = S.pearson_from_corr_num(corr_num, T, N)
+    for c in range(k):
+        want = np.mean([np.corrcoef(p, np.arange(N))[0, 1] for p in pis[c]])
+        assert abs(r[c] - want) < 1e-12
+    assert abs(float(np.sum(r * T / 1000) / k) - oracle_mod.exp_ages(pis, k)) < 1e-12
+    got_pi = S.carry_over_mean([p.sum(axis=0) for p in pis], k, keep_total=False)
+    assert np.allclose(got_pi, oracle_mod.exp_pi(pis, k), rtol=0, atol=1e-12)
+    got_a = S.carry_over_mean([a.sum(axis=0) for a in a_s], k, keep_total=True)
+    assert np.allclose(got_a, oracle_mod.exp_a(a_s, k), rtol=0, atol=1e-12)
+    clean = S.carry_over_mean([p.sum(axis=0) for p in pis], k, keep_total=False, faithful=False)
+    assert np.allclose(clean, sum(p.sum(axis=0) for p in pis) / 1000 / k)

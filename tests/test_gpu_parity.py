@@ -411,3 +411,24 @@ def test_sample_store_capacity_and_modes(S):
     with pytest.raises(S.SeriationError):
         none.po_counts([0])                                  # no pi history without SER_STORE_PI
     assert none.chain_stats()["n_samples"] == 2
+
+
+def test_posterior_summaries_on_device(S, oracle_mod):
+    """SURVEY section 8f #1: compute_exp_ages / compute_exp_pi / compute_exp_a over the GPU's sample store"""
+    X, hard = load_hex_dataset("g10s10")
+    batch = S.run_all_chains(S.Dataset.from_bits(X, hard), 24, 30, 16, seed=4, store=S.STORE_FULL)
+    chains = S.choose_chains(batch, 3)
+    assert len(chains) == 3
+    samples = [batch.run.fetch_samples(c) for c in chains]
+    ps = batch.run.posterior_sums(chains, with_ab=True)
+    assert ps["n_samples"] == 16
+    for slot, smp in enumerate(samples):
+        assert np.array_equal(ps["pi_sum"][slot], smp["pi"].sum(axis=0))
+        assert np.array_equal(ps["a_sum"][slot], smp["a"].sum(axis=0)) and np.array_equal(ps["b_sum"][slot], smp["b"].sum(axis=0))
+        assert ps["corr_num"][slot] == int((smp["pi"] * np.arange(124)).sum())
+    pis, a_s = [s["pi"] for s in samples], [s["a"] for s in samples]
+    assert abs(S.compute_exp_ages(batch, chains, 3, 124) - oracle_mod.exp_ages(pis, 3)) < 1e-12
+    assert np.allclose(S.compute_exp_pi(batch, chains, 124, 3), oracle_mod.exp_pi(pis, 3), rtol=0, atol=1e-12)
+    assert np.allclose(S.compute_exp_a(batch, chains, 3, 139), oracle_mod.exp_a(a_s, 3), rtol=0, atol=1e-12)
+    exp_c, exp_d = S.compute_exp_cd(batch, chains, 3)
+    assert 0.001 < exp_c < 0.1 and 0.2 < exp_d < 0.8
