@@ -161,6 +161,11 @@ int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32_t k, int64
  * reference): chain_data.csv, exp_data.csv, taxa.csv, sites.csv, hard_sites.csv. */
 int ser_write_chain_files(ser_run *run, int32_t chain, const char *dir);
 
+/* Labelled companions of taxa.csv / sites.csv for a dataset that carries names
+ * (ser_dataset_read_names): taxa_named.csv "taxon,a,b" and sites_named.csv
+ * "site,mn_unit,age_ma,hard,pi" (final state of one local chain). */
+int ser_write_labelled_files(ser_run *run, int32_t chain, const ser_dataset *ds, const char *dir);
+
 /* micro-benchmarks of the SM-local ceilings the sweep is bound by (DESIGN.md "roofline"):
  * out[0] = fp64 FMA TFLOP/s, out[1] = shared-memory load GB/s, out[2] = popc Gop/s */
 int ser_microbench(int32_t device, double out[3]);

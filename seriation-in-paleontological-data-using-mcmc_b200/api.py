@@ -70,6 +70,7 @@ SYMBOLS = [
     ("ser_po_finalize", C.c_int, [_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]),
     ("ser_run_posterior_sums", C.c_int, [_vp, _i32p, C.c_int32, _i64p, _i32p, _i32p, _i32p, _i32p]),
     ("ser_write_chain_files", C.c_int, [_vp, C.c_int32, C.c_char_p]),
+    ("ser_write_labelled_files", C.c_int, [_vp, C.c_int32, _vp, C.c_char_p]),
     ("ser_microbench", C.c_int, [C.c_int32, _dp]),
 ]
 
@@ -280,6 +281,9 @@ class Run:
 
     def write_chain_files(self, chain: int, directory: str):
         _check(lib().ser_write_chain_files(self._h, chain, directory.encode()))
+
+    def write_labelled_files(self, chain: int, directory: str):
+        _check(lib().ser_write_labelled_files(self._h, chain, self.ds._h, directory.encode()))
 
 
 def select_chains(e_negloglik, k: int):

@@ -427,3 +427,38 @@ done:
   free(a); free(b); free(pi); free(c); free(d); free(ll); free(fa); free(fb); free(fpi);
   return rc;
 }
+
+/* labelled final state: names from the .genus / .sites files next to the sampler's a, b, pi */
+int ser_write_labelled_files(ser_run *run, int32_t chain, const ser_dataset *ds, const char *dir)
+{
+  int32_t N, M, nh, nc;
+  char path[1024];
+  FILE *f;
+  if (!run || !ds || !dir) { ser_set_error("ser_write_labelled_files: null argument"); return SER_E_ARG; }
+  ser_run_dims(run, &N, &M, &nh, &nc);
+  if (ds->N != N || ds->M != M) { ser_set_error("ser_write_labelled_files: dataset does not match the run"); return SER_E_ARG; }
+  if (!ds->taxon_names || !ds->site_names) { ser_set_error("ser_write_labelled_files: no labels loaded (ser_dataset_read_names)"); return SER_E_STATE; }
+  int32_t *a = (int32_t *)malloc((size_t)M * 4), *b = (int32_t *)malloc((size_t)M * 4), *pi = (int32_t *)malloc((size_t)N * 4);
+  int rc = ser_run_get_state(run, chain, a, b, pi, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+  if (!rc) {
+    snprintf(path, sizeof(path), "%s/taxa_named.csv", dir);
+    if (!(f = fopen(path, "w"))) { ser_set_error("cannot open %s", path); rc = SER_E_IO; }
+    else {
+      fprintf(f, "taxon,a,b\n");
+      for (int32_t m = 0; m < M; m++) fprintf(f, "%s,%d,%d\n", ds->taxon_names[m], a[m], b[m]);
+      fclose(f);
+    }
+  }
+  if (!rc) {
+    snprintf(path, sizeof(path), "%s/sites_named.csv", dir);
+    if (!(f = fopen(path, "w"))) { ser_set_error("cannot open %s", path); rc = SER_E_IO; }
+    else {
+      fprintf(f, "site,mn_unit,age_ma,hard,pi\n");
+      for (int32_t n = 0; n < N; n++)
+        fprintf(f, "%s,%d,%g,%d,%d\n", ds->site_names[n], ds->site_mn[n], ds->site_age[n], (int)ds->hard[n], pi[n]);
+      fclose(f);
+    }
+  }
+  free(a); free(b); free(pi);
+  return rc;
+}

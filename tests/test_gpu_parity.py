@@ -432,3 +432,21 @@ def test_posterior_summaries_on_device(S, oracle_mod):
     assert np.allclose(S.compute_exp_a(batch, chains, 3, 139), oracle_mod.exp_a(a_s, 3), rtol=0, atol=1e-12)
     exp_c, exp_d = S.compute_exp_cd(batch, chains, 3)
     assert 0.001 < exp_c < 0.1 and 0.2 < exp_d < 0.8
+
+
+def test_labelled_outputs(S, tmp_path):
+    X = (np.random.default_rng(2).random((12, 5)) < .4).astype(np.uint8)
+    hard = np.zeros(12, np.uint8); hard[[2, 9]] = 1
+    ds = S.Dataset.from_bits(X, hard)
+    (tmp_path / "t.genus").write_text("".join("Genus_%d \n" % m for m in range(5)))
+    (tmp_path / "t.sites").write_text("".join("Site_%d [%d,%.2f]%s\n" % (n, n // 3, 20 - n, " *" if hard[n] else "") for n in range(12)))
+    run = S.Run(ds, 1, seed=3).init().advance(3, False).sync()
+    with pytest.raises(S.SeriationError):
+        run.write_labelled_files(0, str(tmp_path))            # no labels yet
+    ds.read_names(str(tmp_path / "t.genus"), str(tmp_path / "t.sites"))
+    run.write_labelled_files(0, str(tmp_path))
+    st = run.state(0)
+    taxa = (tmp_path / "taxa_named.csv").read_text().split("\n")
+    assert taxa[0] == "taxon,a,b" and taxa[1] == "Genus_0,%d,%d" % (st["a"][0], st["b"][0])
+    sites = (tmp_path / "sites_named.csv").read_text().split("\n")
+    assert sites[3] == "Site_2,0,18,1,%d" % st["pi"][2]
