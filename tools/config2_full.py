@@ -4,7 +4,7 @@
 MT19937 seeds 0..99, one process per host core), replayed on one B200 and compared bit for bit.
 
     python tools/config2_full.py [n_chains=100] [burn=1000] [samp=1000] [dataset=g10s2]
-Writes gpurun_out/config2_full.json."""
+Writes gpurun_out/replay_full_<dataset>_<chains>x<sweeps>.json."""
 import json
 import os
 import sys
@@ -65,7 +65,7 @@ def main():
                gpu_seconds=t_gpu, inconsistent_chains=bad, chains_with_mismatch=mism, max_loglik_rel_err=max_ll_rel,
                passed=bool(bad == 0 and not any(mism.values())))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "config2_full.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "replay_full_%s_%dx%d.json" % (name, n, 10 * (burn + samp))), "w"), indent=1)
     print(json.dumps(out))
 
 
