@@ -50,6 +50,7 @@ typedef struct draw_source {
   /* structured Philox */
   uint32_t seed, chain, sweep, block, idx;
   int state;
+  int manycd, ntaxa, nbeta; /* manycd: M Betas for c then M for d per sweep; nbeta counts them */
   /* tape in */
   const double *tape;
   size_t tape_len, cur;
@@ -108,7 +109,7 @@ static inline void ds_init_mt(draw_source *s, unsigned long seed)
 
 static inline void ds_init_philox(draw_source *s, uint32_t seed, uint32_t chain)
 {
-  memset(s, 0, sizeof(*s));
+  memset(s, 0, sizeof(*s)); /* scalar c/d; ds_set_manycd() switches to per-taxon Betas */
   s->kind = DS_PHILOX;
   s->seed = seed;
   s->chain = chain;
@@ -116,6 +117,8 @@ static inline void ds_init_philox(draw_source *s, uint32_t seed, uint32_t chain)
   s->block = SER_BLK_INIT;
   s->state = DS_ST_INIT;
 }
+
+static inline void ds_set_manycd(draw_source *s, int ntaxa) { s->manycd = 1; s->ntaxa = ntaxa; }
 
 static inline void ds_init_tape(draw_source *s, const double *tape, size_t len)
 {
@@ -234,6 +237,21 @@ static inline double ds_beta(draw_source *s, double a, double b, double *logy, d
     if (s->kind == DS_MT) {
       double g1 = ds_mt_gamma(s, a), g2 = ds_mt_gamma(s, b);
       y = g1 / (g1 + g2);
+    } else if (s->manycd) {
+      /* per-taxon c then per-taxon d: Beta number k of the sweep belongs to taxon k % M */
+      uint32_t blk;
+      if (s->state != DS_ST_C && s->state != DS_ST_D) { /* first Beta of a new sweep */
+        s->sweep = (s->state == DS_ST_INIT) ? 0u : s->sweep + 1u;
+        s->state = DS_ST_C;
+        s->nbeta = 0;
+      }
+      blk = SER_BLK_MANYCD + 4u * (uint32_t)(s->nbeta % s->ntaxa) + (s->nbeta >= s->ntaxa ? 2u : 0u);
+      if (++s->nbeta >= s->ntaxa) s->state = DS_ST_D;
+      {
+        double g1 = ser_gamma_ge1(a, s->seed, s->chain, s->sweep, blk);
+        double g2 = ser_gamma_ge1(b, s->seed, s->chain, s->sweep, blk + 1u);
+        y = ser_beta_from_gammas(g1, g2);
+      }
     } else {
       uint32_t blk;
       if (s->state == DS_ST_C) { s->state = DS_ST_D; blk = SER_BLK_D_GAMMA_A; }
@@ -242,9 +260,11 @@ static inline double ds_beta(draw_source *s, double a, double b, double *logy, d
         s->state = DS_ST_C;
         blk = SER_BLK_C_GAMMA_A;
       }
-      double g1 = ser_gamma_ge1(a, s->seed, s->chain, s->sweep, blk);
-      double g2 = ser_gamma_ge1(b, s->seed, s->chain, s->sweep, blk + 1u);
-      y = ser_beta_from_gammas(g1, g2);
+      {
+        double g1 = ser_gamma_ge1(a, s->seed, s->chain, s->sweep, blk);
+        double g2 = ser_gamma_ge1(b, s->seed, s->chain, s->sweep, blk + 1u);
+        y = ser_beta_from_gammas(g1, g2);
+      }
     }
     ly = (y > 0.0) ? log(y) : -INFINITY;
     l1 = log(1. - exp(ly));

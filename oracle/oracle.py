@@ -59,6 +59,8 @@ def lib():
         L.orc_tape_mismatches.restype = C.c_longlong
         L.orc_tape_mismatches.argtypes = [vp]
         L.orc_set_detmath.argtypes = [vp, C.c_int]
+        L.orc_set_manycd.argtypes = [vp, C.c_int]
+        L.orc_get_cd.argtypes = [vp, dp, dp]
         for name in ("orc_randomize", "orc_recount"):
             getattr(L, name).argtypes = [vp]
             getattr(L, name).restype = None
@@ -133,21 +135,27 @@ class State:
     c: float
     d: float
     loglik: float
+    c_all: np.ndarray = None   # per-taxon c, d (manycd)
+    d_all: np.ndarray = None
 
     def same_ints(self, o: "State") -> bool:
         return all(np.array_equal(getattr(self, k), getattr(o, k))
                    for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"))
 
     def same_bits(self, o: "State") -> bool:
-        return self.same_ints(o) and struct.pack("3d", self.c, self.d, self.loglik) == \
+        ok = self.same_ints(o) and struct.pack("3d", self.c, self.d, self.loglik) == \
             struct.pack("3d", o.c, o.d, o.loglik)
+        if ok and self.c_all is not None and o.c_all is not None:
+            ok = self.c_all.tobytes() == o.c_all.tobytes() and self.d_all.tobytes() == o.d_all.tobytes()
+        return ok
 
 
 def read_dump(path: str):
     """Parse a dump written by ``ref_mcmc trace`` (format in oracle/ref_harness.c)."""
     buf = open(path, "rb").read()
     magic, N, M, nh = struct.unpack_from("<4i", buf, 0)
-    assert magic == 0x5345524D, "bad dump magic"
+    assert magic in (0x5345524D, 0x5345524E), "bad dump magic"
+    manycd = magic == 0x5345524E
     off = 16
     rec_ints = 2 * M + 2 * N + 4 * M + 4
     out = []
@@ -158,12 +166,17 @@ def read_dump(path: str):
         off += 4 * rec_ints
         c, d, ll = struct.unpack_from("<3d", buf, off)
         off += 24
+        c_all = d_all = None
+        if manycd:
+            c_all = np.frombuffer(buf, dtype="<f8", count=M, offset=off).copy()
+            d_all = np.frombuffer(buf, dtype="<f8", count=M, offset=off + 8 * M).copy()
+            off += 16 * M
         o = 0
         fields = []
         for ln in (M, M, N, N, M, M, M, M, 4):
             fields.append(ints[o:o + ln])
             o += ln
-        out.append(State(kind, ret, slots, *fields, c, d, ll))
+        out.append(State(kind, ret, slots, *fields, c, d, ll, c_all, d_all))
     return (N, M, nh), out
 
 
@@ -212,6 +225,17 @@ class Oracle:
         lib().orc_set_detmath(self._h, int(on))
         return self
 
+    def manycd(self, on: bool = True):
+        """per-taxon c, d; call BEFORE choosing the draw source"""
+        lib().orc_set_manycd(self._h, int(on))
+        self._manycd = bool(on)
+        return self
+
+    def cd(self):
+        c, d = np.empty(self.M), np.empty(self.M)
+        lib().orc_get_cd(self._h, _p(c, C.c_double), _p(d, C.c_double))
+        return c, d
+
     @property
     def slots(self) -> int:
         return lib().orc_tape_slots(self._h)
@@ -242,7 +266,8 @@ class Oracle:
         tot, cdl = np.empty(4, np.int32), np.empty(3, np.float64)
         lib().orc_get_state(self._h, *(_p(v, C.c_int32) for v in (a, b, pi, rpi, t0, f0, t1, f1, tot)),
                             _p(cdl, C.c_double))
-        return State(kind, ret, self.slots, a, b, pi, rpi, t0, f0, t1, f1, tot, *cdl)
+        c_all, d_all = self.cd() if getattr(self, "_manycd", False) else (None, None)
+        return State(kind, ret, self.slots, a, b, pi, rpi, t0, f0, t1, f1, tot, *cdl, c_all, d_all)
 
     def set_state(self, a, b, pi, c: float, d: float):
         a, b, pi = (np.ascontiguousarray(v, dtype=np.int32) for v in (a, b, pi))
@@ -273,7 +298,7 @@ def ref_available() -> bool:
 
 
 def ref_trace(dataset_path: str, burn_calls: int, sample_calls: int, workdir: str, *, seed: int = 0,
-              philox=None, step: bool = False, tape_in: str | None = None, binary: str = REF_BIN):
+              philox=None, step: bool = False, tape_in: str | None = None, binary: str = REF_BIN, manycd: bool = False):
     """Run the unmodified reference under the harness; returns (dims, states, tape)."""
     dump = os.path.join(workdir, "ref.dump")
     tape = os.path.join(workdir, "ref.tape")
@@ -286,7 +311,8 @@ def ref_trace(dataset_path: str, burn_calls: int, sample_calls: int, workdir: st
         env.update(SER_RNG="philox", SER_SEED=str(philox[0]), SER_CHAIN=str(philox[1]))
     else:
         env["GSL_RNG_SEED"] = str(seed)
-    cmd = [binary, "trace", dataset_path, str(burn_calls), str(sample_calls), dump] + (["step"] if step else [])
+    cmd = [binary, "trace", dataset_path, str(burn_calls), str(sample_calls), dump] + (["step"] if step else []) + \
+        (["manycd"] if manycd else [])
     subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     dims, states = read_dump(dump)
     return dims, states, np.fromfile(tape, dtype="<f8")

@@ -7,7 +7,7 @@
  *
  *   ref_mcmc cli <chain_idx>                      the reference's own main()
  *        (stdin = dataset, writes Chains/chain_XX/, honours GSL_RNG_SEED)
- *   ref_mcmc trace <dataset> <burn_calls> <sample_calls> <dump_file> [step]
+ *   ref_mcmc trace <dataset> <burn_calls> <sample_calls> <dump_file> [step] [manycd]
  *        mcmc_init / readmodel / randomize, then <burn>+<sample> calls of
  *        mcmc_sample(); the full model state is appended to <dump_file> after
  *        randomize and after every call.  With "step" the 10-sweep body of
@@ -16,10 +16,10 @@
  *        records the draw tape (see draw_source.h).
  *   ref_mcmc bench <dataset> <sample_calls>       times mcmc_sample() only
  *
- * Dump file: int32 header {0x5345524d, N, M, nh}; then records
+ * Dump file: int32 header {0x5345524d (0x5345524e with manycd), N, M, nh}; then records
  *   int32 kind, int32 ret, int64 tape_slots,
  *   int32 a[M], b[M], pi[N], rpi[N], t0[M], f0[M], t1[M], f1[M], tot[4],
- *   double c, d, loglik
+ *   double c, d, loglik            (c[0], d[0]); with manycd followed by double c[M], d[M]
  * kind: 0 after randomize, 1 after mcmc_sample, 10 samplec, 11 sampled,
  *       12 sampleab, 13 pi2(swap), 14 pi1, 15 pi2(0), 16 pi3
  */
@@ -40,6 +40,7 @@
 
 extern int ref_main(int argc, char *argv[]);
 extern draw_source *shim_source(void);
+static int g_manycd = 0;
 
 static void put_i32(FILE *f, int32_t v) { fwrite(&v, 4, 1, f); }
 static void put_i64(FILE *f, int64_t v) { fwrite(&v, 8, 1, f); }
@@ -64,6 +65,10 @@ static void dump_state(FILE *f, const mcmc_model *x, int kind, int ret)
   put_f64(f, gsl_vector_get(x->c, 0));
   put_f64(f, gsl_vector_get(x->d, 0));
   put_f64(f, x->loglik);
+  if (g_manycd) {
+    for (i = 0; i < x->M; i++) put_f64(f, gsl_vector_get(x->c, i));
+    for (i = 0; i < x->M; i++) put_f64(f, gsl_vector_get(x->d, i));
+  }
 }
 
 /* mcmc_consistent (mcmc.c:1078-1080) replaces x->loglik by a fresh recount as a side effect;
@@ -92,17 +97,21 @@ static int do_trace(int argc, char **argv)
   if (argc < 6) return 64;
   burn = atoi(argv[3]);
   samp = atoi(argv[4]);
-  if (argc > 6 && strcmp(argv[6], "step") == 0) step = 1;
+  for (i = 6; i < argc; i++) {
+    if (strcmp(argv[i], "step") == 0) step = 1;
+    if (strcmp(argv[i], "manycd") == 0) g_manycd = 1;
+  }
   fin = open_or_die(argv[2], "r");
   fout = open_or_die(argv[5], "wb");
 
   mcmc_init();
-  mcmc_readmodel(&x, fin, 0);
+  mcmc_readmodel(&x, fin, g_manycd);
   fclose(fin);
+  if (g_manycd && shim_source()) ds_set_manycd(shim_source(), x.M);
   mcmc_randomize(&x);
   if (check_consistent(&x)) { fprintf(stderr, "ref_mcmc: inconsistent after randomize\n"); return 1; }
 
-  put_i32(fout, 0x5345524d); put_i32(fout, x.N); put_i32(fout, x.M); put_i32(fout, x.nh);
+  put_i32(fout, g_manycd ? 0x5345524e : 0x5345524d); put_i32(fout, x.N); put_i32(fout, x.M); put_i32(fout, x.nh);
   dump_state(fout, &x, 0, 0);
 
   for (call = 0; call < burn + samp; call++) {

@@ -33,7 +33,8 @@ struct orc_model {
   int *rpi;   /* rpi[position] = site */
   int *t0, *f0, *t1, *f1;
   int t0a, f0a, t1a, f1a;
-  double c, d; /* log P(false 1), log P(false 0); scalar (manycd = 0) */
+  double *c, *d; /* log P(false 1), log P(false 0) per taxon; all equal unless manycd (mcmc.h:39-40) */
+  int manycd;
   double loglik;
   draw_source src;
   int detmath;
@@ -84,13 +85,13 @@ orc_model *orc_create(int N, int M, const uint8_t *X, const uint8_t *hard)
   x->dt0 = (int *)xcalloc(N + 1, sizeof(int)); x->df0 = (int *)xcalloc(N + 1, sizeof(int));
   x->dt1 = (int *)xcalloc(N + 1, sizeof(int)); x->df1 = (int *)xcalloc(N + 1, sizeof(int));
   x->p = (int *)xcalloc(N, sizeof(int));
+  x->c = (double *)xcalloc(M, sizeof(double)); x->d = (double *)xcalloc(M, sizeof(double));
   ds_init_mt(&x->src, 0);
   x->min_pick = x->min_accept = INFINITY;
   /* mcmc_readmodel, mcmc.c:405-433: identity order, a/b from the data,
    * c = log .01, d = log .3, counts, likelihood */
   for (int n = 0; n < N; n++) x->pi[n] = x->rpi[n] = n;
-  x->c = log(.01);
-  x->d = log(.3);
+  for (int m = 0; m < M; m++) { x->c[m] = log(.01); x->d[m] = log(.3); }
   orc_initab(x);
   orc_recount(x);
   return x;
@@ -101,13 +102,18 @@ void orc_free(orc_model *x)
   if (!x) return;
   free(x->X); free(x->h); free(x->a); free(x->b); free(x->pi); free(x->rpi);
   free(x->t0); free(x->f0); free(x->t1); free(x->f1);
-  free(x->v); free(x->q); free(x->dt0); free(x->df0); free(x->dt1); free(x->df1); free(x->p);
+  free(x->v); free(x->q); free(x->dt0); free(x->df0); free(x->dt1); free(x->df1); free(x->p); free(x->c); free(x->d);
   free(x->src.rec);
   free(x);
 }
 
 void orc_source_mt(orc_model *x, unsigned long seed) { free(x->src.rec); ds_init_mt(&x->src, seed); }
-void orc_source_philox(orc_model *x, uint32_t seed, uint32_t chain) { free(x->src.rec); ds_init_philox(&x->src, seed, chain); }
+void orc_source_philox(orc_model *x, uint32_t seed, uint32_t chain)
+{
+  free(x->src.rec);
+  ds_init_philox(&x->src, seed, chain);
+  if (x->manycd) ds_set_manycd(&x->src, x->M);
+}
 void orc_source_tape(orc_model *x, const double *tape, size_t len) { free(x->src.rec); ds_init_tape(&x->src, tape, len); }
 void orc_record(orc_model *x, int on) { x->src.recording = on; }
 size_t orc_tape_len(const orc_model *x) { return x->src.rec_n; }
@@ -117,6 +123,12 @@ long long orc_tape_slots(const orc_model *x)
   return (long long)(x->src.n_uniform + x->src.n_pos + x->src.n_int + 3 * x->src.n_beta);
 }
 void orc_set_detmath(orc_model *x, int on) { x->detmath = on; }
+/* per-taxon c, d (mcmc_readmodel's manycd argument, mcmc.c:363); call before choosing the draw source */
+void orc_set_manycd(orc_model *x, int on)
+{
+  x->manycd = on;
+  if (on && x->src.kind == DS_PHILOX) ds_set_manycd(&x->src, x->M);
+}
 
 /* mcmc_initab, mcmc.c:440-474: a = first position holding a 1, b = last + 1;
  * an all-zero column spans everything. */
@@ -135,10 +147,10 @@ void orc_initab(orc_model *x)
 static double orc_logl(const orc_model *x)
 {
   double loglik = 0.;
-  const double c = x->c, d = x->d;
-  const double lc = orc_log1mexp(x, c), ld = orc_log1mexp(x, d);
-  for (int m = 0; m < x->M; m++)
-    loglik += x->t0[m] * lc + x->f0[m] * d + x->t1[m] * ld + x->f1[m] * c;
+  for (int m = 0; m < x->M; m++) {
+    const double c = x->c[m], d = x->d[m];
+    loglik += x->t0[m] * orc_log1mexp(x, c) + x->f0[m] * d + x->t1[m] * orc_log1mexp(x, d) + x->f1[m] * c;
+  }
   return loglik;
 }
 
@@ -224,15 +236,27 @@ static void orc_samplebeta(orc_model *x, double *val, double a, double b, double
   }
 }
 
-int orc_samplec(orc_model *x) /* mcmc.c:768-795, scalar branch */
+int orc_samplec(orc_model *x) /* mcmc.c:768-795 */
 {
-  orc_samplebeta(x, &x->c, x->f1a, x->t0a, ORC_MINC, ORC_MAXC);
+  if (x->manycd) { /* :777-785 one Beta per taxon from its own counts */
+    for (int m = 0; m < x->M; m++) orc_samplebeta(x, &x->c[m], x->f1[m], x->t0[m], ORC_MINC, ORC_MAXC);
+    return x->M;
+  }
+  double y = x->c[0];
+  orc_samplebeta(x, &y, x->f1a, x->t0a, ORC_MINC, ORC_MAXC);
+  for (int m = 0; m < x->M; m++) x->c[m] = y;
   return 1;
 }
 
-int orc_sampled(orc_model *x) /* mcmc.c:798-825, scalar branch */
+int orc_sampled(orc_model *x) /* mcmc.c:798-825 */
 {
-  orc_samplebeta(x, &x->d, x->f0a, x->t1a, ORC_MIND, ORC_MAXD);
+  if (x->manycd) {
+    for (int m = 0; m < x->M; m++) orc_samplebeta(x, &x->d[m], x->f0[m], x->t1[m], ORC_MIND, ORC_MAXD);
+    return x->M;
+  }
+  double y = x->d[0];
+  orc_samplebeta(x, &y, x->f0a, x->t1a, ORC_MIND, ORC_MAXD);
+  for (int m = 0; m < x->M; m++) x->d[m] = y;
   return 1;
 }
 
@@ -295,11 +319,11 @@ int orc_sampleab(orc_model *x)
   for (int m = 0; m < x->M; m++) {
     for (int pos = 0; pos < N; pos++) x->v[pos] = x->X[(size_t)x->rpi[pos] * x->M + m];
     int t = x->a[m], t0 = x->t0[m], f0 = x->f0[m], t1 = x->t1[m], f1 = x->f1[m];
-    orc_gibbs_boundary(x, x->v, x->b[m], x->c, x->d, &t, &t0, &f0, &t1, &f1);
+    orc_gibbs_boundary(x, x->v, x->b[m], x->c[m], x->d[m], &t, &t0, &f0, &t1, &f1);
     if (t != x->a[m]) { x->a[m] = t; changed++; }
     for (int i = 0; i < N / 2; i++) { uint8_t s = x->v[i]; x->v[i] = x->v[N - 1 - i]; x->v[N - 1 - i] = s; }
     t = N - x->b[m];
-    orc_gibbs_boundary(x, x->v, N - x->a[m], x->c, x->d, &t, &t0, &f0, &t1, &f1);
+    orc_gibbs_boundary(x, x->v, N - x->a[m], x->c[m], x->d[m], &t, &t0, &f0, &t1, &f1);
     x->t0[m] = t0; x->f0[m] = f0; x->t1[m] = t1; x->f1[m] = f1;
     if (t != N - x->b[m]) { x->b[m] = N - t; changed++; }
   }
@@ -318,9 +342,10 @@ static int in_window(int v, int lo, int hi, int inc_lo, int inc_hi)
 }
 
 /* the 4-term per-taxon likelihood change, operand order of mcmc.c:1214 */
-static double orc_term(const orc_model *x, int dt0, int df0, int dt1, int df1, double lc, double ld)
+static double orc_term(const orc_model *x, int m, int dt0, int df0, int dt1, int df1)
 {
-  return dt0 * lc + df0 * x->d + dt1 * ld + df1 * x->c;
+  const double c = x->c[m], d = x->d[m];
+  return dt0 * orc_log1mexp(x, c) + df0 * d + dt1 * orc_log1mexp(x, d) + df1 * c;
 }
 
 /* common MH tail: mcmc.c:1261, :1441, :1636 */
@@ -355,7 +380,6 @@ int orc_samplepi1(orc_model *x)
     for (int n = lo; n <= hi; n++) { cnt += x->h[x->rpi[n]]; if (cnt > 1) return 0; }
   }
   const uint8_t *row = x->X + (size_t)x->rpi[i] * M;
-  const double lc = orc_log1mexp(x, x->c), ld = orc_log1mexp(x, x->d);
   double delta = 0.;
   long s0 = 0, s1 = 0; int any = 0;
   for (int m = 0; m < M; m++) {
@@ -371,7 +395,7 @@ int orc_samplepi1(orc_model *x)
     }
     if (gain) { if (row[m]) { dt1++; df1--; } else { dt0--; df0++; } }
     else if (lose) { if (row[m]) { dt1--; df1++; } else { dt0++; df0--; } }
-    delta += orc_term(x, dt0, df0, dt1, df1, lc, ld);
+    delta += orc_term(x, m, dt0, df0, dt1, df1);
     s0 += dt0; s1 += dt1; any |= (dt0 | dt1) != 0;
   }
   if (!orc_accept(x, delta, s0, s1, any)) return 0;
@@ -424,7 +448,6 @@ int orc_samplepi2(orc_model *x, int swap)
     for (int n = i; n <= j; n++) { cnt += x->h[x->rpi[n]]; if (cnt > 1) return 0; }
   }
   const int inc1 = (int)ds_uniform_int(&x->src, 2), inc2 = (int)ds_uniform_int(&x->src, 2);
-  const double lc = orc_log1mexp(x, x->c), ld = orc_log1mexp(x, x->d);
   double delta = 0.;
   long s0 = 0, s1 = 0; int any = 0;
   for (int m = 0; m < M; m++) { /* :1368-1436 */
@@ -441,7 +464,7 @@ int orc_samplepi2(orc_model *x, int swap)
         else { if (one) { dt1--; df1++; } else { dt0++; df0--; } }
       }
     }
-    delta += orc_term(x, dt0, df0, dt1, df1, lc, ld);
+    delta += orc_term(x, m, dt0, df0, dt1, df1);
     s0 += dt0; s1 += dt1; any |= (dt0 | dt1) != 0;
   }
   if (!orc_accept(x, delta, s0, s1, any)) return 0;
@@ -476,7 +499,6 @@ int orc_samplepi3(orc_model *x)
     else { p[lo] = hi; p[hi] = lo; lo++; hi--; }
   }
   const int inc1 = (int)ds_uniform_int(&x->src, 2), inc2 = (int)ds_uniform_int(&x->src, 2);
-  const double lc = orc_log1mexp(x, x->c), ld = orc_log1mexp(x, x->d);
   double delta = 0.;
   long s0 = 0, s1 = 0; int any = 0;
   for (int m = 0; m < M; m++) { /* :1569-1631 */
@@ -492,7 +514,7 @@ int orc_samplepi3(orc_model *x)
       if (was) { if (one) { dt1--; df1++; } else { df0--; dt0++; } }
       else { if (one) { dt1++; df1--; } else { df0++; dt0--; } }
     }
-    delta += orc_term(x, dt0, df0, dt1, df1, lc, ld);
+    delta += orc_term(x, m, dt0, df0, dt1, df1);
     s0 += dt0; s1 += dt1; any |= (dt0 | dt1) != 0;
   }
   if (!orc_accept(x, delta, s0, s1, any)) return 0;
@@ -569,7 +591,7 @@ void orc_get_state(const orc_model *x, int32_t *a, int32_t *b, int32_t *pi, int3
     if (rpi) rpi[n] = x->rpi[n];
   }
   if (tot) { tot[0] = x->t0a; tot[1] = x->f0a; tot[2] = x->t1a; tot[3] = x->f1a; }
-  if (cdl) { cdl[0] = x->c; cdl[1] = x->d; cdl[2] = x->loglik; }
+  if (cdl) { cdl[0] = x->c[0]; cdl[1] = x->d[0]; cdl[2] = x->loglik; }
 }
 
 void orc_set_state(orc_model *x, const int32_t *a, const int32_t *b, const int32_t *pi, double c,
@@ -578,7 +600,7 @@ void orc_set_state(orc_model *x, const int32_t *a, const int32_t *b, const int32
   for (int m = 0; m < x->M; m++) { x->a[m] = a[m]; x->b[m] = b[m]; }
   for (int n = 0; n < x->N; n++) x->pi[n] = pi[n];
   invert(x->pi, x->rpi, x->N);
-  x->c = c; x->d = d;
+  for (int m = 0; m < x->M; m++) { x->c[m] = c; x->d[m] = d; }
   orc_recount(x);
 }
 
@@ -597,8 +619,8 @@ void orc_run(orc_model *x, int burn_calls, int sample_calls, int32_t *a, int32_t
     if (counts) memcpy(counts + (size_t)s * 4, tot, sizeof(tot));
     /* compute_exp_data, mcmc.c:53-58 */
     s_ll += -(x->loglik);
-    s_c += exp(x->c);
-    s_d += exp(x->d);
+    s_c += exp(x->c[0]);
+    s_d += exp(x->d[0]);
   }
   if (sums) { sums[0] = s_ll; sums[1] = s_c; sums[2] = s_d; }
 }
@@ -613,3 +635,9 @@ void orc_margins(const orc_model *x, double *min_pick, double *min_accept,
 }
 
 long long orc_tape_mismatches(const orc_model *x) { return x->n_tape_mismatch; }
+
+/* per-taxon c, d (any pointer may be NULL) */
+void orc_get_cd(const orc_model *x, double *c, double *d)
+{
+  for (int m = 0; m < x->M; m++) { if (c) c[m] = x->c[m]; if (d) d[m] = x->d[m]; }
+}

@@ -38,6 +38,9 @@ long long orc_tape_slots(const orc_model *x);         /* slots consumed so far *
 
 /* 0: libm log/exp exactly like the reference (default); 1: ser_detmath.h */
 void orc_set_detmath(orc_model *x, int on);
+/* per-taxon c, d (mcmc_readmodel's manycd, mcmc.c:363, :777-785, :807-815); set before the draw source */
+void orc_set_manycd(orc_model *x, int on);
+void orc_get_cd(const orc_model *x, double *c, double *d);
 
 void orc_randomize(orc_model *x);     /* mcmc.c:477-578 */
 int orc_samplec(orc_model *x);        /* mcmc.c:768-795 */

@@ -166,6 +166,7 @@ SER_HD double ser_u53(uint32_t hi, uint32_t lo)
 #define SER_BLK_AB 4u        /* index 2m -> U for a_m, 2m+1 -> U for b_m */
 #define SER_BLK_PI 5u        /* sequential draws of the 16 pi proposals */
 #define SER_BLK_INIT 6u      /* mcmc_randomize draws; sweep field = 0xFFFFFFFF */
+#define SER_BLK_MANYCD 8u     /* manycd: taxon m uses blocks 8+4m .. 8+4m+3 (c: Gamma a, b; d: Gamma a, b) */
 #define SER_SWEEP_INIT 0xFFFFFFFFu
 
 SER_HD double ser_stream_uniform(uint32_t seed, uint32_t chain, uint32_t sweep, uint32_t block,

@@ -65,6 +65,21 @@ def test_restatement_matches_reference_on_philox_stream(oracle_mod):
     assert np.array_equal(o.tape(), g["tape"])
 
 
+def test_restatement_matches_reference_manycd(oracle_mod):
+    """per-taxon c, d (manycd = 1, mcmc.c:777-785, :807-815): trace of the unmodified reference"""
+    g = np.load(os.path.join(GOLDEN, "ref_g10s10_manycd.npz"))
+    X, hard = load_hex_dataset("g10s10")
+    o = oracle_mod.Oracle(X, hard).manycd().source_tape(g["tape"])
+    o.randomize()
+    _cmp(o.state(), g, 0)
+    for r in range(1, len(g["kind"])):
+        o.sample()
+        s = o.state()
+        _cmp(s, g, r)
+        assert s.c_all.tobytes() == g["c_all"][r].tobytes() and s.d_all.tobytes() == g["d_all"][r].tobytes()
+    assert o.slots == g["tape"].size and len(set(g["c_all"][-1])) > 100
+
+
 def test_philox_known_answers():
     """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
     import ctypes as C

@@ -35,9 +35,9 @@ def write_hex(name):
     return X, hard
 
 
-def trace(name, burn, samp, seed, step=False, philox=None, tag=""):
+def trace(name, burn, samp, seed, step=False, philox=None, tag="", manycd=False):
     with tempfile.TemporaryDirectory() as td:
-        dims, states, tape = O.ref_trace(f"{REF}/{name}.txt", burn, samp, td, seed=seed, step=step, philox=philox)
+        dims, states, tape = O.ref_trace(f"{REF}/{name}.txt", burn, samp, td, seed=seed, step=step, philox=philox, manycd=manycd)
     keys = ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot")
     out = {k: np.stack([getattr(s, k) for s in states]).astype(np.int16 if k != "tot" else np.int32) for k in keys}
     out["cdl"] = np.array([[s.c, s.d, s.loglik] for s in states])
@@ -46,6 +46,9 @@ def trace(name, burn, samp, seed, step=False, philox=None, tag=""):
     out["slots"] = np.array([s.slots for s in states], np.int64)
     out["tape"] = tape
     out["meta"] = np.array([burn, samp, seed, int(step)], np.int64)
+    if manycd:
+        out["c_all"] = np.stack([s.c_all for s in states])
+        out["d_all"] = np.stack([s.d_all for s in states])
     np.savez_compressed(f"{OUT}/ref_{name}{tag}.npz", **out)
     print(name, tag, "records", len(states), "tape", tape.size)
 
@@ -60,3 +63,4 @@ if __name__ == "__main__":
     trace("g5s5", 2, 2, seed=4)
     trace("g2s2", 2, 2, seed=5)
     trace("g10s10", 2, 2, seed=0, philox=(20060206, 17), tag="_philox")
+    trace("g10s10", 2, 2, seed=8, tag="_manycd", manycd=True)
