@@ -223,9 +223,17 @@ struct SerWeights {
   double g, A;         /* g = -w0: log-weight gained per zero passed; A = w0 - w1: change per one passed */
   double inv_g;
   double eps;          /* exp(LOGEPSILON) as the host libm evaluates it (mcmc.c:734) */
-  const double *H;     /* H[m] = sum_{u<m} exp(-u g), m = 0..hmax: geometric partial sums (per sweep) */
+  const double *H;     /* H[m] = sum_{u<m} exp(-u g), m = 0..hmax: geometric partial sums (per sweep);
+                          NULL with per-taxon c/d (manycd): evaluated on the fly from hs */
+  double hs;           /* 1 / (1 - exp(-g)) */
   int hmax;
 };
+
+/* geometric partial sum H(m) = sum_{u<m} exp(-u g) */
+SER_HD double ser_H(const SerWeights &w, int m)
+{
+  return w.H ? w.H[m] : SER_MUL(SER_SUB(1.0, exp(-SER_MUL(w.g, (double)m))), w.hs);
+}
 
 /* number of entries (-1) the per-sweep table H needs for a given g and N */
 SER_HD int ser_hmax(double g, int N)
@@ -245,6 +253,14 @@ SER_HD void ser_set_weights(struct SerWeights *wt, double c, double cc, double d
   wt->w1 = dd - c; wt->w0 = d - cc;
   wt->g = -wt->w0; wt->A = wt->w0 - wt->w1;
   wt->inv_g = 1.0 / wt->g;
+}
+/* per-taxon weights (manycd): no shared table, geometric sums on the fly */
+SER_HD void ser_set_weights_own(struct SerWeights *wt, double c, double cc, double d, double dd, int N)
+{
+  ser_set_weights(wt, c, cc, d, dd);
+  wt->H = 0;
+  wt->hs = 1.0 / (1.0 - exp(-wt->g));
+  wt->hmax = N + 1;
 }
 
 /* exact int -> double on the fp64 add pipe (no I2F): 2^52 + 2^31 + k, minus the bias */
@@ -293,7 +309,7 @@ SER_HD double ser_run_sum(const SerWeights &w, int n, double le, int *m_out, dou
   if (m > w.hmax) m = w.hmax;
   const double ye = ser_exp_weight(le);
   *m_out = m; *ye_out = ye;
-  return ser_fma(ye, w.H[m], SER_MUL(ser_i2d(n - m), w.eps));
+  return ser_fma(ye, ser_H(w, m), SER_MUL(ser_i2d(n - m), w.eps));
 }
 
 /*
@@ -396,10 +412,11 @@ SER_HD int ser_run_pick(const SerWeights &wt, int n, double le, double s, double
     return t;
   }
   /* cumulative weight through geometric candidate k (k = 0..m-1): sf + ye (H[m] - H[m-1-k]) */
+  const double hm = ser_H(wt, m);
   int lo = 0, hi = m - 1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (ser_fma(ye, SER_SUB(wt.H[m], wt.H[m - 1 - mid]), sf) >= target) hi = mid; else lo = mid + 1;
+    if (ser_fma(ye, SER_SUB(hm, ser_H(wt, m - 1 - mid)), sf) >= target) hi = mid; else lo = mid + 1;
   }
   return nf + lo;
 }

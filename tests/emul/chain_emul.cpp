@@ -31,6 +31,9 @@ struct Chain {
   std::vector<uint16_t> pre, hp; // pre[(W+1)][C] prefix ones; hp = sorted hard positions
   std::vector<uint16_t> rpi;
   SerWeights wt;
+  bool manycd = false;
+  std::vector<SerWeights> wts; // per-taxon weights (manycd)
+  const SerWeights &WT(int m) const { return manycd ? wts[m] : wt; }
   double loglik;
   int t0a, f0a, t1a, f1a;
   const double *tape;
@@ -80,6 +83,14 @@ struct Chain {
     for (int m = 0; m < M; m++) { T1 += ser_col_popc(col(m), pcol(m), C, a[m], b[m]); LEN += b[m] - a[m]; ONES += ones[m]; }
     t1a = (int)T1; f1a = (int)(ONES - T1); f0a = (int)(LEN - T1); t0a = (int)((long)N * M - LEN - f1a);
     loglik = t0a * wt.cc + f0a * wt.d + t1a * wt.dd + f1a * wt.c;
+    if (manycd) { // mcmc_logl, mcmc.c:625-648, per-taxon coefficients
+      loglik = 0.0;
+      for (int m = 0; m < M; m++) {
+        int t0, f0, t1, f1;
+        ser_counts(col(m), pcol(m), C, N, a[m], b[m], ones[m], &t0, &f0, &t1, &f1);
+        loglik += t0 * wts[m].cc + f0 * wts[m].d + t1 * wts[m].dd + f1 * wts[m].c;
+      }
+    }
   }
 };
 
@@ -89,7 +100,10 @@ bool decide(Chain &ch, const std::vector<int> &dt0, const std::vector<int> &dt1,
   long D0 = 0, D1 = 0; bool any = false;
   for (int m = 0; m < ch.M; m++) { D0 += dt0[m]; D1 += dt1[m]; any |= (dt0[m] | dt1[m]) != 0; }
   double delta;
-  if (D0 == 0 && D1 == 0) {
+  if (ch.manycd) { // per-taxon coefficients: the reference's sequential sum is the definition
+    delta = 0.0;
+    for (int m = 0; m < ch.M; m++) delta = delta + ser_term(ch.wts[m], dt0[m], dt1[m]);
+  } else if (D0 == 0 && D1 == 0) {
     delta = 0.0;
     if (any) { // sequential sum of the per-taxon terms, in taxon order, like mcmc.c:1214
       for (int m = 0; m < ch.M; m++) delta = delta + ser_term(ch.wt, dt0[m], dt1[m]);
@@ -191,6 +205,20 @@ int pi3(Chain &ch) {
 }
 
 void sample_cd(Chain &ch) {
+  if (ch.manycd) { // mcmc.c:777-785, :807-815: M Betas for c, then M for d (the draws do not depend on acceptance)
+    for (int pass = 0; pass < 2; pass++)
+      for (int m = 0; m < ch.M; m++) {
+        const double y = ch.next(), ly = ch.next(), l1 = ch.next();
+        SerWeights &w = ch.wts[m];
+        double c = w.c, cc = w.cc, d = w.d, dd = w.dd;
+        if (pass == 0) { if (y > 0. && MINC <= ly && ly <= MAXC) { c = ly; cc = l1; } }
+        else { if (y > 0. && MIND <= ly && ly <= MAXD) { d = ly; dd = l1; } }
+        const double eps = w.eps;
+        ser_set_weights_own(&w, c, cc, d, dd, ch.N);
+        w.eps = eps;
+      }
+    return;
+  }
   double c = ch.wt.c, cc = ch.wt.cc, d = ch.wt.d, dd = ch.wt.dd;
   { const double y = ch.next(), ly = ch.next(), l1 = ch.next();
     if (y > 0. && MINC <= ly && ly <= MAXC) { c = ly; cc = l1; } }
@@ -215,13 +243,13 @@ int sample_ab(Chain &ch) {
     for (int m = 0; m < M; m++) {
       st[m] = step == 0 ? ser_step_a(ch.col(m), ch.pcol(m), C, W, N, ch.a[m], ch.b[m])
                         : ser_step_b(ch.col(m), ch.pcol(m), C, W, N, ch.a[m], ch.b[m]);
-      lmax[m] = ser_step_lmax(ch.wt, st[m], pos.data() + off[m]);
+      lmax[m] = ser_step_lmax(ch.WT(m), st[m], pos.data() + off[m]);
     }
     for (int m = 0; m < M; m++)          // dense over items in the kernel
       for (int kk = 0; kk <= st[m].kb; kk++)
-        val[off[m] + kk] = ser_item_weight(ch.wt, st[m], pos.data() + off[m], kk, lmax[m]);
+        val[off[m] + kk] = ser_item_weight(ch.WT(m), st[m], pos.data() + off[m], kk, lmax[m]);
     for (int m = 0; m < M; m++) {
-      const int pick = ser_step_pick(ch.wt, st[m], pos.data() + off[m], val.data() + off[m], lmax[m], step == 0 ? ua[m] : ub[m]);
+      const int pick = ser_step_pick(ch.WT(m), st[m], pos.data() + off[m], val.data() + off[m], lmax[m], step == 0 ? ua[m] : ub[m]);
       if (step == 0) { changed += pick != ch.a[m]; ch.a[m] = pick; }
       else { changed += (N - pick) != ch.b[m]; ch.b[m] = N - pick; }
     }
@@ -241,9 +269,14 @@ void sweep(Chain &ch) {
 
 extern "C" {
 
+void *emul_create_ex(int N, int M, const uint8_t *X, const uint8_t *hard, double c0, double cc0, double d0,
+                     double dd0, double eps, int manycd);
 void *emul_create(int N, int M, const uint8_t *X, const uint8_t *hard, double c0, double cc0, double d0,
-                  double dd0, double eps) {
+                  double dd0, double eps) { return emul_create_ex(N, M, X, hard, c0, cc0, d0, dd0, eps, 0); }
+void *emul_create_ex(int N, int M, const uint8_t *X, const uint8_t *hard, double c0, double cc0, double d0,
+                     double dd0, double eps, int manycd) {
   Chain *ch = new Chain();
+  ch->manycd = manycd != 0;
   ch->N = N; ch->M = M; ch->W = N / 32 + 1; ch->C = M + 1; ch->nh = 0;
   ch->X.assign(X, X + (size_t)N * M);
   ch->hard.assign(hard, hard + N);
@@ -256,6 +289,10 @@ void *emul_create(int N, int M, const uint8_t *X, const uint8_t *hard, double c0
   for (int m = 0; m < M; m++) for (int n = 0; n < N; n++) ch->ones[m] += X[(size_t)n * M + m] != 0;
   ch->wt.eps = eps;
   ch->set_cd(c0, cc0, d0, dd0);
+  if (ch->manycd) {
+    ch->wts.resize(M);
+    for (int m = 0; m < M; m++) { ser_set_weights_own(&ch->wts[m], c0, cc0, d0, dd0, N); ch->wts[m].eps = eps; }
+  }
   ch->tape = nullptr; ch->tape_len = ch->cur = 0; ch->n_degenerate = 0;
   ch->build_columns();
   ch->initab();
@@ -316,9 +353,13 @@ void emul_get_state(void *p, int32_t *a, int32_t *b, int32_t *pi, int32_t *rpi, 
   }
   for (int n = 0; n < ch.N; n++) { rpi[n] = ch.rpi[n]; pi[ch.rpi[n]] = n; }
   tot[0] = ch.t0a; tot[1] = ch.f0a; tot[2] = ch.t1a; tot[3] = ch.f1a;
-  cdl[0] = ch.wt.c; cdl[1] = ch.wt.d; cdl[2] = ch.loglik;
+  cdl[0] = ch.WT(0).c; cdl[1] = ch.WT(0).d; cdl[2] = ch.loglik;
   *slots = (long long)ch.cur;
 }
 long long emul_degenerate(void *p) { return ((Chain *)p)->n_degenerate; }
+void emul_get_cd(void *p, double *c, double *d) {
+  Chain &ch = *(Chain *)p;
+  for (int m = 0; m < ch.M; m++) { c[m] = ch.WT(m).c; d[m] = ch.WT(m).d; }
+}
 
 } // extern "C"
