@@ -16,6 +16,7 @@
  *   ser_run_advance           mcmc_sample loop          mcmc.c:214-258 (main: :140-143, :180-185)
  *   ser_run_get_state         mcmc_model fields         mcmc.h:32-45
  *   ser_run_fetch_samples     mcmc_save_chain rows      mcmc.c:69-92
+ *   ser_run_get_cd/_fetch_cd_samples  per-taxon c[], d[] (manycd)  mcmc.c:777-785, :807-815, :82-91
  *   ser_run_chain_stats       compute/print_exp_data    mcmc.c:53-67
  *   ser_run_check             mcmc_consistent           mcmc.c:999-1094
  *   ser_write_chain_files     main's five fopen()s      mcmc.c:148-197, :261-294
@@ -69,6 +70,7 @@ typedef struct ser_run_config {
   int32_t store;           /* SER_STORE_*                                                      */
   int32_t max_samples;     /* capacity of the thinned-sample store per chain                   */
   int32_t device;          /* CUDA device ordinal                                              */
+  int32_t manycd;          /* 1: per-taxon c, d (mcmc_readmodel's manycd, mcmc.c:363, :777-785) */
 } ser_run_config;
 
 const char *ser_last_error(void);
@@ -125,6 +127,12 @@ int ser_run_chain_stats_device(ser_run *run, double *d_e_negloglik);
  * a,b: [n][M]; pi: [n][N]; c,d,loglik: [n].  Returns the number of samples in *n. */
 int ser_run_fetch_samples(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32_t *pi, double *c,
                           double *d, double *loglik, int32_t *n);
+/* manycd = 1 runs (mcmc.c:777-785, :807-815): per-taxon c, d of one chain, M doubles each, file
+ * order; ser_run_get_state's cdl then carries taxon 0's c, d -- what compute_exp_data (mcmc.c:56-57)
+ * and mcmc_save_chain (mcmc.c:88-89) read.  The fetch returns the per-taxon values of every stored
+ * sample, [n][M] each (SER_STORE_FULL), the rows mcmc_save_chain prints for chain_data.csv. */
+int ser_run_get_cd(ser_run *run, int32_t chain, double *c, double *d);
+int ser_run_fetch_cd_samples(ser_run *run, int32_t chain, double *c, double *d, int32_t *n);
 
 /* ---------------------------------------------------------------- cross-chain steps */
 /* choose_chains: population sigma over all n values, keep min-sigma < x < min+sigma, the k

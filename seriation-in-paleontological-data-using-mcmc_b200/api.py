@@ -30,7 +30,7 @@ class SeriationError(RuntimeError):
 class RunConfig(C.Structure):
     _fields_ = [("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("sweeps_per_call", C.c_int32),
                 ("mode", C.c_int32), ("seed", C.c_uint32), ("store", C.c_int32), ("max_samples", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("manycd", C.c_int32)]
 
 
 # every symbol include/seriation_b200.h declares: (name, restype, argtypes)
@@ -63,6 +63,8 @@ SYMBOLS = [
     ("ser_run_chain_stats", C.c_int, [_vp, _dp, _dp, _dp, _i32p]),
     ("ser_run_chain_stats_device", C.c_int, [_vp, _vp]),
     ("ser_run_fetch_samples", C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _dp, _dp, _dp, _i32p]),
+    ("ser_run_get_cd", C.c_int, [_vp, C.c_int32, _dp, _dp]),
+    ("ser_run_fetch_cd_samples", C.c_int, [_vp, C.c_int32, _dp, _dp, _i32p]),
     ("ser_select_chains", C.c_int, [_dp, C.c_int32, C.c_int32, _i32p, _i32p, _dp, _dp]),
     ("ser_select_chains_device", C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp]),
     ("ser_run_po_counts_device", C.c_int, [_vp, _vp, C.c_int32, _vp]),
@@ -168,10 +170,11 @@ class Run:
     """A batch of independent chains on one GPU (replaces script.py's Pool of `mcmc` processes)."""
 
     def __init__(self, ds: Dataset, n_chains: int, *, mode=MODE_FREE, seed=0, chain_offset=0, sweeps_per_call=10,
-                 store=STORE_NONE, max_samples=0, device=0):
+                 store=STORE_NONE, max_samples=0, device=0, manycd=False):
         self.ds = ds
         self.N, self.M, self.n_chains = ds.N, ds.M, n_chains
-        self.cfg = RunConfig(n_chains, chain_offset, sweeps_per_call, mode, seed, store, max_samples, device)
+        self.manycd = bool(manycd)
+        self.cfg = RunConfig(n_chains, chain_offset, sweeps_per_call, mode, seed, store, max_samples, device, int(self.manycd))
         h = _vp()
         _check(lib().ser_run_create(ds._h, C.byref(self.cfg), C.byref(h)))
         self._h = h
@@ -223,6 +226,12 @@ class Run:
         return dict(a=a, b=b, pi=pi, rpi=rpi, t0=t0, f0=f0, t1=t1, f1=f1, tot=tot, c=cdl[0], d=cdl[1],
                     loglik=cdl[2], slots=slots.value)
 
+    def cd(self, chain: int):
+        """per-taxon (c, d) of a manycd run, file order"""
+        c, d = np.empty(self.M), np.empty(self.M)
+        _check(lib().ser_run_get_cd(self._h, chain, _p(c, C.c_double), _p(d, C.c_double)))
+        return c, d
+
     def counters(self, chain: int) -> np.ndarray:
         out = np.empty(8, np.int64)
         _check(lib().ser_run_get_counters(self._h, chain, _p(out, C.c_int64)))
@@ -256,7 +265,12 @@ class Run:
         c, d, ll = np.empty(S), np.empty(S), np.empty(S)
         _check(lib().ser_run_fetch_samples(self._h, chain, _p(a, C.c_int32), _p(b, C.c_int32), _p(pi, C.c_int32),
                                            _p(c, C.c_double), _p(d, C.c_double), _p(ll, C.c_double), C.byref(n)))
-        return dict(a=a, b=b, pi=pi, c=c, d=d, loglik=ll)
+        out = dict(a=a, b=b, pi=pi, c=c, d=d, loglik=ll)
+        if self.manycd:
+            c_all, d_all = np.empty((S, M)), np.empty((S, M))
+            _check(lib().ser_run_fetch_cd_samples(self._h, chain, _p(c_all, C.c_double), _p(d_all, C.c_double), C.byref(n)))
+            out.update(c_all=c_all, d_all=d_all)
+        return out
 
     def po_counts(self, chosen) -> np.ndarray:
         chosen = np.ascontiguousarray(chosen, dtype=np.int32)

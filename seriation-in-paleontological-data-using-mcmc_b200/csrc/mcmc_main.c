@@ -11,11 +11,11 @@
  * Differences, all deliberate: the random stream is the structured Philox stream keyed by
  * (GSL_RNG_SEED, chain index) instead of GSL's MT19937; Chains/chain_XX/ is created when missing
  * (the reference dereferences a NULL FILE*); `mcmc` without arguments prints usage instead of
- * crashing at atoi(NULL) (mcmc.c:153); `manycd=1` is refused (out of scope).
+ * crashing at atoi(NULL) (mcmc.c:153).
  *
  * Batch mode (replaces script.py's Pool over 100 processes by one launch):
  *   mcmc --chains N [--first I] [--burn B] [--samples S] [--seed X] [--dataset file]
- *        [--chains-dir DIR] [--select K] [--po file.csv] [--device D]
+ *        [--chains-dir DIR] [--select K] [--po file.csv] [--device D] [--manycd 0|1]
  * Replay mode: SER_TAPE_IN=<file of raw doubles> mcmc <idx> < dataset.txt
  */
 #include <errno.h>
@@ -36,9 +36,9 @@ static void usage(const char *argv0)
 {
   fprintf(stderr,
           "usage: %s <chain_index> < dataset.txt          (reference-compatible single chain)\n"
-          "       %s [manycd Tburnin T] < dataset.txt      (manycd must be 0; chain 0)\n"
+          "       %s [manycd Tburnin T] < dataset.txt      (manycd 1: per-taxon c, d; chain 0)\n"
           "       %s --chains N [--first I] [--burn B] [--samples S] [--seed X] [--dataset F]\n"
-          "              [--chains-dir DIR] [--select K] [--po out.csv] [--device D]\n",
+          "              [--chains-dir DIR] [--select K] [--po out.csv] [--device D] [--manycd 0|1]\n",
           argv0, argv0, argv0);
   exit(1);
 }
@@ -61,7 +61,7 @@ static double *read_tape(const char *path, uint64_t *len)
 
 int main(int argc, char **argv)
 {
-  int n_chains = 1, first = 0, burn = 1000, samples = 1000, select_k = 0, device = 0, batch = 0, i;
+  int n_chains = 1, first = 0, burn = 1000, samples = 1000, select_k = 0, device = 0, batch = 0, manycd = 0, i;
   unsigned long seed = 0;
   const char *dataset = NULL, *chains_dir = "Chains", *po_path = NULL, *tape_path = getenv("SER_TAPE_IN");
   const char *env_seed = getenv("GSL_RNG_SEED");
@@ -90,6 +90,7 @@ int main(int argc, char **argv)
       else if (!strcmp(a, "--select")) select_k = atoi(v);
       else if (!strcmp(a, "--po")) po_path = v;
       else if (!strcmp(a, "--device")) device = atoi(v);
+      else if (!strcmp(a, "--manycd")) manycd = atoi(v) != 0;
       else usage(argv[0]);
       i++;
     }
@@ -97,11 +98,10 @@ int main(int argc, char **argv)
   } else if (argc == 2) {
     first = atoi(argv[1]); /* mcmc.c:115,153 */
   } else if (argc == 4) {
-    int manycd = 0;
     if (!(sscanf(argv[1], "%d", &manycd) == 1 && sscanf(argv[2], "%d", &burn) == 1 && burn >= 0 &&
           sscanf(argv[3], "%d", &samples) == 1 && samples >= 0))
       usage(argv[0]);
-    if (manycd) { fprintf(stderr, "mcmc: manycd=1 (per-taxon c, d) is not supported by this build\n"); return 1; }
+    manycd = manycd != 0; /* mcmc_readmodel tests it as a flag (mcmc.c:363) */
   } else {
     usage(argv[0]);
   }
@@ -118,6 +118,7 @@ int main(int argc, char **argv)
   cfg.store = (n_chains <= 100) ? SER_STORE_FULL : SER_STORE_PI;
   cfg.max_samples = samples;
   cfg.device = device;
+  cfg.manycd = manycd;
   if (ser_run_create(ds, &cfg, &run)) die("ser_run_create");
   if (tape_path) {
     uint64_t offs[2] = {0, 0};

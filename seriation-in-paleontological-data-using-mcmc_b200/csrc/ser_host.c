@@ -373,8 +373,17 @@ int ser_write_chain_files(ser_run *run, int32_t chain, const char *dir)
   double *ll = (double *)malloc((size_t)(ns ? ns : 1) * 8);
   int32_t *fa = (int32_t *)malloc((size_t)M * 4), *fb = (int32_t *)malloc((size_t)M * 4), *fpi = (int32_t *)malloc((size_t)N * 4);
   double cdl[3], sums[3];
+  /* manycd: per-taxon c, d of every sample and of the final state */
+  const int many = ser_run_is_manycd(run);
+  double *call = NULL, *dall = NULL, *fc = NULL, *fd = NULL;
   FILE *f = NULL;
   rc = ser_run_fetch_samples(run, chain, a, b, pi, c, d, ll, &ns);
+  if (!rc && many) {
+    call = (double *)malloc((size_t)(ns ? ns : 1) * M * 8); dall = (double *)malloc((size_t)(ns ? ns : 1) * M * 8);
+    fc = (double *)malloc((size_t)M * 8); fd = (double *)malloc((size_t)M * 8);
+    rc = ser_run_fetch_cd_samples(run, chain, call, dall, NULL);
+    if (!rc) rc = ser_run_get_cd(run, chain, fc, fd);
+  }
   if (!rc) rc = ser_run_get_state(run, chain, fa, fb, fpi, NULL, NULL, NULL, NULL, NULL, NULL, cdl, NULL);
   if (!rc) rc = ser_run_chain_sums(run, chain, sums, NULL);
   if (rc) goto done;
@@ -390,9 +399,9 @@ int ser_write_chain_files(ser_run *run, int32_t chain, const char *dir)
     fprintf(f, ",");
     for (int32_t i = 0; i < N; i++) fprintf(f, "%d ", pi[(size_t)s * N + i]);
     fprintf(f, ",");
-    for (int32_t i = 0; i < M; i++) fprintf(f, "%.14f ", ec);
+    for (int32_t i = 0; i < M; i++) fprintf(f, "%.14f ", many ? exp(call[(size_t)s * M + i]) : ec);
     fprintf(f, ",");
-    for (int32_t i = 0; i < M; i++) fprintf(f, "%.14f ", ed);
+    for (int32_t i = 0; i < M; i++) fprintf(f, "%.14f ", many ? exp(dall[(size_t)s * M + i]) : ed);
     fprintf(f, ",%.14f\n", ll[s]);
   }
   fclose(f);
@@ -408,7 +417,8 @@ int ser_write_chain_files(ser_run *run, int32_t chain, const char *dir)
   snprintf(path, sizeof(path), "%s/taxa.csv", dir);
   if (!(f = fopen(path, "w"))) { ser_set_error("cannot open %s", path); rc = SER_E_IO; goto done; }
   fprintf(f, "a,b,c,d\n");
-  for (int32_t i = 0; i < M; i++) fprintf(f, "%d,%d,%.14f,%.14f\n", fa[i], fb[i], exp(cdl[0]), exp(cdl[1]));
+  for (int32_t i = 0; i < M; i++)
+    fprintf(f, "%d,%d,%.14f,%.14f\n", fa[i], fb[i], exp(many ? fc[i] : cdl[0]), exp(many ? fd[i] : cdl[1]));
   fclose(f);
   snprintf(path, sizeof(path), "%s/sites.csv", dir);
   if (!(f = fopen(path, "w"))) { ser_set_error("cannot open %s", path); rc = SER_E_IO; goto done; }
@@ -425,6 +435,7 @@ int ser_write_chain_files(ser_run *run, int32_t chain, const char *dir)
   fclose(f);
 done:
   free(a); free(b); free(pi); free(c); free(d); free(ll); free(fa); free(fb); free(fpi);
+  free(call); free(dall); free(fc); free(fd);
   return rc;
 }
 

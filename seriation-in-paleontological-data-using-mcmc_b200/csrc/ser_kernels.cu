@@ -75,6 +75,10 @@ struct KParams {
   double *samp_cdl;
   double c0, cc0, d0, dd0, eps;
   long long ones_total;
+  /* per-taxon c, d (manycd = 1, mcmc.c:777-785, :807-815) */
+  int manycd;
+  double *cd4;         /* [chain][4][Mpad]: c, log(1-e^c), d, log(1-e^d) per column */
+  double *samp_cd_all; /* [chain][sample][2][M]: c, d per taxon (SER_STORE_FULL) */
 };
 
 /* ------------------------------------------------------------------ shared-memory carve-up */
@@ -92,10 +96,12 @@ struct Smem {
   uint16_t *st4;    /* 4*C: per-column step geometry: cur, bound, ocur, kb */
   uint16_t *pre;    /* (W+1)*C: pre[w][col] = ones of the column in words < w */
   uint16_t *hp;     /* N+1: hard positions, ascending */
+  double *wcol;     /* manycd only: 4*C per-column weights A, g, 1/g, 1/(1-e^-g) for the dense item phase */
+  double *redd;     /* manycd only: 2*32 doubles of reduction scratch */
   uint16_t *rpi, *tmp16, *perm16; /* N each */
 };
 
-__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C, int I)
+__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C, int I, int manycd = 0)
 {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
@@ -103,6 +109,7 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
   size_t o_H = take(sizeof(double) * (N + 2));
   size_t o_val = take(sizeof(double) * (I + 1)), o_lm = take(sizeof(double) * C);
+  size_t o_wc = take(manycd ? sizeof(double) * 4 * C : 0), o_rd = take(manycd ? sizeof(double) * 2 * SER_MAX_WARPS : 0);
   size_t o_pos = take(sizeof(uint16_t) * (I + 1)), o_st = take(sizeof(uint16_t) * 4 * C);
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
@@ -112,6 +119,7 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
     s->H = (double *)(base + o_H);
     s->val = (double *)(base + o_val); s->lmax = (double *)(base + o_lm);
+    s->wcol = (double *)(base + o_wc); s->redd = (double *)(base + o_rd);
     s->pos = (uint16_t *)(base + o_pos); s->st4 = (uint16_t *)(base + o_st);
     s->V = (uint32_t *)(base + o_v); s->red = (int *)(base + o_r); s->pre = (uint16_t *)(base + o_h); s->hp = (uint16_t *)(base + o_hp);
     s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q); s->perm16 = (uint16_t *)(base + o_m);
@@ -300,6 +308,11 @@ __global__ void ser_init_kernel(KParams p)
   totals_from(p, wt, T1, LEN, &t0a, &f0a, &t1a, &f1a, &loglik);
 
   for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
+  if (p.manycd)
+    for (int c = tid; c < M; c += C) {
+      double *cd = p.cd4 + (size_t)chain * 4 * p.Mpad + c;
+      cd[0] = p.c0; cd[p.Mpad] = p.cc0; cd[2 * p.Mpad] = p.d0; cd[3 * p.Mpad] = p.dd0;
+    }
   if (tid == 0) {
     ChainScalars sc;
     memset(&sc, 0, sizeof(sc));
@@ -638,6 +651,341 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
   }
   for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
   if (tid == 0) p.scal[chain] = sc;
+}
+
+/* ------------------------------------------------------------------ the sweep kernel, per-taxon c/d
+ * manycd = 1 (mcmc.c:777-785, :807-815): every taxon has its own c_m, d_m.  Same choreography as
+ * ser_sweep_kernel; what changes: the Beta draws, weights and likelihood terms are per thread, the
+ * geometric run sums are evaluated on the fly (no shared table), and delta / loglik are float
+ * sums over taxa -- reduced in parallel, and re-done as the reference's sequential sum whenever the
+ * sign could be ambiguous or the value is about to be saved. */
+__device__ __forceinline__ void block_sum3d(int v0, int v1, int v2, double x, int *red, double *redd, int &buf, int *o0, int *o1,
+                                            int *o2, double *ox)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v0 = __reduce_add_sync(0xffffffffu, v0);
+  v1 = __reduce_add_sync(0xffffffffu, v1);
+  v2 = __reduce_add_sync(0xffffffffu, v2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  int *r = red + buf * (SER_MAX_WARPS * 4);
+  double *rd = redd + buf * SER_MAX_WARPS;
+  if (lane == 0) { r[warp * 4 + 0] = v0; r[warp * 4 + 1] = v1; r[warp * 4 + 2] = v2; rd[warp] = x; }
+  __syncthreads();
+  int s0 = 0, s1 = 0, s2 = 0;
+  double sx = 0.0;
+  if (lane < nwarp) { s0 = r[lane * 4 + 0]; s1 = r[lane * 4 + 1]; s2 = r[lane * 4 + 2]; sx = rd[lane]; }
+  s0 = __reduce_add_sync(0xffffffffu, s0);
+  s1 = __reduce_add_sync(0xffffffffu, s1);
+  s2 = __reduce_add_sync(0xffffffffu, s2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+  buf ^= 1;
+  *o0 = s0; *o1 = s1; *o2 = s2; *ox = sx;
+}
+
+__device__ __forceinline__ bool mh_decide_many(const KParams &p, const Smem &sm, const SerWeights &wt, PropState &ps, int taxon,
+                                               bool is_taxon, int dt0, int dt1, bool exact, int *D0, int *D1, double *delta_out)
+{
+  int nz;
+  double delta;
+  block_sum3d(dt0, dt1, (dt0 | dt1) != 0, is_taxon ? ser_term(wt, dt0, dt1) : 0.0, sm.red, sm.redd, ps.buf, D0, D1, &nz, &delta);
+  auto reference_sum = [&]() { /* mcmc.c:1214/1435/1630: per-taxon terms added in taxon order */
+    double acc = 0.0;
+    __syncthreads();
+    if (is_taxon) sm.terms[taxon] = ser_term(wt, dt0, dt1);
+    __syncthreads();
+    for (int m = 0; m < p.M; m++) acc = SER_ADD(acc, sm.terms[m]);
+    return acc;
+  };
+  bool seq = false;
+  if (!nz) delta = 0.0;
+  else if (fabs(delta) < 1e-7) { delta = reference_sum(); seq = true; } /* the parallel sum is good to ~1e-12 */
+  bool accept = delta >= 0.0;
+  if (!accept) accept = delta > sm.logdraw[ps.k++];
+  if (accept && exact && !seq && nz) delta = reference_sum();
+  *delta_out = delta;
+  return accept;
+}
+
+__global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_manycd(KParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem sm;
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I, 1);
+
+  const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
+  const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+  uint32_t *col = sm.V + tid;
+  uint16_t *pre = sm.pre + tid;
+  const bool is_taxon = tid < M, is_col = tid <= M;
+
+  ChainScalars sc = p.scal[chain];
+  for (int n = tid; n < N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
+  int a = 0, b = 0, taxon = 0, off_c = 0, ones_c = 0;
+  double c = p.c0, cc = p.cc0, d = p.d0, dd = p.dd0;
+  if (is_taxon) {
+    a = p.ab[(size_t)chain * 2 * p.Mpad + tid];
+    b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
+    taxon = p.order[tid];
+    off_c = p.off[tid];
+    ones_c = p.ones[tid];
+    const double *cd = p.cd4 + (size_t)chain * 4 * p.Mpad + tid;
+    c = cd[0]; cc = cd[p.Mpad]; d = cd[2 * p.Mpad]; dd = cd[3 * p.Mpad];
+  }
+  __syncthreads();
+  build_columns(p, sm);
+  __syncthreads();
+  if (tid == M) rebuild_hard(p, sm);
+  __syncthreads();
+
+  const double *tape = nullptr;
+  long long tape_len = 0;
+  if (p.mode == SER_MODE_REPLAY) {
+    tape = p.tape + p.tape_off[chain];
+    tape_len = (long long)(p.tape_off[chain + 1] - p.tape_off[chain]);
+  }
+  SerWeights wt;
+  ser_set_weights_own(&wt, c, cc, d, dd, N);
+  wt.eps = p.eps;
+  SerHard hd;
+  hd.hcol = sm.V + M; hd.hpre = sm.pre + M; hd.hp = sm.hp; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh;
+  PropState ps;
+  ps.k = 0; ps.buf = 0;
+
+  for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
+    for (int s = 0; s < p.sweeps_per_call; s++) {
+      /* ================= draws: M Betas for c, M for d, 2M uniforms, then the pi draws ================= */
+      __syncthreads();
+      double ua = 0.0, ub = 0.0, yc = 0.0, lyc = 0.0, l1c = 0.0, yd = 0.0, lyd = 0.0, l1d = 0.0;
+      if (p.mode == SER_MODE_REPLAY) {
+        const long long need = sc.cursor + 8 * (long long)M;
+        if (need > tape_len) { sc.flags |= 1; break; }
+        for (int t = tid; t < SER_PI_DRAWS; t += C) {
+          const long long idx = need + t;
+          const double u = idx < tape_len ? tape[idx] : 0.5;
+          sm.draws_pi[t] = u;
+          sm.logdraw[t] = log(u);
+        }
+        if (is_taxon) {
+          const double *tc = tape + sc.cursor + 3 * taxon, *td = tape + sc.cursor + 3 * (long long)M + 3 * taxon;
+          yc = tc[0]; lyc = tc[1]; l1c = tc[2];
+          yd = td[0]; lyd = td[1]; l1d = td[2];
+          ua = tape[sc.cursor + 6 * (long long)M + 2 * taxon]; ub = tape[sc.cursor + 6 * (long long)M + 2 * taxon + 1];
+        }
+      } else {
+        for (int t = tid; t < SER_PI_DRAWS; t += C) {
+          const double u = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+          sm.draws_pi[t] = u;
+          sm.logdraw[t] = log(ser_pos(u));
+        }
+        if (is_taxon) { /* Beta(1+f1_m, 1+t0_m) and Beta(1+f0_m, 1+t1_m) from the taxon's own counts */
+          const int t1 = ser_col_popc(col, pre, C, a, b), len = b - a;
+          const int f1 = ones_c - t1, f0 = len - t1, t0 = N - len - f1;
+          const uint32_t blk = SER_BLK_MANYCD + 4u * (uint32_t)taxon;
+          yc = ser_beta_from_gammas(ser_gamma_ge1(1.0 + (double)f1, p.seed, gchain, sc.sweep, blk),
+                                    ser_gamma_ge1(1.0 + (double)t0, p.seed, gchain, sc.sweep, blk + 1u));
+          yd = ser_beta_from_gammas(ser_gamma_ge1(1.0 + (double)f0, p.seed, gchain, sc.sweep, blk + 2u),
+                                    ser_gamma_ge1(1.0 + (double)t1, p.seed, gchain, sc.sweep, blk + 3u));
+          if (yc > 0.0) { lyc = ser_log(yc); l1c = ser_log(SER_SUB(1.0, ser_exp(lyc))); }
+          if (yd > 0.0) { lyd = ser_log(yd); l1d = ser_log(SER_SUB(1.0, ser_exp(lyd))); }
+          uint32_t o[4];
+          ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+          ua = ser_u53(o[0], o[1]); ub = ser_u53(o[2], o[3]);
+        }
+      }
+      /* ================= c_m, d_m (mcmc_samplebeta per taxon) ================= */
+      if (is_taxon) {
+        if (yc > 0.0 && SER_MINC <= lyc && lyc <= SER_MAXC) { c = lyc; cc = l1c; }
+        if (yd > 0.0 && SER_MIND <= lyd && lyd <= SER_MAXD) { d = lyd; dd = l1d; }
+        ser_set_weights_own(&wt, c, cc, d, dd, N);
+        sm.wcol[4 * tid + 0] = wt.A; sm.wcol[4 * tid + 1] = wt.g; sm.wcol[4 * tid + 2] = wt.inv_g; sm.wcol[4 * tid + 3] = wt.hs;
+        if (taxon == 0) { sm.draws_cd[0] = c; sm.draws_cd[1] = d; }
+      }
+      sc.counters[0] += M; sc.counters[1] += M;
+
+      /* ================= a/b Gibbs, item formulation ================= */
+      if (is_taxon) ser_expand_ones(col, C, W, sm.pos + off_c);
+      int changed = 0;
+#pragma unroll 1
+      for (int step = 0; step < 2; step++) {
+        SerStep st;
+        double lmax = 0.0;
+        if (is_taxon) {
+          st = step == 0 ? ser_step_a(col, pre, C, W, N, a, b) : ser_step_b(col, pre, C, W, N, a, b);
+          lmax = ser_step_lmax(wt, st, sm.pos + off_c);
+          sm.lmax[tid] = lmax;
+          *reinterpret_cast<uint2 *>(sm.st4 + 4 * tid) =
+              make_uint2((uint32_t)st.cur | ((uint32_t)st.bound << 16), (uint32_t)st.ocur | ((uint32_t)st.kb << 16));
+        }
+        __syncthreads(); /* also publishes the staged draws, wcol and the postings */
+        for (int e = tid; e < p.I; e += C) {
+          const uint32_t ck = p.item_col[e];
+          const int cix = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
+          const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cix);
+          SerStep it;
+          it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
+          if (kk <= it.kb) {
+            SerWeights w;
+            w.A = sm.wcol[4 * cix + 0]; w.g = sm.wcol[4 * cix + 1]; w.inv_g = sm.wcol[4 * cix + 2]; w.hs = sm.wcol[4 * cix + 3];
+            w.eps = p.eps; w.H = nullptr; w.hmax = N + 1;
+            it.nones = p.ones[cix]; it.N = N; it.rev = step;
+            sm.val[e] = ser_item_weight(w, it, sm.pos + (e - kk), kk, sm.lmax[cix]);
+          }
+        }
+        __syncthreads();
+        if (is_taxon) {
+          const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + off_c, lmax, step == 0 ? ua : ub);
+          if (step == 0) { changed += pick != a; a = pick; }
+          else { changed += (N - pick) != b; b = N - pick; }
+        }
+      }
+      const bool exact = p.sampling && s == p.sweeps_per_call - 1;
+      {
+        int t1 = 0, len = 0, T1, LEN, CH;
+        double term = 0.0, ll;
+        if (is_taxon) {
+          t1 = ser_col_popc(col, pre, C, a, b); len = b - a;
+          const int f1 = ones_c - t1, f0 = len - t1, t0 = N - len - f1;
+          term = SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)t0, wt.cc), SER_MUL((double)f0, wt.d)), SER_MUL((double)t1, wt.dd)),
+                         SER_MUL((double)f1, wt.c));
+        }
+        block_sum3d(t1, len, changed, term, sm.red, sm.redd, ps.buf, &T1, &LEN, &CH, &ll);
+        sc.t1a = T1; sc.f1a = (int)p.ones_total - T1; sc.f0a = LEN - T1; sc.t0a = N * M - LEN - sc.f1a;
+        sc.loglik = ll;
+        sc.counters[2] += CH;
+        if (exact) { /* mcmc_logl's own order */
+          if (is_taxon) sm.terms[taxon] = term;
+          __syncthreads();
+          double acc = 0.0;
+          for (int m = 0; m < M; m++) acc = SER_ADD(acc, sm.terms[m]);
+          sc.loglik = acc;
+        }
+      }
+
+      /* ================= 16 proposals for pi ================= */
+      ps.k = 0;
+      for (int prop = 0; prop < 16; prop++) {
+        const int kind = prop == 0 ? 3 : ((prop - 1) % 3);
+        int dt0 = 0, dt1 = 0, D0, D1;
+        double delta;
+        if (kind == 0) {
+          const int i = ser_draw_int(sm.draws_pi[ps.k], N);
+          int j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+          ps.k += 2;
+          if (j >= i) j++;
+          const int lo = min(i, j), hi = max(i, j);
+          if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
+          if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
+          if (!mh_decide_many(p, sm, wt, ps, taxon, is_taxon, dt0, dt1, exact, &D0, &D1, &delta)) continue;
+          if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
+          if (is_col) { ser_col_rotate(col, C, W, i, j); ser_col_fix_pre(col, pre, C, lo >> 5, hi >> 5); }
+          for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
+          __syncthreads();
+          for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
+          if (tid == M) rebuild_hard(p, sm);
+          sc.counters[3]++;
+        } else if (kind == 1 || kind == 3) {
+          int i, j;
+          if (kind == 1) {
+            i = ser_draw_int(sm.draws_pi[ps.k], N);
+            j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+            ps.k += 2;
+            if (j >= i) j++;
+            else { const int t = i; i = j; j = t; }
+          } else {
+            i = ser_draw_int(sm.draws_pi[ps.k], N - 1);
+            ps.k += 1;
+            j = i + 1;
+          }
+          if (ser_hard_count(hd, i, j) > 1) continue;
+          const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+          ps.k += 2;
+          if (is_taxon) ser_pi2_delta(col, pre, C, a, b, i, j, inc1, inc2, &dt0, &dt1);
+          if (!mh_decide_many(p, sm, wt, ps, taxon, is_taxon, dt0, dt1, exact, &D0, &D1, &delta)) continue;
+          if (is_taxon) {
+            const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
+            ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
+          }
+          if (is_col) { ser_col_reverse(col, C, W, i, j); ser_col_fix_pre(col, pre, C, i >> 5, j >> 5); }
+          for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
+          __syncthreads();
+          for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
+          if (tid == M) rebuild_hard(p, sm);
+          sc.counters[kind == 1 ? 4 : 5]++;
+        } else {
+          const int nfree = N - p.nh;
+          if (nfree < 2) continue;
+          const int r1 = ser_draw_int(sm.draws_pi[ps.k], nfree), r2 = ser_draw_int(sm.draws_pi[ps.k + 1], nfree - 1);
+          ps.k += 2;
+          int ir, jr;
+          if (r1 <= r2) { ir = r1; jr = r2 + 1; } else { ir = r2; jr = r1; }
+          const SerPi3 g = ser_pi3_window(hd, ir, jr);
+          const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+          ps.k += 2;
+          if (is_taxon) ser_pi3_delta(col, pre, C, hd, g, a, b, inc1, inc2, &dt0, &dt1);
+          if (!mh_decide_many(p, sm, wt, ps, taxon, is_taxon, dt0, dt1, exact, &D0, &D1, &delta)) continue;
+          for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
+          __syncthreads();
+          if (is_taxon) {
+            const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
+            ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
+            ser_col_permute(col, C, W, g.i, g.j, sm.perm16);
+            ser_col_fix_pre(col, pre, C, g.i >> 5, g.j >> 5);
+          }
+          for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
+          __syncthreads();
+          for (int n = g.i + tid; n <= g.j; n += C) sm.rpi[n] = sm.tmp16[n];
+          sc.counters[6]++;
+        }
+        sc.t0a += D0; sc.f0a -= D0; sc.t1a += D1; sc.f1a -= D1;
+        sc.loglik = SER_ADD(sc.loglik, delta);
+        __syncthreads();
+      }
+
+      if (p.mode == SER_MODE_REPLAY) sc.cursor += 8 * (long long)M + ps.k;
+      else sc.sweep++;
+      sc.counters[7]++;
+    }
+    if (sc.flags & 1) break;
+
+    if (p.sampling) {
+      const int sidx = sc.n_samples;
+      const double c_first = sm.draws_cd[0], d_first = sm.draws_cd[1]; /* taxon 0's c, d (compute_exp_data, mcmc.c:56-57) */
+      if (sidx < p.max_samples) {
+        const size_t row = (size_t)chain * p.max_samples + sidx;
+        if (p.store >= SER_STORE_PI)
+          for (int pos = tid; pos < N; pos += C) p.samp_pi[row * N + sm.rpi[pos]] = (uint16_t)pos;
+        if (p.store >= SER_STORE_FULL) {
+          if (is_taxon) {
+            p.samp_a[row * M + taxon] = (uint16_t)a; p.samp_b[row * M + taxon] = (uint16_t)b;
+            p.samp_cd_all[(row * 2 + 0) * M + taxon] = c; p.samp_cd_all[(row * 2 + 1) * M + taxon] = d;
+          }
+          if (tid == 0) { p.samp_cdl[row * 3 + 0] = c_first; p.samp_cdl[row * 3 + 1] = d_first; p.samp_cdl[row * 3 + 2] = sc.loglik; }
+        }
+      }
+      sc.c = c_first; sc.d = d_first;
+      sc.sum_negll = SER_ADD(sc.sum_negll, -sc.loglik);
+      sc.sum_ec = SER_ADD(sc.sum_ec, exp(c_first));
+      sc.sum_ed = SER_ADD(sc.sum_ed, exp(d_first));
+      sc.n_samples++;
+    }
+  }
+
+  __syncthreads();
+  if (is_taxon) {
+    p.ab[(size_t)chain * 2 * p.Mpad + tid] = (uint16_t)a;
+    p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid] = (uint16_t)b;
+    double *cd = p.cd4 + (size_t)chain * 4 * p.Mpad + tid;
+    cd[0] = c; cd[p.Mpad] = cc; cd[2 * p.Mpad] = d; cd[3 * p.Mpad] = dd;
+    if (taxon == 0) { sm.draws_cd[0] = c; sm.draws_cd[1] = cc; sm.draws_cd[2] = d; sm.draws_cd[3] = dd; }
+  }
+  for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
+  __syncthreads();
+  if (tid == 0) { /* the scalar slots carry taxon 0's c, d */
+    sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3];
+    p.scal[chain] = sc;
+  }
 }
 
 /* ------------------------------------------------------------------ the sweep kernel, large shapes
@@ -1040,13 +1388,28 @@ __global__ void ser_check_kernel(KParams p, int *bad_count)
     if (cnt != p.nh) atomicOr(&s_flags, 8);
   }
   int t1 = 0, len = 0;
+  double llp = 0.0; /* manycd: the log-likelihood is a sum of per-taxon terms */
   for (int c = tid; c < M; c += C) {
     const int a = p.ab[(size_t)chain * 2 * p.Mpad + c], b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c];
     if (!(0 <= a && a <= b && b <= N)) atomicOr(&s_flags, 2);
-    else { t1 += taxon_count(p, sm.rpi, c, a, b); len += b - a; }
+    else {
+      const int k1 = taxon_count(p, sm.rpi, c, a, b);
+      t1 += k1; len += b - a;
+      if (p.manycd) {
+        const double *cd = p.cd4 + (size_t)chain * 4 * p.Mpad + c;
+        const int f1 = p.ones[c] - k1, f0 = (b - a) - k1, t0 = N - (b - a) - f1;
+        llp += (double)t0 * cd[p.Mpad] + (double)f0 * cd[2 * p.Mpad] + (double)k1 * cd[3 * p.Mpad] + (double)f1 * cd[0];
+      }
+    }
   }
   int buf = 0, T1, LEN, dummy;
   block_sum3(t1, len, 0, sm.red, buf, &T1, &LEN, &dummy);
+  __shared__ double s_ll[32];
+  if (p.manycd) {
+    for (int o = 16; o > 0; o >>= 1) llp += __shfl_xor_sync(0xffffffffu, llp, o);
+    if ((tid & 31) == 0) s_ll[tid >> 5] = llp;
+    __syncthreads();
+  }
   if (tid == 0) {
     const ChainScalars sc = p.scal[chain];
     SerWeights wt;
@@ -1054,6 +1417,7 @@ __global__ void ser_check_kernel(KParams p, int *bad_count)
     int t0a, f0a, t1a, f1a;
     double ll;
     totals_from(p, wt, T1, LEN, &t0a, &f0a, &t1a, &f1a, &ll);
+    if (p.manycd) { ll = 0.0; for (int w = 0; w < (C + 31) / 32; w++) ll += s_ll[w]; }
     if (t0a != sc.t0a || f0a != sc.f0a || t1a != sc.t1a || f1a != sc.f1a || fabs(ll - sc.loglik) > 1e-8) s_flags |= 16;
     const int fl = s_flags | (sc.flags & 1);
     if (fl) atomicAdd(bad_count, 1);
@@ -1245,7 +1609,8 @@ struct ser_run {
   double *d_tape;
   unsigned long long *d_tape_off;
   uint16_t *d_samp_a, *d_samp_b, *d_samp_pi;
-  double *d_samp_cdl;
+  double *d_samp_cdl, *d_cd4, *d_samp_cd_all;
+  size_t smem_many;
   int *d_scratch_i; /* export buffers: a,b,pi,rpi,cnt[4M] */
   int *d_bad;
   cudaStream_t stream;
@@ -1298,6 +1663,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   if (M < 1 || M > SER_MAX_TAXA) { ser_set_error("ser_run_create: M=%d outside [1,%d]", M, SER_MAX_TAXA); return SER_E_ARG; }
   if (cfg->n_chains < 1 || cfg->sweeps_per_call < 1) { ser_set_error("ser_run_create: n_chains and sweeps_per_call must be >= 1"); return SER_E_ARG; }
   if (cfg->mode != SER_MODE_FREE && cfg->mode != SER_MODE_REPLAY) { ser_set_error("ser_run_create: bad mode"); return SER_E_ARG; }
+  if (cfg->manycd != 0 && cfg->manycd != 1) { ser_set_error("ser_run_create: manycd must be 0 or 1"); return SER_E_ARG; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     ser_set_error("ser_run_create: no CUDA device (this library has no CPU path)");
@@ -1389,10 +1755,25 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   kp.order = run->d_order; kp.off = run->d_off; kp.item_col = run->d_item_col;
   kp.ab = run->d_ab; kp.rpi = run->d_rpi; kp.scal = run->d_scal;
   kp.samp_a = run->d_samp_a; kp.samp_b = run->d_samp_b; kp.samp_pi = run->d_samp_pi; kp.samp_cdl = run->d_samp_cdl;
+  if (cfg->manycd) { /* per-taxon c, d: state rows and, with the full store, per-sample rows */
+    kp.manycd = 1;
+    CUDA_TRY(POOL_ALLOC(&run->d_cd4, nc * 4 * kp.Mpad * sizeof(double)));
+    if (cfg->store >= SER_STORE_FULL && cfg->max_samples > 0)
+      CUDA_TRY(POOL_ALLOC(&run->d_samp_cd_all, nc * cfg->max_samples * 2 * M * sizeof(double)));
+    kp.cd4 = run->d_cd4; kp.samp_cd_all = run->d_samp_cd_all;
+  }
 
   run->smem_small = aux_layout(nullptr, nullptr, N);
   run->smem_init = run->smem_small + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
   CUDA_TRY(cudaFuncSetAttribute(ser_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_init));
+  if (cfg->manycd) {
+    run->smem_many = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I, 1);
+    if (run->big || run->smem_many > 227 * 1024) {
+      ser_set_error("ser_run_create: manycd=1 needs one thread per taxon and %zu B of shared memory per chain (M <= 1023)", run->smem_many);
+      return SER_E_ARG;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel_manycd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_many));
+  }
   if (!run->big) {
     run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
     if (run->smem_sweep > 227 * 1024) run->big = 1; /* columns + items do not fit: use the L2-resident variant */
@@ -1436,7 +1817,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   cudaSetDevice(run->cfg.device);
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
-                  run->d_scratch_i, run->d_bad, run->d_gV, run->d_gpre, run->d_gpos, run->d_gval, run->d_gterms};
+                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_gpos, run->d_gval, run->d_gterms};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   cudaStreamSynchronize(run->stream);
   cudaEventDestroy(run->ev_start); cudaEventDestroy(run->ev_stop);
@@ -1455,6 +1836,7 @@ extern "C" int ser_run_dims(const ser_run *run, int32_t *N, int32_t *M, int32_t 
   return SER_OK;
 }
 extern "C" const uint8_t *ser_run_hard_flags(const ser_run *run) { return run ? run->h_hard : nullptr; }
+extern "C" int ser_run_is_manycd(const ser_run *run) { return run ? run->cfg.manycd : 0; }
 
 extern "C" int ser_run_set_tapes(ser_run *run, const double *flat, const uint64_t *offsets)
 {
@@ -1496,7 +1878,8 @@ extern "C" int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling)
   KParams kp = run->kp;
   kp.n_calls = n_calls; kp.sampling = sampling;
   mark_launch(run);
-  if (run->big) ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+  if (run->cfg.manycd) ser_sweep_kernel_manycd<<<run->cfg.n_chains, run->C, run->smem_many, run->stream>>>(kp);
+  else if (run->big) ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
   else if (run->variant == 1) ser_sweep_kernel<384, 2><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
   else ser_sweep_kernel<1024, 1><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
   CUDA_TRY(cudaGetLastError());
@@ -1679,6 +2062,50 @@ extern "C" int ser_run_fetch_samples(ser_run *run, int32_t chain, int32_t *a, in
         if (d) d[s] = cdl[3 * s + 1];
         if (loglik) loglik[s] = cdl[3 * s + 2];
       }
+    }
+  }
+  return SER_OK;
+}
+
+/* manycd runs: per-taxon c, d of one chain (file order) */
+extern "C" int ser_run_get_cd(ser_run *run, int32_t chain, double *c, double *d)
+{
+  if (!chain_ok(run, chain)) return SER_E_ARG;
+  if (!run->cfg.manycd) { ser_set_error("ser_run_get_cd: run was created with manycd = 0"); return SER_E_STATE; }
+  if (!run->initialized) { ser_set_error("ser_run_get_cd: run not initialised"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  const int M = run->M, Mpad = run->kp.Mpad;
+  std::vector<double> h((size_t)4 * Mpad);
+  std::vector<uint16_t> order(M);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), run->d_cd4 + (size_t)chain * 4 * Mpad, h.size() * 8, cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(order.data(), run->d_order, M * sizeof(uint16_t), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  for (int col = 0; col < M; col++) {
+    if (c) c[order[col]] = h[col];
+    if (d) d[order[col]] = h[2 * Mpad + col];
+  }
+  return SER_OK;
+}
+
+/* manycd runs with SER_STORE_FULL: per-taxon c, d of every stored sample, [n][M] each */
+extern "C" int ser_run_fetch_cd_samples(ser_run *run, int32_t chain, double *c, double *d, int32_t *n)
+{
+  if (!chain_ok(run, chain)) return SER_E_ARG;
+  if (!run->cfg.manycd || !run->d_samp_cd_all) { ser_set_error("ser_run_fetch_cd_samples: needs manycd = 1 and SER_STORE_FULL"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples, M = run->M;
+  if (n) *n = ns;
+  if (ns > 0 && (c || d)) {
+    std::vector<double> h((size_t)ns * 2 * M);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), run->d_samp_cd_all + (size_t)chain * run->cfg.max_samples * 2 * M, h.size() * 8,
+                             cudaMemcpyDeviceToHost, run->stream));
+    CUDA_TRY(cudaStreamSynchronize(run->stream));
+    for (int s = 0; s < ns; s++) {
+      if (c) memcpy(c + (size_t)s * M, h.data() + ((size_t)s * 2 + 0) * M, M * 8);
+      if (d) memcpy(d + (size_t)s * M, h.data() + ((size_t)s * 2 + 1) * M, M * 8);
     }
   }
   return SER_OK;

@@ -450,3 +450,165 @@ def test_labelled_outputs(S, tmp_path):
     assert taxa[0] == "taxon,a,b" and taxa[1] == "Genus_0,%d,%d" % (st["a"][0], st["b"][0])
     sites = (tmp_path / "sites_named.csv").read_text().split("\n")
     assert sites[3] == "Site_2,0,18,1,%d" % st["pi"][2]
+
+
+# ----------------------------------------------------------------------------- per-taxon c, d (manycd = 1)
+def _manycd_oracle(O, X, hard, seed=None, philox=None, tape=None, detmath=False):
+    o = O.Oracle(X, hard).manycd()
+    if tape is not None:
+        o.source_tape(tape)
+    elif philox is not None:
+        o.source_philox(*philox)
+    else:
+        o.source_mt(seed)
+    o.record(True).detmath(detmath)
+    o.randomize()
+    return o
+
+
+def _cmp_manycd(run, i, want, what, exact_ll):
+    got = run.state(i)
+    for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+        assert np.array_equal(got[k], getattr(want, k)), (what, k)
+    c, d = run.cd(i)
+    assert c.tobytes() == want.c_all.tobytes() and d.tobytes() == want.d_all.tobytes(), what
+    assert got["c"] == want.c_all[0] and got["d"] == want.d_all[0], what
+    if exact_ll:
+        assert got["loglik"] == want.loglik, (what, got["loglik"], want.loglik)
+    else:
+        assert abs(got["loglik"] - want.loglik) <= LL_RTOL * abs(want.loglik), what
+
+
+def _manycd_replay_case(S, O, X, hard, seeds, burn, samp):
+    oracles = [_manycd_oracle(O, X, hard, seed=s) for s in seeds]
+    inits = [o.state() for o in oracles]
+    trace = []
+    for o in oracles:   # record the tapes first: the run needs them whole
+        trace.append([o.sample() and None or o.state() for _ in range(burn + samp)])
+    run = S.Run(S.Dataset.from_bits(X, hard), len(seeds), mode=S.MODE_REPLAY, store=S.STORE_FULL, max_samples=samp, manycd=True)
+    run.set_tapes([o.tape() for o in oracles]).init().sync()
+    for i in range(len(seeds)):
+        _cmp_manycd(run, i, inits[i], ("init", i), False)
+    run.advance(burn, False).sync()
+    for i in range(len(seeds)):
+        _cmp_manycd(run, i, trace[i][burn - 1], ("burn", i), False)
+    for s in range(samp):
+        run.advance(1, True).sync()
+        for i in range(len(seeds)):
+            _cmp_manycd(run, i, trace[i][burn + s], ("sample", s, i), True)
+    assert run.check() == 0
+    for i, o in enumerate(oracles):
+        assert run.state(i)["slots"] == o.tape().size
+        got = run.fetch_samples(i)
+        for s in range(samp):
+            w = trace[i][burn + s]
+            assert np.array_equal(got["a"][s], w.a) and np.array_equal(got["b"][s], w.b) and np.array_equal(got["pi"][s], w.pi)
+            assert got["c_all"][s].tobytes() == w.c_all.tobytes() and got["d_all"][s].tobytes() == w.d_all.tobytes()
+            assert got["c"][s] == w.c_all[0] and got["d"][s] == w.d_all[0] and got["loglik"][s] == w.loglik
+    run.close()
+
+
+@pytest.mark.parametrize("name,burn,samp", [("g10s10", 20, 20), ("g5s5", 3, 3), ("g2s2", 3, 3)])
+def test_manycd_replay_bit_exact(S, oracle_mod, name, burn, samp):
+    X, hard = load_hex_dataset(name)
+    _manycd_replay_case(S, oracle_mod, X, hard, [31, 32, 0], burn, samp)
+
+
+@pytest.mark.parametrize("shape", EDGE_SHAPES)
+def test_manycd_replay_edge_shapes(S, oracle_mod, shape):
+    rng = np.random.default_rng(hash(shape) & 0xffff)
+    X, hard = random_dataset(rng, *shape)
+    _manycd_replay_case(S, oracle_mod, X, hard, [4, 5], 8, 8)
+
+
+def test_manycd_replay_of_unmodified_reference_trace(S):
+    """golden trace of the UNMODIFIED reference run as `mcmc 1 tb ts` (tools/make_golden.py)"""
+    g = np.load(os.path.join(GOLDEN, "ref_g10s10_manycd.npz"))
+    X, hard = load_hex_dataset("g10s10")
+    run = S.Run(S.Dataset.from_bits(X, hard), 1, mode=S.MODE_REPLAY, manycd=True)
+    run.set_tapes([g["tape"]]).init()
+    for r in range(len(g["kind"])):
+        if r:
+            run.advance(1, True)
+        st = run.state(0)
+        for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+            assert np.array_equal(st[k], g[k][r].astype(np.int32)), (k, r)
+        assert st["slots"] == int(g["slots"][r])
+        c, d = run.cd(0)
+        assert c.tobytes() == g["c_all"][r].tobytes() and d.tobytes() == g["d_all"][r].tobytes(), r
+        if r:
+            assert st["loglik"] == g["cdl"][r][2], r
+        else:
+            assert abs(st["loglik"] - g["cdl"][r][2]) <= LL_RTOL * abs(g["cdl"][r][2])
+    run.close()
+
+
+@pytest.mark.parametrize("name,burn,samp", [("g10s10", 10, 10), ("g2s2", 2, 2)])
+def test_manycd_free_running_equals_oracle_philox(S, oracle_mod, name, burn, samp):
+    X, hard = load_hex_dataset(name)
+    seed, offset, n = 1234, 17, 4
+    run = S.Run(S.Dataset.from_bits(X, hard), n, mode=S.MODE_FREE, seed=seed, chain_offset=offset, manycd=True)
+    run.init().advance(burn, False).advance(samp, True).sync()
+    assert run.check() == 0
+    for i in range(n):
+        o = _manycd_oracle(oracle_mod, X, hard, philox=(seed, offset + i), detmath=True)
+        for _ in range(burn + samp):
+            o.sample()
+        _cmp_manycd(run, i, o.state(), ("free", i), True)
+    run.close()
+
+
+def test_manycd_errors_and_writers(S, oracle_mod, tmp_path):
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    with pytest.raises(S.SeriationError):   # one thread per taxon: no large-shape variant
+        S.Run(S.Dataset.from_bits(np.ones((8, 2000), np.uint8)), 1, manycd=True)
+    plain = S.Run(ds, 1).init()
+    with pytest.raises(S.SeriationError):
+        plain.cd(0)
+    plain.close()
+    o = _manycd_oracle(oracle_mod, X, hard, seed=3)
+    states = [o.sample() and None or o.state() for _ in range(6)]
+    run = S.Run(ds, 1, mode=S.MODE_REPLAY, store=S.STORE_FULL, max_samples=4, manycd=True)
+    run.set_tapes([o.tape()]).init().advance(2, False).advance(4, True).sync()
+    run.write_chain_files(0, str(tmp_path))
+    N, M = X.shape
+    lines = (tmp_path / "chain_data.csv").read_text().split("\n")
+    for s, line in enumerate(lines[:4]):
+        f, w = line.split(","), states[2 + s]
+        assert [int(v) for v in f[0].split()] == w.a.tolist()
+        assert f[3].split() == ["%.14f" % np.exp(v) for v in w.c_all]   # mcmc.c:86-87 prints exp(c[i]) per taxon
+        assert f[4].split() == ["%.14f" % np.exp(v) for v in w.d_all]
+        assert f[5] == "%.14f" % w.loglik
+    taxa = (tmp_path / "taxa.csv").read_text().split("\n")
+    w = states[-1]
+    assert taxa[1:M + 1] == ["%d,%d,%.14f,%.14f" % (w.a[i], w.b[i], np.exp(w.c_all[i]), np.exp(w.d_all[i])) for i in range(M)]
+    run.close()
+
+
+def test_manycd_cli(S, oracle_mod, tmp_path):
+    """`mcmc 1 3 4 < g10s10.txt` (manycd Tburnin T, mcmc.c:115-121).  The unmodified reference cannot
+    finish this form -- chain_index stays NULL and atoi(NULL) faults at mcmc.c:153 -- so the files are
+    checked against the oracle (itself pinned to the reference's manycd sampler by the golden trace)."""
+    import subprocess
+    from tools.datasets import write_txt
+    X, hard = load_hex_dataset("g10s10")
+    N, M = X.shape
+    ds = tmp_path / "g10s10.txt"
+    write_txt(str(ds), X, hard)
+    o = _manycd_oracle(oracle_mod, X, hard, seed=77)
+    states = [o.sample() and None or o.state() for _ in range(7)]
+    tape = tmp_path / "tape.bin"
+    o.tape().tofile(str(tape))
+    env = dict(os.environ, SER_TAPE_IN=str(tape))
+    with open(ds) as f:
+        subprocess.run([os.path.join(S.PKG_DIR, "mcmc"), "1", "3", "4"], stdin=f, cwd=tmp_path, env=env, check=True)
+    out = tmp_path / "Chains" / "chain_00"
+    lines = (out / "chain_data.csv").read_text().split("\n")
+    assert len(lines) == 5
+    for s, line in enumerate(lines[:4]):
+        f, w = line.split(","), states[3 + s]
+        assert [int(v) for v in f[1].split()] == w.b.tolist() and [int(v) for v in f[2].split()] == w.pi.tolist()
+        assert f[3].split() == ["%.14f" % np.exp(v) for v in w.c_all] and f[5] == "%.14f" % w.loglik
+    w = states[-1]
+    assert (out / "taxa.csv").read_text().split("\n")[M] == "%d,%d,%.14f,%.14f" % (w.a[M - 1], w.b[M - 1], np.exp(w.c_all[M - 1]), np.exp(w.d_all[M - 1]))
