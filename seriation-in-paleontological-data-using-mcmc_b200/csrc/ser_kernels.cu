@@ -708,7 +708,8 @@ __device__ __forceinline__ bool mh_decide_many(const KParams &p, const Smem &sm,
   return accept;
 }
 
-__global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_manycd(KParams p)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
@@ -1619,7 +1620,7 @@ struct ser_run {
   double elapsed_ms;
   long long launches;
   size_t smem_sweep, smem_init, smem_small, smem_big;
-  int Caux, big, big_threads, big_slots, variant;
+  int Caux, big, big_threads, big_slots, variant, variant_many;
   uint32_t *d_gV;
   uint16_t *d_gpre, *d_gpos;
   double *d_gval, *d_gterms;
@@ -1772,7 +1773,12 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
       ser_set_error("ser_run_create: manycd=1 needs one thread per taxon and %zu B of shared memory per chain (M <= 1023)", run->smem_many);
       return SER_E_ARG;
     }
-    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel_manycd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_many));
+    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel_manycd<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_many));
+    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel_manycd<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_many));
+    int occ64 = 0, occ85 = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel_manycd<1024, 1>, run->C, run->smem_many));
+    if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel_manycd<384, 2>, run->C, run->smem_many));
+    run->variant_many = (occ85 >= occ64 && occ85 > 0) ? 1 : 0;
   }
   if (!run->big) {
     run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
@@ -1878,7 +1884,8 @@ extern "C" int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling)
   KParams kp = run->kp;
   kp.n_calls = n_calls; kp.sampling = sampling;
   mark_launch(run);
-  if (run->cfg.manycd) ser_sweep_kernel_manycd<<<run->cfg.n_chains, run->C, run->smem_many, run->stream>>>(kp);
+  if (run->cfg.manycd && run->variant_many) ser_sweep_kernel_manycd<384, 2><<<run->cfg.n_chains, run->C, run->smem_many, run->stream>>>(kp);
+  else if (run->cfg.manycd) ser_sweep_kernel_manycd<1024, 1><<<run->cfg.n_chains, run->C, run->smem_many, run->stream>>>(kp);
   else if (run->big) ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
   else if (run->variant == 1) ser_sweep_kernel<384, 2><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
   else ser_sweep_kernel<1024, 1><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
