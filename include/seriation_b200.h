@@ -24,6 +24,7 @@
  *   ser_run_po_counts*        compute_pair_order_matrix script.py:155-189
  *   ser_run_posterior_sums    compute_exp_ages / compute_exp_pi / compute_exp_a
  *                                                       script.py:129-152, :230-276
+ *   ser_run_alive_counts      plot_taxa_occurence_probability_matrix / plot_false_*  script.py:306-448
  *   run_all_chains' Pool(8) over 100 processes (script.py:48-67) is replaced by
  *   n_chains in ser_run_config: one CTA per chain in one launch.
  */
@@ -163,6 +164,12 @@ int ser_po_finalize(const int32_t *counts, int32_t k, int32_t N, int32_t chains_
  * n_samples receives T. */
 int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32_t k, int64_t *corr_num, int32_t *pi_sum,
                            int32_t *a_sum, int32_t *b_sum, int32_t *n_samples);
+
+/* alive[c][j][m] = #{t : a_t(m) <= j <= b_t(m)} over the stored samples of the chosen chains owned by
+ * this run (same slab convention as above; int32 [k][N][M], host memory; needs SER_STORE_FULL).
+ * The counts behind plot_taxa_occurence_probability_matrix, plot_false_taxa_occurence_probability
+ * and plot_false_ones_probability (script.py:306-448): alive, T - alive, X * (T - alive). */
+int ser_run_alive_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *alive, int32_t *n_samples);
 
 /* ---------------------------------------------------------------- reference-compatible files */
 /* Writes Chains-style files for one local chain into `dir` (which must exist, like the

@@ -391,3 +391,67 @@ def exp_a(a_samples_per_chain, chains_selected: int) -> np.ndarray:
         a_sum_chain /= 1000
         a_sum += a_sum_chain
     return a_sum / chains_selected
+
+
+def exp_cd(c_samples_per_chain, d_samples_per_chain, chains_selected: int):
+    """script.py:102-126: the file carries exp(c) printed with %.14f; per chain sum / 1000, summed, / chains_selected"""
+    c_tot = d_tot = 0.0
+    for cs, ds_ in zip(c_samples_per_chain, d_samples_per_chain):
+        c_sum = d_sum = 0
+        for c, d in zip(cs, ds_):
+            c_sum += float("%.14f" % np.exp(c))
+            d_sum += float("%.14f" % np.exp(d))
+        c_tot += c_sum / 1000
+        d_tot += d_sum / 1000
+    return c_tot / chains_selected, d_tot / chains_selected
+
+
+def _shuffle_like_script(X_sum, exp_pi_v, exp_a_v):
+    """script.py:339-353: rows by the rank of each site in exp_pi, columns by argsort(exp_a)"""
+    rpi = np.argsort(exp_pi_v)
+    idx = np.empty_like(rpi)
+    idx[rpi] = np.arange(len(rpi))
+    X_sum = X_sum[idx, :]
+    ra = np.argsort(exp_a_v)
+    out = np.zeros_like(X_sum)
+    for i, taxon in enumerate(ra):
+        out[:, i] = X_sum[:, taxon]
+    return out
+
+
+def _interval_maps(a_samples_per_chain, b_samples_per_chain, N, chains_selected, cell):
+    """common loop of script.py:306-448: X_sum_chain is divided by 1000 but never reset between chains"""
+    M = np.asarray(a_samples_per_chain[0]).shape[1]
+    j = np.arange(N)[:, None]
+    X_sum_chain = np.zeros((N, M))
+    X_sum = np.zeros((N, M))
+    for a_s, b_s in zip(a_samples_per_chain, b_samples_per_chain):
+        for a, b in zip(np.asarray(a_s), np.asarray(b_s)):
+            alive = (j >= a[None, :]) & (j <= b[None, :])   # closed at b (script.py:329), unlike the sampler's [a, b)
+            X_sum_chain += cell(alive)
+        X_sum_chain /= 1000
+        X_sum += X_sum_chain
+    return X_sum / chains_selected
+
+
+def alive_matrix(a_spc, b_spc, pi_spc, chains_selected: int) -> np.ndarray:
+    """plot_taxa_occurence_probability_matrix, script.py:306-353 (the returned matrix; no plot)"""
+    N = np.asarray(pi_spc[0]).shape[1]
+    X = _interval_maps(a_spc, b_spc, N, chains_selected, lambda alive: alive.astype(np.float64))
+    return _shuffle_like_script(X, exp_pi(pi_spc, chains_selected), exp_a(a_spc, chains_selected))
+
+
+def false_taxa_matrix(a_spc, b_spc, pi_spc, chains_selected: int) -> np.ndarray:
+    """plot_false_taxa_occurence_probability, script.py:356-403"""
+    N = np.asarray(pi_spc[0]).shape[1]
+    X = _interval_maps(a_spc, b_spc, N, chains_selected, lambda alive: (~alive).astype(np.float64))
+    return _shuffle_like_script(X, exp_pi(pi_spc, chains_selected), exp_a(a_spc, chains_selected))
+
+
+def false_ones_matrix(a_spc, b_spc, pi_spc, chains_selected: int, Xdata: np.ndarray) -> np.ndarray:
+    """plot_false_ones_probability, script.py:406-448: X[j][i] is read in FILE order while a, b are
+    positions -- the reference mixes the two index spaces; kept"""
+    N = np.asarray(pi_spc[0]).shape[1]
+    ones = np.asarray(Xdata) == 1
+    X = _interval_maps(a_spc, b_spc, N, chains_selected, lambda alive: (ones & ~alive).astype(np.float64))
+    return _shuffle_like_script(X, exp_pi(pi_spc, chains_selected), exp_a(a_spc, chains_selected))

@@ -63,6 +63,7 @@ SYMBOLS = [
     ("ser_run_chain_stats", C.c_int, [_vp, _dp, _dp, _dp, _i32p]),
     ("ser_run_chain_stats_device", C.c_int, [_vp, _vp]),
     ("ser_run_fetch_samples", C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _dp, _dp, _dp, _i32p]),
+    ("ser_run_alive_counts", C.c_int, [_vp, _i32p, C.c_int32, _i32p, _i32p]),
     ("ser_run_get_cd", C.c_int, [_vp, C.c_int32, _dp, _dp]),
     ("ser_run_fetch_cd_samples", C.c_int, [_vp, C.c_int32, _dp, _dp, _i32p]),
     ("ser_select_chains", C.c_int, [_dp, C.c_int32, C.c_int32, _i32p, _i32p, _dp, _dp]),
@@ -290,6 +291,13 @@ class Run:
                                             _p(a_sum, C.c_int32), _p(b_sum, C.c_int32), C.byref(n)))
         return dict(corr_num=corr, pi_sum=pi_sum, a_sum=a_sum, b_sum=b_sum, n_samples=n.value)
 
+    def alive_counts(self, chosen) -> tuple:
+        """int32 [k][N][M]: #{t: a_t(m) <= j <= b_t(m)} per chosen chain, and the number of samples T"""
+        chosen = np.ascontiguousarray(chosen, dtype=np.int32)
+        out, n = np.zeros((len(chosen), self.N, self.M), np.int32), C.c_int32()
+        _check(lib().ser_run_alive_counts(self._h, _p(chosen, C.c_int32), len(chosen), _p(out, C.c_int32), C.byref(n)))
+        return out, n.value
+
     def po_counts_device(self, chosen_ptr: int, k: int, counts_ptr: int):
         _check(lib().ser_run_po_counts_device(self._h, chosen_ptr, k, counts_ptr))
 
@@ -423,6 +431,54 @@ def compute_exp_a(batch: ChainBatch, chains, chains_selected: int, taxa: int | N
     """script.py:255-276; needs a batch created with the full sample store"""
     ps = batch.run.posterior_sums(np.asarray(chains, dtype=np.int32), with_ab=True)
     return carry_over_mean(list(ps["a_sum"]), chains_selected, keep_total=True, faithful=faithful)
+
+
+def _reorder_like_script(X_sum, exp_pi, exp_a):
+    """script.py:339-353: row r <- the row at site r's rank in exp_pi; column i <- taxon argsort(exp_a)[i]"""
+    rpi = np.argsort(exp_pi)
+    idx = np.empty_like(rpi)
+    idx[rpi] = np.arange(len(rpi))
+    return X_sum[idx, :][:, np.argsort(exp_a)]
+
+
+def _interval_map(batch: ChainBatch, chains, chains_selected: int, cell, faithful: bool):
+    alive, T = batch.run.alive_counts(np.asarray(chains, dtype=np.int32))
+    X_sum = carry_over_mean([cell(alive[c].astype(np.float64), T) for c in range(len(alive))], chains_selected,
+                            keep_total=True, faithful=faithful)
+    return _reorder_like_script(X_sum, compute_exp_pi(batch, chains, None, chains_selected, faithful),
+                                compute_exp_a(batch, chains, chains_selected, None, faithful))
+
+
+def taxa_occurence_probability_matrix(batch: ChainBatch, chains, chains_selected: int, sites: int | None = None,
+                                      taxa: int | None = None, faithful: bool = True):
+    """What plot_taxa_occurence_probability_matrix returns (script.py:306-353): X_ij = Pr(taxon i alive at
+    position j), rows ordered by E[pi], columns by E[a]; interval closed at b as the reference tests it;
+    counts on the GPU (ser_run_alive_counts).  Needs a batch with the full sample store."""
+    return _interval_map(batch, chains, chains_selected, lambda alive, T: alive, faithful)
+
+
+def false_taxa_occurence_probability_matrix(batch: ChainBatch, chains, chains_selected: int, sites: int | None = None,
+                                            taxa: int | None = None, faithful: bool = True):
+    """plot_false_taxa_occurence_probability's matrix (script.py:356-403): Pr(taxon i not alive at j)"""
+    return _interval_map(batch, chains, chains_selected, lambda alive, T: T - alive, faithful)
+
+
+def false_ones_probability_matrix(batch: ChainBatch, chains, chains_selected: int, dataset=None, sites: int | None = None,
+                                  taxa: int | None = None, faithful: bool = True):
+    """plot_false_ones_probability's matrix (script.py:406-448): Pr(X_ij = 1 is a false one).  The reference
+    indexes X by FILE row while a, b are positions; kept.  ``dataset``: path / Dataset, default the batch's own."""
+    ds = batch.run.ds if dataset is None else (dataset if isinstance(dataset, Dataset) else Dataset.read_txt(str(dataset)))
+    X = ds.arrays()[0].astype(np.float64)
+    return _interval_map(batch, chains, chains_selected, lambda alive, T: X * (T - alive), faithful)
+
+
+def new_data_matrix(batch: ChainBatch, chains, chains_selected: int, dataset=None, sites: int | None = None,
+                    taxa: int | None = None, faithful: bool = True):
+    """The matrix plot_new_data_matrix draws (script.py:279-303): occurrences with sites ordered by E[pi]
+    and taxa by E[a]."""
+    ds = batch.run.ds if dataset is None else (dataset if isinstance(dataset, Dataset) else Dataset.read_txt(str(dataset)))
+    return _reorder_like_script(ds.arrays()[0].astype(np.float64), compute_exp_pi(batch, chains, None, chains_selected, faithful),
+                                compute_exp_a(batch, chains, chains_selected, None, faithful))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1547,6 +1547,28 @@ __global__ void ser_posterior_kernel(const uint16_t *samp_pi, const uint16_t *sa
   atomicAdd((unsigned long long *)&corr_num[blockIdx.x], (unsigned long long)s);
 }
 
+/* alive[c][j][m] = #{t : a_t(m) <= j <= b_t(m)} over the stored samples of chosen chain c
+ * (script.py:321-329; closed at b, as the reference tests it).  One thread per taxon: +1 / -1
+ * marks at a and b+1 in its own column of the slab, then a running sum down the positions. */
+__global__ void ser_alive_kernel(const uint16_t *samp_a, const uint16_t *samp_b, int N, int M, int max_samples, int n_samples,
+                                 const int *chosen, int chain_offset, int n_local, int *alive)
+{
+  const int g = chosen[blockIdx.x];
+  if (g < chain_offset || g >= chain_offset + n_local) return;
+  const int m = blockIdx.y * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const size_t base = (size_t)(g - chain_offset) * max_samples;
+  int *col = alive + (size_t)blockIdx.x * N * M + m;
+  for (int j = 0; j < N; j++) col[(size_t)j * M] = 0;
+  for (int t = 0; t < n_samples; t++) {
+    const int a = samp_a[(base + t) * M + m], b = samp_b[(base + t) * M + m];
+    if (a < N) col[(size_t)a * M] += 1;
+    if (b + 1 < N) col[(size_t)(b + 1) * M] -= 1;
+  }
+  int acc = 0;
+  for (int j = 0; j < N; j++) { acc += col[(size_t)j * M]; col[(size_t)j * M] = acc; }
+}
+
 /* ------------------------------------------------------------------ micro-benchmarks */
 __global__ void mb_fp64_kernel(double *out, int iters)
 {
@@ -2202,6 +2224,32 @@ extern "C" int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32
   cudaFreeAsync(d_ch, run->stream); cudaFreeAsync(d_corr, run->stream); cudaFreeAsync(d_pi, run->stream);
   if (d_a) cudaFreeAsync(d_a, run->stream);
   if (d_b) cudaFreeAsync(d_b, run->stream);
+  if (n_samples) *n_samples = ns;
+  return SER_OK;
+}
+
+extern "C" int ser_run_alive_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *alive, int32_t *n_samples)
+{
+  if (!run || !chosen || !alive || k < 1) { ser_set_error("ser_run_alive_counts: bad argument"); return SER_E_ARG; }
+  if (run->cfg.store < SER_STORE_FULL) { ser_set_error("ser_run_alive_counts: needs SER_STORE_FULL (a, b samples)"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples, N = run->N, M = run->M;
+  const size_t cells = (size_t)k * N * M;
+  int *d_ch = nullptr, *d_alive = nullptr;
+  CUDA_TRY(POOL_ALLOC(&d_ch, k * sizeof(int)));
+  CUDA_TRY(POOL_ALLOC(&d_alive, cells * sizeof(int)));
+  CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_alive, alive, cells * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  mark_launch(run);
+  ser_alive_kernel<<<dim3(k, (M + 127) / 128), 128, 0, run->stream>>>(run->d_samp_a, run->d_samp_b, N, M, run->cfg.max_samples, ns, d_ch,
+                                                                     run->cfg.chain_offset, run->cfg.n_chains, d_alive);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(alive, d_alive, cells * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  cudaFreeAsync(d_ch, run->stream); cudaFreeAsync(d_alive, run->stream);
   if (n_samples) *n_samples = ns;
   return SER_OK;
 }

@@ -612,3 +612,40 @@ def test_manycd_cli(S, oracle_mod, tmp_path):
         assert f[3].split() == ["%.14f" % np.exp(v) for v in w.c_all] and f[5] == "%.14f" % w.loglik
     w = states[-1]
     assert (out / "taxa.csv").read_text().split("\n")[M] == "%d,%d,%.14f,%.14f" % (w.a[M - 1], w.b[M - 1], np.exp(w.c_all[M - 1]), np.exp(w.d_all[M - 1]))
+
+
+# ----------------------------------------------------------------------------- script.py's analysis, end to end
+def test_script_mirror_equals_unmodified_script_py(S):
+    """tests/golden/script_g10s10.npz holds what the UNMODIFIED script.py computed (choose_chains,
+    compute_exp_cd, compute_exp_ages, compute_pair_order_matrix, compute_exp_pi, compute_exp_a and the three
+    probability maps) over a Chains/ directory of 6 Philox chains; the GPU free-running mode
+    reproduces those chains, and the Python mirror over the device reductions must give the same numbers."""
+    g = np.load(os.path.join(GOLDEN, "script_g10s10.npz"))
+    seed, n_chains, burn, samp, k = (int(v) for v in g["meta"])
+    X, hard = load_hex_dataset("g10s10")
+    N, M = X.shape
+    batch = S.run_all_chains(S.Dataset.from_bits(X, hard), n_chains, burn, samp, seed=seed, store=S.STORE_FULL)
+    # exp_data.csv divides by the literal 1000 (mcmc.c:65); the mirror's E[-logL] divides by the samples taken
+    e = batch.stats()["e_negloglik"]
+    for i in range(n_chains):
+        assert e[i] == float(g["e_negloglik_%d" % i]), i
+    chosen = S.choose_chains(batch, k)
+    assert chosen == g["chosen"].tolist()
+    ec, ed = S.compute_exp_cd(batch, chosen, k)
+    # the reference sums the %.14f-printed values and divides by 1000 instead of the sample count
+    assert abs(ec * samp / 1000 - g["exp_cd"][0]) < 1e-13 and abs(ed * samp / 1000 - g["exp_cd"][1]) < 1e-13
+    assert abs(S.compute_exp_ages(batch, chosen, k, N) - float(g["exp_ages"])) < 1e-12
+    assert np.allclose(S.compute_pair_order_matrix(batch, chosen, k, N), g["po"], rtol=0, atol=1e-15)
+    assert np.allclose(S.compute_exp_pi(batch, chosen, N, k), g["exp_pi"], rtol=0, atol=1e-13)
+    assert np.allclose(S.compute_exp_a(batch, chosen, k, M), g["exp_a"], rtol=0, atol=1e-13)
+    assert np.allclose(S.taxa_occurence_probability_matrix(batch, chosen, k, N, M), g["alive"], rtol=0, atol=1e-15)
+    assert np.allclose(S.false_taxa_occurence_probability_matrix(batch, chosen, k, N, M), g["false_taxa"], rtol=0, atol=1e-15)
+    assert np.allclose(S.false_ones_probability_matrix(batch, chosen, k, None, N, M), g["false_ones"], rtol=0, atol=1e-15)
+    Y = S.new_data_matrix(batch, chosen, k)
+    assert Y.shape == (N, M) and Y.sum() == X.sum()
+    alive, T = batch.run.alive_counts(np.array([chosen[0], -1], np.int32))
+    fs = batch.run.fetch_samples(chosen[0])
+    j = np.arange(N)[None, :, None]
+    want = ((j >= fs["a"][:, None, :]) & (j <= fs["b"][:, None, :])).sum(axis=0)
+    assert T == samp and np.array_equal(alive[0], want) and not alive[1].any()
+    batch.run.close()

@@ -101,3 +101,32 @@ def test_philox_known_answers():
     assert out[0] == "6627e8d5 e169c58d bc57ac4c 9b00dbd8"
     assert out[1] == "408f276d 41c83b0e a20bc7c6 6d5451fd"
     assert out[2] == "d16cfe09 94fdcceb 5001e420 24126ea1"
+
+
+def test_script_restatements_match_unmodified_script_py(oracle_mod):
+    """The numpy restatements of script.py's cross-chain / posterior steps against outputs of the
+    UNMODIFIED script.py (tools/make_golden_script.py imported it here and ran its functions over a
+    Chains/ directory holding exactly these chains)."""
+    g = np.load(os.path.join(GOLDEN, "script_g10s10.npz"))
+    seed, n_chains, burn, samp, k = (int(v) for v in g["meta"])
+    X, hard = load_hex_dataset("g10s10")
+    res = []
+    for i in range(n_chains):
+        o = oracle_mod.Oracle(X, hard).source_philox(seed, i).detmath(True)
+        o.randomize()
+        res.append(o.run(burn, samp))
+    e = np.array([float("%.14f" % (r["sums"][0] / 1000)) for r in res])   # what exp_data.csv carries
+    chosen = oracle_mod.choose_chains(e, k)
+    assert chosen == g["chosen"].tolist()
+    pis, a_s, b_s = ([res[c][key] for c in chosen] for key in ("pi", "a", "b"))
+    ec, ed = oracle_mod.exp_cd([res[c]["c"] for c in chosen], [res[c]["d"] for c in chosen], k)
+    assert abs(ec - g["exp_cd"][0]) < 1e-15 and abs(ed - g["exp_cd"][1]) < 1e-15
+    assert abs(oracle_mod.exp_ages(pis, k) - float(g["exp_ages"])) < 1e-13
+    po = oracle_mod.pair_order_matrix([oracle_mod.pair_order_counts(p) for p in pis], k)
+    assert np.allclose(po, g["po"], rtol=0, atol=1e-15)
+    assert np.allclose(oracle_mod.exp_pi(pis, k), g["exp_pi"], rtol=0, atol=1e-13)
+    assert np.allclose(oracle_mod.exp_a(a_s, k), g["exp_a"], rtol=0, atol=1e-13)
+    assert np.allclose(oracle_mod.alive_matrix(a_s, b_s, pis, k), g["alive"], rtol=0, atol=1e-15)
+    assert np.allclose(oracle_mod.false_taxa_matrix(a_s, b_s, pis, k), g["false_taxa"], rtol=0, atol=1e-15)
+    assert np.allclose(oracle_mod.false_ones_matrix(a_s, b_s, pis, k, X), g["false_ones"], rtol=0, atol=1e-15)
+    assert g["alive"].max() > 0 and g["false_ones"].max() > 0
