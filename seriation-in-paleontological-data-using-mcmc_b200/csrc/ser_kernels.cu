@@ -30,6 +30,7 @@
 
 #define SER_PI_DRAWS 72 /* >= 4 + 5*13 = 69 draws a sweep's pi part can consume */
 #define SER_MAX_WARPS 32
+#define SER_MAX_GROUPS 8 /* column groups the item weights of a Gibbs step are evaluated in */
 
 /* ------------------------------------------------------------------ per-chain global state */
 struct ChainScalars {
@@ -79,6 +80,10 @@ struct KParams {
   int manycd;
   double *cd4;         /* [chain][4][Mpad]: c, log(1-e^c), d, log(1-e^d) per column */
   double *samp_cd_all; /* [chain][sample][2][M]: c, d per taxon (SER_STORE_FULL) */
+  /* the item weights of a Gibbs step are evaluated group by group of columns through a buffer of
+   * Ival doubles: a smaller buffer = more resident chains per SM */
+  int n_groups, Ival;
+  int grp_c[SER_MAX_GROUPS + 1], grp_e[SER_MAX_GROUPS + 1];
 };
 
 /* ------------------------------------------------------------------ shared-memory carve-up */
@@ -101,14 +106,14 @@ struct Smem {
   uint16_t *rpi, *tmp16, *perm16; /* N each */
 };
 
-__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C, int I, int manycd = 0)
+__host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C, int I, int manycd = 0, int Ival = -1)
 {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_ld = take(sizeof(double) * SER_PI_DRAWS);
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
   size_t o_H = take(sizeof(double) * (N + 2));
-  size_t o_val = take(sizeof(double) * (I + 1)), o_lm = take(sizeof(double) * C);
+  size_t o_val = take(sizeof(double) * ((Ival < 0 ? I : Ival) + 1)), o_lm = take(sizeof(double) * C);
   size_t o_wc = take(manycd ? sizeof(double) * 4 * C : 0), o_rd = take(manycd ? sizeof(double) * 2 * SER_MAX_WARPS : 0);
   size_t o_pos = take(sizeof(uint16_t) * (I + 1)), o_st = take(sizeof(uint16_t) * 4 * C);
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
-  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I);
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I, 0, p.Ival);
 
   const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
   const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
@@ -493,22 +498,27 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           sm.st4[4 * tid + 2] = (uint16_t)st.ocur; sm.st4[4 * tid + 3] = (uint16_t)st.kb;
         }
         __syncthreads();
-        for (int e = tid; e < p.I; e += C) {
-          const uint32_t ck = p.item_col[e];
-          const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
-          const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c); /* cur, bound | ocur, kb */
-          SerStep it;
-          it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
-          if (kk <= it.kb) {
-            it.nones = p.ones[c]; it.N = N; it.rev = step;
-            sm.val[e] = ser_item_weight(wt, it, sm.pos + (e - kk), kk, sm.lmax[c]);
+#pragma unroll 1
+        for (int g = 0; g < p.n_groups; g++) { /* columns grp_c[g]..grp_c[g+1] = items grp_e[g]..grp_e[g+1] */
+          const int e0 = p.grp_e[g], e1 = p.grp_e[g + 1];
+          if (g) __syncthreads(); /* the previous group's scans are done with val */
+          for (int e = e0 + tid; e < e1; e += C) {
+            const uint32_t ck = p.item_col[e];
+            const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
+            const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c); /* cur, bound | ocur, kb */
+            SerStep it;
+            it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
+            if (kk <= it.kb) {
+              it.nones = p.ones[c]; it.N = N; it.rev = step;
+              sm.val[e - e0] = ser_item_weight(wt, it, sm.pos + (e - kk), kk, sm.lmax[c]);
+            }
           }
-        }
-        __syncthreads();
-        if (is_taxon) {
-          const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + off_c, lmax, step == 0 ? ua : ub);
-          if (step == 0) { changed += pick != a; a = pick; }
-          else { changed += (N - pick) != b; b = N - pick; }
+          __syncthreads();
+          if (is_taxon && tid >= p.grp_c[g] && tid < p.grp_c[g + 1]) {
+            const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
+            if (step == 0) { changed += pick != a; a = pick; }
+            else { changed += (N - pick) != b; b = N - pick; }
+          }
         }
       }
       int t1 = 0, len = 0;
@@ -713,7 +723,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem sm;
-  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I, 1);
+  smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I, 1, p.Ival);
 
   const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
   const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
@@ -820,25 +830,30 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
               make_uint2((uint32_t)st.cur | ((uint32_t)st.bound << 16), (uint32_t)st.ocur | ((uint32_t)st.kb << 16));
         }
         __syncthreads(); /* also publishes the staged draws, wcol and the postings */
-        for (int e = tid; e < p.I; e += C) {
-          const uint32_t ck = p.item_col[e];
-          const int cix = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
-          const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cix);
-          SerStep it;
-          it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
-          if (kk <= it.kb) {
-            SerWeights w;
-            w.A = sm.wcol[4 * cix + 0]; w.g = sm.wcol[4 * cix + 1]; w.inv_g = sm.wcol[4 * cix + 2]; w.hs = sm.wcol[4 * cix + 3];
-            w.eps = p.eps; w.H = nullptr; w.hmax = N + 1;
-            it.nones = p.ones[cix]; it.N = N; it.rev = step;
-            sm.val[e] = ser_item_weight(w, it, sm.pos + (e - kk), kk, sm.lmax[cix]);
+#pragma unroll 1
+        for (int g = 0; g < p.n_groups; g++) {
+          const int e0 = p.grp_e[g], e1 = p.grp_e[g + 1];
+          if (g) __syncthreads();
+          for (int e = e0 + tid; e < e1; e += C) {
+            const uint32_t ck = p.item_col[e];
+            const int cix = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
+            const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cix);
+            SerStep it;
+            it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
+            if (kk <= it.kb) {
+              SerWeights w;
+              w.A = sm.wcol[4 * cix + 0]; w.g = sm.wcol[4 * cix + 1]; w.inv_g = sm.wcol[4 * cix + 2]; w.hs = sm.wcol[4 * cix + 3];
+              w.eps = p.eps; w.H = nullptr; w.hmax = N + 1;
+              it.nones = p.ones[cix]; it.N = N; it.rev = step;
+              sm.val[e - e0] = ser_item_weight(w, it, sm.pos + (e - kk), kk, sm.lmax[cix]);
+            }
           }
-        }
-        __syncthreads();
-        if (is_taxon) {
-          const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + off_c, lmax, step == 0 ? ua : ub);
-          if (step == 0) { changed += pick != a; a = pick; }
-          else { changed += (N - pick) != b; b = N - pick; }
+          __syncthreads();
+          if (is_taxon && tid >= p.grp_c[g] && tid < p.grp_c[g + 1]) {
+            const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
+            if (step == 0) { changed += pick != a; a = pick; }
+            else { changed += (N - pick) != b; b = N - pick; }
+          }
         }
       }
       const bool exact = p.sampling && s == p.sweeps_per_call - 1;
@@ -1678,6 +1693,43 @@ static void mark_launch(ser_run *run)
   run->launches++;
 }
 
+/* Column groups of the Gibbs step: the item weights of a step go through a buffer of Ival doubles,
+ * one group of columns at a time.  Fewer, larger groups = fewer barriers; a smaller buffer = more
+ * resident chains per SM (measured on B200: +15-20 % per extra resident CTA, -4 % per extra group).
+ * Take the fewest groups that reach the best residency; SER_SWEEP_GROUPS forces a count. */
+template <typename K>
+static int choose_groups(KParams &kp, const std::vector<int> &off, int M, int N, int W, int C, int manycd, K kernel, size_t *smem_out)
+{
+  int best_occ = 0, force = 0;
+  if (const char *v = getenv("SER_SWEEP_GROUPS")) force = std::max(1, std::min(SER_MAX_GROUPS, atoi(v)));
+  for (int G = 1; G <= SER_MAX_GROUPS; G++) {
+    if (force && G != force) continue;
+    int gc[SER_MAX_GROUPS + 1], ge[SER_MAX_GROUPS + 1], ng = 0, ival = 0;
+    gc[0] = 0; ge[0] = 0;
+    for (int c = 0; c < M && ng < G; c++) /* close a group at the column where its share of the items is reached */
+      if (c + 1 == M || off[c + 1] >= (long long)kp.I * (ng + 1) / G) {
+        ng++; gc[ng] = c + 1; ge[ng] = off[c + 1];
+        ival = std::max(ival, ge[ng] - ge[ng - 1]);
+      }
+    const size_t sz = smem_layout(nullptr, nullptr, N, W, C, kp.I, manycd, ival);
+    if (sz > 227 * 1024) continue;
+    int occ = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, C, sz) != cudaSuccess) {
+      ser_set_error("ser_run_create: occupancy query failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return SER_E_CUDA;
+    }
+    if (occ > best_occ) {
+      best_occ = occ;
+      kp.n_groups = ng; kp.Ival = ival;
+      memcpy(kp.grp_c, gc, sizeof(gc)); memcpy(kp.grp_e, ge, sizeof(ge));
+      *smem_out = sz;
+    }
+  }
+  if (!best_occ) { ser_set_error("ser_run_create: the chain state does not fit shared memory"); return SER_E_ARG; }
+  return SER_OK;
+}
+
 extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, ser_run **out)
 {
   if (!ds || !cfg || !out) { ser_set_error("ser_run_create: null argument"); return SER_E_ARG; }
@@ -1791,6 +1843,12 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   CUDA_TRY(cudaFuncSetAttribute(ser_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_init));
   if (cfg->manycd) {
     run->smem_many = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I, 1);
+    /* the per-taxon kernel needs its 80 registers (2.7 M vs 2.5 M sweeps/s on g2s2 with 64): size the
+     * groups for the instantiation that will run */
+    if (!run->big && run->smem_many <= 227 * 1024 &&
+        (run->C <= 384 ? choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel_manycd<384, 2>, &run->smem_many)
+                       : choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel_manycd<1024, 1>, &run->smem_many)))
+      return SER_E_ARG;
     if (run->big || run->smem_many > 227 * 1024) {
       ser_set_error("ser_run_create: manycd=1 needs one thread per taxon and %zu B of shared memory per chain (M <= 1023)", run->smem_many);
       return SER_E_ARG;
@@ -1808,6 +1866,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     else {
       /* two register budgets: 64 regs (any block size) and 85 regs (blocks <= 384 threads, two of
        * them resident); take the one with more resident CTAs, the roomier one on a tie */
+      if (!cfg->manycd && choose_groups(kp, off, M, N, run->W, run->C, 0, ser_sweep_kernel<1024, 1>, &run->smem_sweep)) return SER_E_ARG;
       CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
       CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
       int occ64 = 0, occ85 = 0;
