@@ -118,6 +118,9 @@ int ser_run_get_state(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32
 int ser_run_get_counters(ser_run *run, int32_t chain, int64_t out[8]);
 /* mcmc_consistent on every local chain, on device; *n_bad = number of inconsistent chains */
 int ser_run_check(ser_run *run, int32_t *n_bad);
+/* what ser_run_check found for one chain: bit 1 tape exhausted, 2 a/b out of range, 4 pi not a permutation,
+ * 8 hard sites out of order, 16 totals / log-likelihood do not match a recount (mcmc.c:999-1094) */
+int ser_run_get_flags(ser_run *run, int32_t chain, int32_t *flags);
 
 /* per local chain: mean(-loglik), mean(exp c), mean(exp d) over the samples emitted so far;
  * host arrays of n_chains doubles (any may be NULL).  n_samples receives the divisor. */

@@ -64,6 +64,7 @@ SYMBOLS = [
     ("ser_run_chain_stats_device", C.c_int, [_vp, _vp]),
     ("ser_run_fetch_samples", C.c_int, [_vp, C.c_int32, _i32p, _i32p, _i32p, _dp, _dp, _dp, _i32p]),
     ("ser_run_alive_counts", C.c_int, [_vp, _i32p, C.c_int32, _i32p, _i32p]),
+    ("ser_run_get_flags", C.c_int, [_vp, C.c_int32, _i32p]),
     ("ser_run_get_cd", C.c_int, [_vp, C.c_int32, _dp, _dp]),
     ("ser_run_fetch_cd_samples", C.c_int, [_vp, C.c_int32, _dp, _dp, _i32p]),
     ("ser_select_chains", C.c_int, [_dp, C.c_int32, C.c_int32, _i32p, _i32p, _dp, _dp]),
@@ -244,6 +245,11 @@ class Run:
         if rc not in (0, -7):
             _check(rc)
         return bad.value
+
+    def flags(self, chain: int) -> int:
+        f = C.c_int32()
+        _check(lib().ser_run_get_flags(self._h, chain, C.byref(f)))
+        return f.value
 
     def chain_stats(self):
         e, c, d = (np.empty(self.n_chains) for _ in range(3))

@@ -39,7 +39,7 @@
 #define SER_FFS(x) __ffs((int)(x))
 SER_HD uint32_t ser_funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }
 SER_HD double ser_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
-SER_HD double ser_fmax(double a, double b) { return fmax(a, b); }
+SER_HD double ser_fmax(double a, double b) { return a > b ? a : b; } /* no NaNs here; fmax() costs twice the instructions */
 #else
 #define SER_POPC(x) __builtin_popcount((x))
 #define SER_FFS(x) __builtin_ffs((int)(x))
@@ -421,14 +421,12 @@ SER_HD int ser_run_pick(const SerWeights &wt, int n, double le, double s, double
   return nf + lo;
 }
 
-/* the taxon's own part: val[0..kb] holds the item weights; turns them into cumulative sums,
- * inverts the CDF (mcmc_randompick) and returns the picked candidate (logical index) */
-SER_HD int ser_step_pick(const SerWeights &wt, const SerStep &st, const uint16_t *pos, double *val, double lmax,
-                         double U)
+/* val[0..kb] already holds the CUMULATIVE item weights: inverts the CDF (mcmc_randompick) and
+ * returns the picked candidate (logical index) */
+SER_HD int ser_step_pick_scanned(const SerWeights &wt, const SerStep &st, const uint16_t *pos, const double *val, double lmax,
+                                 double U)
 {
-  double S = 0.0;
-  for (int kk = 0; kk <= st.kb; kk++) { S = SER_ADD(S, val[kk]); val[kk] = S; }
-  const double target = SER_MUL(U, S);
+  const double target = SER_MUL(U, val[st.kb]);
   int lo = 0, hi = st.kb; /* first item whose cumulative weight reaches the target */
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -437,6 +435,15 @@ SER_HD int ser_step_pick(const SerWeights &wt, const SerStep &st, const uint16_t
   int q, n;
   const double le = SER_SUB(ser_item_eval(wt, st, pos, lo, &q, &n), lmax);
   return q - n + 1 + ser_run_pick(wt, n, le, lo ? val[lo - 1] : 0.0, target);
+}
+
+/* the taxon's own part: val[0..kb] holds the item weights; turns them into cumulative sums and picks */
+SER_HD int ser_step_pick(const SerWeights &wt, const SerStep &st, const uint16_t *pos, double *val, double lmax,
+                         double U)
+{
+  double S = 0.0;
+  for (int kk = 0; kk <= st.kb; kk++) { S = SER_ADD(S, val[kk]); val[kk] = S; }
+  return ser_step_pick_scanned(wt, st, pos, val, lmax, U);
 }
 
 /* ------------------------------------------------------------------ pi proposals */

@@ -59,8 +59,8 @@ struct KParams {
   int Cs;                   /* column stride of the scratch bit matrix (>= M+1) */
   uint32_t *gV;             /* [slot][W][Cs] */
   uint16_t *gpre;           /* [slot][W+1][Cs] */
-  uint16_t *gpos;           /* [slot][I+1] */
-  double *gval;             /* [slot][I+1] */
+  const int *bgrp;          /* large-shape column groups: [g] = {first column, first item}, big_ng + 1 entries */
+  int big_ng, big_icap, big_gcap;
   double *gterms;           /* [slot][M] */
   int n_chains;
   uint16_t *ab;        /* [chain][2][Mpad] */
@@ -1004,25 +1004,47 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
   }
 }
 
+/* phase timing of the large-shape kernel (debug builds: NVCC_EXTRA=-DSER_PHASE_TIMING): thread 0 of every
+ * CTA adds the cycles between marks; ser_debug_phase_cycles() reads and clears the totals */
+#ifdef SER_PHASE_TIMING
+__device__ unsigned long long ser_phase_cycles[8];
+#define PHASE_T0() long long ph_t = clock64()
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long ph_n = clock64(); atomicAdd(&ser_phase_cycles[i], (unsigned long long)(ph_n - ph_t)); ph_t = ph_n; } } while (0)
+extern "C" int ser_debug_phase_cycles(unsigned long long out[8])
+{
+  unsigned long long zero[8] = {0};
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out, ser_phase_cycles, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(ser_phase_cycles, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define PHASE_T0() do { } while (0)
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 /* ------------------------------------------------------------------ the sweep kernel, large shapes
  * Same algorithm and building blocks as ser_sweep_kernel, for matrices whose bit columns, prefix
  * tables and item buffers exceed shared memory (e.g. 1024 sites x 4096 taxa: 0.7 MB + 0.3 MB +
  * 3.2 MB per chain).  A CTA owns a slot of L2-resident global scratch and walks over chains
  * (persistent grid); every thread owns the columns tid, tid+C, ...; a/b live in shared memory. */
 struct BigSmem {
-  double *draws_pi, *logdraw, *draws_cd, *H, *lmax;
+  double *draws_pi, *logdraw, *draws_cd, *H;
+  double *lmax; /* gcap: per column of the running group */
+  double *val;  /* icap: item weights / cumulative weights of the running group */
   int *red;
-  uint16_t *a16, *b16, *st4, *hp, *rpi, *tmp16, *perm16;
+  uint16_t *a16, *b16, *hp, *rpi, *tmp16, *perm16;
+  uint16_t *st4; /* 4 * gcap */
+  uint16_t *pos; /* icap: postings of the running group's columns */
 };
-__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M)
+__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap)
 {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_dp = take(8 * SER_PI_DRAWS), o_ld = take(8 * SER_PI_DRAWS), o_dc = take(8 * 8), o_H = take(8 * (size_t)(N + 2));
-  size_t o_lm = take(8 * (size_t)M), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
-  size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)M), o_hp = take(2 * (size_t)(N + 1));
-  size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N);
+  size_t o_lm = take(8 * (size_t)gcap), o_val = take(8 * (size_t)icap), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
+  size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)gcap), o_hp = take(2 * (size_t)(N + 1));
+  size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
   if (s) {
+    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos);
     s->draws_pi = (double *)(base + o_dp); s->logdraw = (double *)(base + o_ld); s->draws_cd = (double *)(base + o_dc);
     s->H = (double *)(base + o_H); s->lmax = (double *)(base + o_lm); s->red = (int *)(base + o_r);
     s->a16 = (uint16_t *)(base + o_a); s->b16 = (uint16_t *)(base + o_b); s->st4 = (uint16_t *)(base + o_st);
@@ -1072,12 +1094,10 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BigSmem sm;
-  big_layout(&sm, smem_raw, p.N, p.M);
+  big_layout(&sm, smem_raw, p.N, p.M, p.big_icap, p.big_gcap);
   const int tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, W = p.W, Cs = p.Cs;
   uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
   uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
-  uint16_t *POS = p.gpos + (size_t)blockIdx.x * (p.I + 1);
-  double *VAL = p.gval + (size_t)blockIdx.x * (p.I + 1);
   double *TERMS = p.gterms + (size_t)blockIdx.x * M;
 
   for (int chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
@@ -1122,6 +1142,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
       for (int s = 0; s < p.sweeps_per_call; s++) {
         /* ================= stage this sweep's draws ================= */
         __syncthreads();
+        PHASE_T0();
         if (p.mode == SER_MODE_REPLAY) {
           const long long need = sc.cursor + 6 + 2 * (long long)M;
           if (need > tape_len) { sc.flags |= 1; break; }
@@ -1166,48 +1187,121 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         wt.hmax = ser_hmax(wt.g, N);
         for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
 
-        /* ================= a/b Gibbs, item formulation ================= */
-        for (int c = tid; c < M; c += C) ser_expand_ones(V + c, Cs, W, POS + p.off[c]);
+        /* ================= a/b Gibbs, item formulation, one column group at a time =================
+         * The group's postings and item weights live in shared memory (icap items), so the per-column
+         * loops run at shared-memory latency.  A column is served by `lpc` adjacent lanes (1..8, as many as
+         * the block can spare for the group), which split its loops: the maximum is a lane-strided partial
+         * maximum + shuffle, the cumulative weights are a per-lane serial sum over a contiguous chunk + a
+         * shuffle scan of the lane totals.  Per group: postings; then for the a-step and the b-step:
+         * geometry + maximum, run weights (dense over the group's items), scan + inverse CDF. */
         int changed = 0;
 #pragma unroll 1
-        for (int step = 0; step < 2; step++) {
-          for (int c = tid; c < M; c += C) {
-            const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
-                                         : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
-            sm.lmax[c] = ser_step_lmax(wt, st, POS + p.off[c]);
-            sm.st4[4 * c + 0] = (uint16_t)st.cur; sm.st4[4 * c + 1] = (uint16_t)st.bound;
-            sm.st4[4 * c + 2] = (uint16_t)st.ocur; sm.st4[4 * c + 3] = (uint16_t)st.kb;
-          }
-          __syncthreads(); /* also publishes H and POS */
-          for (int e = tid; e < p.I; e += C) {
-            const uint32_t ck = p.item_col[e];
-            const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
-            const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c);
-            SerStep it;
-            it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
-            if (kk <= it.kb) {
-              it.nones = p.ones[c]; it.N = N; it.rev = step;
-              VAL[e] = ser_item_weight(wt, it, POS + (e - kk), kk, sm.lmax[c]);
+        for (int g = 0; g < p.big_ng; g++) {
+          const int c0 = p.bgrp[2 * g], e0 = p.bgrp[2 * g + 1], c1 = p.bgrp[2 * g + 2], e1 = p.bgrp[2 * g + 3], nc = c1 - c0;
+          int lpc = 1, lsh = 0;
+          while (lpc < 8 && nc * lpc * 2 <= C) { lpc <<= 1; lsh++; }
+          const int units = nc << lsh, sub = tid & (lpc - 1);
+          __syncthreads(); /* previous group is done with pos / val; first group: publishes H */
+          PHASE_MARK(0);
+          { /* postings: a unit = (column, run of wq words); the prefix table gives the first slot */
+            const int wq = (W + lpc - 1) >> lsh;
+            for (int u = tid; u < units; u += C) {
+              const int c = c0 + (u >> lsh), w0 = sub * wq, w1 = min(W, w0 + wq);
+              if (w0 < w1) {
+                uint16_t *out = sm.pos + (p.off[c] - e0) + PRE[w0 * Cs + c];
+                for (int wb = w0; wb < w1; wb += 8) {
+                  uint32_t vv[8];
+#pragma unroll
+                  for (int k = 0; k < 8; k++) vv[k] = wb + k < w1 ? V[(wb + k) * Cs + c] : 0u;
+#pragma unroll
+                  for (int k = 0; k < 8; k++) {
+                    uint32_t v = vv[k];
+                    while (v) { *out++ = (uint16_t)(32 * (wb + k) + SER_FFS(v) - 1); v &= v - 1u; }
+                  }
+                }
+              }
             }
           }
           __syncthreads();
-          for (int c = tid; c < M; c += C) {
-            SerStep st;
-            st.cur = sm.st4[4 * c + 0]; st.bound = sm.st4[4 * c + 1]; st.ocur = sm.st4[4 * c + 2]; st.kb = sm.st4[4 * c + 3];
-            st.nones = p.off[c + 1] - p.off[c] - 1; st.N = N; st.rev = step;
-            const int taxon = p.order[c];
-            double u;
-            if (p.mode == SER_MODE_REPLAY) u = tape[sc.cursor + 6 + 2 * taxon + step];
-            else {
-              uint32_t o[4];
-              ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
-              u = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
+          PHASE_MARK(1);
+#pragma unroll 1
+          for (int step = 0; step < 2; step++) {
+            for (int ub = 0; ub < units; ub += C) { /* warp-uniform trip count: the shuffles need every lane */
+              const int u = ub + tid;
+              const bool live = u < units;
+              const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
+              const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
+                                           : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
+              const uint16_t *pos = sm.pos + (p.off[c] - e0);
+              double lm = -1.0e300;
+              if (live)
+                for (int kk = sub; kk <= st.kb; kk += lpc) {
+                  int q, n;
+                  lm = ser_fmax(lm, ser_item_eval(wt, st, pos, kk, &q, &n));
+                }
+              for (int o = lpc >> 1; o > 0; o >>= 1) lm = ser_fmax(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+              if (live && sub == 0) {
+                sm.lmax[cl] = lm;
+                *reinterpret_cast<uint2 *>(sm.st4 + 4 * cl) =
+                    make_uint2((uint32_t)st.cur | ((uint32_t)st.bound << 16), (uint32_t)st.ocur | ((uint32_t)st.kb << 16));
+              }
             }
-            const int pick = ser_step_pick(wt, st, POS + p.off[c], VAL + p.off[c], sm.lmax[c], u);
-            if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
-            else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
+            __syncthreads();
+            PHASE_MARK(2);
+            for (int e = e0 + tid; e < e1; e += C) {
+              const uint32_t ck = p.item_col[e];
+              const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu), cl = c - c0;
+              const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
+              SerStep it;
+              it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
+              if (kk <= it.kb) {
+                it.nones = p.ones[c]; it.N = N; it.rev = step;
+                sm.val[e - e0] = ser_item_weight(wt, it, sm.pos + (e - kk - e0), kk, sm.lmax[cl]);
+              }
+            }
+            __syncthreads();
+            PHASE_MARK(3);
+            for (int ub = 0; ub < units; ub += C) {
+              const int u = ub + tid;
+              const bool live = u < units;
+              const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
+              const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
+              SerStep st;
+              st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = (int)(g4.y >> 16);
+              st.nones = p.ones[c]; st.N = N; st.rev = step;
+              double *val = sm.val + (p.off[c] - e0);
+              /* cumulative weights: lane `sub` owns items [k0, k1) */
+              const int chunk = (st.kb + lpc) >> lsh, k0 = min(st.kb + 1, sub * chunk), k1 = min(st.kb + 1, k0 + chunk);
+              double tot = 0.0;
+              if (live) for (int kk = k0; kk < k1; kk++) tot = SER_ADD(tot, val[kk]);
+              double incl = tot;
+              for (int o = 1; o < lpc; o <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (sub >= o) incl = SER_ADD(t, incl);
+              }
+              double S = __shfl_up_sync(0xffffffffu, incl, 1);
+              if (sub == 0) S = 0.0;
+              if (live) for (int kk = k0; kk < k1; kk++) { S = SER_ADD(S, val[kk]); val[kk] = S; }
+              __syncwarp();
+              if (live && sub == 0) {
+                const int taxon = p.order[c];
+                double uu;
+                if (p.mode == SER_MODE_REPLAY) uu = tape[sc.cursor + 6 + 2 * taxon + step];
+                else {
+                  uint32_t o[4];
+                  ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+                  uu = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
+                }
+                const int pick = ser_step_pick_scanned(wt, st, sm.pos + (p.off[c] - e0), val, sm.lmax[cl], uu);
+                if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
+                else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
+              }
+              __syncwarp(); /* the b-step's geometry is computed by the same lanes of the same warp */
+            }
+            PHASE_MARK(4);
           }
         }
+        __syncthreads();
         const bool exact = p.sampling && s == p.sweeps_per_call - 1;
         {
           int t1 = 0, len = 0, T1, LEN, CH;
@@ -1230,6 +1324,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           }
         }
 
+        PHASE_MARK(5);
         /* ================= 16 proposals for pi ================= */
         ps.k = 0;
         for (int prop = 0; prop < 16; prop++) {
@@ -1326,6 +1421,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         if (p.mode == SER_MODE_REPLAY) sc.cursor += 6 + 2 * (long long)M + ps.k;
         else sc.sweep++;
         sc.counters[7]++;
+        PHASE_MARK(6);
       }
       if (sc.flags & 1) break;
 
@@ -1434,7 +1530,9 @@ __global__ void ser_check_kernel(KParams p, int *bad_count)
     double ll;
     totals_from(p, wt, T1, LEN, &t0a, &f0a, &t1a, &f1a, &ll);
     if (p.manycd) { ll = 0.0; for (int w = 0; w < (C + 31) / 32; w++) ll += s_ll[w]; }
-    if (t0a != sc.t0a || f0a != sc.f0a || t1a != sc.t1a || f1a != sc.f1a || fabs(ll - sc.loglik) > 1e-8) s_flags |= 16;
+    /* the reference allows 1e-8 absolute (mcmc.c:1084); on large matrices |loglik| ~ 1e6 and the taxon-order
+     * sum of a sampled sweep differs from this recount's closed form by more than that in the last bits */
+    if (t0a != sc.t0a || f0a != sc.f0a || t1a != sc.t1a || f1a != sc.f1a || fabs(ll - sc.loglik) > 1e-8 + 1e-12 * fabs(ll)) s_flags |= 16;
     const int fl = s_flags | (sc.flags & 1);
     if (fl) atomicAdd(bad_count, 1);
     p.scal[chain].flags = (sc.flags & 1) | fl;
@@ -1659,8 +1757,9 @@ struct ser_run {
   size_t smem_sweep, smem_init, smem_small, smem_big;
   int Caux, big, big_threads, big_slots, variant, variant_many;
   uint32_t *d_gV;
-  uint16_t *d_gpre, *d_gpos;
-  double *d_gval, *d_gterms;
+  uint16_t *d_gpre;
+  int *d_bgrp;
+  double *d_gterms;
   int initialized, have_tapes;
 };
 
@@ -1755,6 +1854,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   run->big_threads = 1024;
   if (const char *fb = getenv("SER_FORCE_BIG")) { run->big = 1; if (atoi(fb) >= 32) run->big_threads = std::min(1024, atoi(fb) / 32 * 32); }
   if (run->C > 1024) { run->big = 1; run->C = 1024; }
+  if (const char *bt = getenv("SER_BIG_THREADS")) { if (atoi(bt) >= 32) run->big_threads = std::min(1024, atoi(bt) / 32 * 32); }
   CUDA_TRY(cudaSetDevice(cfg->device));
   CUDA_TRY(cudaStreamCreateWithFlags(&run->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&run->ev_start));
@@ -1877,7 +1977,32 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     }
   }
   if (run->big) {
-    run->smem_big = big_layout(nullptr, nullptr, N, M);
+    /* column groups of the Gibbs phase: as many items as the shared-memory budget holds
+     * (SER_BIG_SMEM_KB, default 200), at most 1024 columns, never splitting a column */
+    int budget_kb = 200;
+    if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(227, atoi(v)));
+    const int gcap = std::min(M, 1024);
+    const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
+    long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32;
+    icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);
+    if (icap < N + 1) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain before any item", fixed); return SER_E_ARG; }
+    std::vector<int> bgrp;
+    {
+      int c0 = 0;
+      while (c0 < M) {
+        int c1 = c0;
+        while (c1 < M && c1 - c0 < gcap && off[c1 + 1] - off[c0] <= icap) c1++;
+        bgrp.push_back(c0); bgrp.push_back(off[c0]);
+        c0 = c1;
+      }
+      bgrp.push_back(M); bgrp.push_back(off[M]);
+    }
+    kp.big_ng = (int)bgrp.size() / 2 - 1; kp.big_icap = (int)icap; kp.big_gcap = gcap;
+    CUDA_TRY(POOL_ALLOC(&run->d_bgrp, bgrp.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(run->d_bgrp, bgrp.data(), bgrp.size() * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+    CUDA_TRY(cudaStreamSynchronize(run->stream));
+    kp.bgrp = run->d_bgrp;
+    run->smem_big = big_layout(nullptr, nullptr, N, M, (int)icap, gcap);
     if (run->smem_big > 227 * 1024) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_big); return SER_E_ARG; }
     CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_big));
     int per_sm = 1, n_sm = 1;
@@ -1888,10 +2013,8 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     const size_t sl = (size_t)run->big_slots;
     CUDA_TRY(POOL_ALLOC(&run->d_gV, sl * run->W * kp.Cs * sizeof(uint32_t)));
     CUDA_TRY(POOL_ALLOC(&run->d_gpre, sl * (run->W + 1) * kp.Cs * sizeof(uint16_t)));
-    CUDA_TRY(POOL_ALLOC(&run->d_gpos, sl * (kp.I + 1) * sizeof(uint16_t)));
-    CUDA_TRY(POOL_ALLOC(&run->d_gval, sl * (kp.I + 1) * sizeof(double)));
     CUDA_TRY(POOL_ALLOC(&run->d_gterms, sl * M * sizeof(double)));
-    kp.gV = run->d_gV; kp.gpre = run->d_gpre; kp.gpos = run->d_gpos; kp.gval = run->d_gval; kp.gterms = run->d_gterms;
+    kp.gV = run->d_gV; kp.gpre = run->d_gpre; kp.gterms = run->d_gterms;
   }
   kp.n_chains = cfg->n_chains;
   *out = run;
@@ -1904,7 +2027,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   cudaSetDevice(run->cfg.device);
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
-                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_gpos, run->d_gval, run->d_gterms};
+                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp, run->d_gterms};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   cudaStreamSynchronize(run->stream);
   cudaEventDestroy(run->ev_start); cudaEventDestroy(run->ev_stop);
@@ -2054,6 +2177,18 @@ extern "C" int ser_run_get_counters(ser_run *run, int32_t chain, int64_t out[8])
   CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
   CUDA_TRY(cudaStreamSynchronize(run->stream));
   for (int i = 0; i < 8; i++) out[i] = sc.counters[i];
+  return SER_OK;
+}
+
+/* flags of one chain after ser_run_check: 1 tape exhausted, 2 a/b range, 4 permutation, 8 hard-site order, 16 totals / loglik */
+extern "C" int ser_run_get_flags(ser_run *run, int32_t chain, int32_t *flags)
+{
+  if (!chain_ok(run, chain) || !flags) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  ChainScalars sc;
+  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaStreamSynchronize(run->stream));
+  *flags = sc.flags;
   return SER_OK;
 }
 

@@ -1,0 +1,13 @@
+import sys, ctypes as C; sys.path.insert(0,'.')
+import seriation_b200 as S
+ds = S.Dataset.synthetic(1024, 4096, 16)
+run = S.Run(ds, 296, seed=1, store=S.STORE_PI, max_samples=4)
+run.init().advance(1, False).sync()
+out = (C.c_ulonglong * 8)()
+S.lib().ser_debug_phase_cycles(out)
+run.advance(2, True).sync(); ms = run.elapsed_ms(reset=True)
+S.lib().ser_debug_phase_cycles(out)
+tot = sum(out)
+names = ["stage+H", "E postings", "S+L", "D dense", "PT pick", "totals", "pi", "-"]
+print("sweeps/s %.0f" % (296 * 20 / (run.elapsed_ms() * 1e-3 + 1e-9)) if False else "", "cycles/sweep/CTA %.0f" % (tot / (296 * 20)))
+for n, v in zip(names, out): print("%-12s %5.1f%%  %.0f cyc/sweep" % (n, 100.0 * v / tot, v / (296 * 20)))
