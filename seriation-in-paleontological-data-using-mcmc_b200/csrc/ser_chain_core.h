@@ -269,30 +269,53 @@ SER_HD double ser_i2d(int k)
   return SER_SUB(ser_u2d(0x4330000000000000ull | (uint64_t)((uint32_t)k ^ 0x80000000u)), 4503601774854144.0);
 }
 
-/* exp(x) for x <= ~0 (weights relative to the maximum); 0 below -708.  FMA Horner, ~1 ulp. */
+/* exp(x) for x <= ~0 (weights relative to the maximum); 0 below -708.  FMA Horner, ~1 ulp.
+ * On the device the coefficients sit in the constant bank, so every FMA takes its constant as an
+ * operand; as literals each costs two extra instructions to materialise (this is the hot loop). */
+#if defined(__CUDACC__)
+__constant__ double ser_expw_c[14] = {
+#else
+static const double ser_expw_c[14] = {
+#endif
+    1.4426950408889634074,       /* 0: log2(e) */
+    -6.93147180369123816490e-01, /* 1: -ln2 hi */
+    -1.90821492927058770002e-10, /* 2: -ln2 lo */
+    1.6059043836821613e-10,      /* 3: 1/13! */
+    2.08767569878681e-09,        /* 4: 1/12! */
+    2.505210838544172e-08,       /* 5: 1/11! */
+    2.755731922398589e-07,       /* 6: 1/10! */
+    2.7557319223985893e-06,      /* 7: 1/9!  */
+    2.48015873015873e-05,        /* 8: 1/8!  */
+    1.984126984126984e-04,       /* 9: 1/7!  */
+    1.388888888888889e-03,       /* 10: 1/6! */
+    8.333333333333333e-03,       /* 11: 1/5! */
+    4.1666666666666664e-02,      /* 12: 1/4! */
+    1.6666666666666666e-01};     /* 13: 1/3! */
+
 SER_HD double ser_exp_weight(double x)
 {
   if (!(x > -708.0)) return 0.0;
-  const double t = ser_fma(x, 1.4426950408889634074, 6755399441055744.0); /* round to nearest int */
+  const double *k = ser_expw_c;
+  const double t = ser_fma(x, k[0], 6755399441055744.0); /* round to nearest int */
   const double kd = t - 6755399441055744.0;
-  double r = ser_fma(kd, -6.93147180369123816490e-01, x);
-  r = ser_fma(kd, -1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;                 /* 1/13! */
-  p = ser_fma(p, r, 2.08767569878681e-09);            /* 1/12! */
-  p = ser_fma(p, r, 2.505210838544172e-08);           /* 1/11! */
-  p = ser_fma(p, r, 2.755731922398589e-07);           /* 1/10! */
-  p = ser_fma(p, r, 2.7557319223985893e-06);          /* 1/9!  */
-  p = ser_fma(p, r, 2.48015873015873e-05);            /* 1/8!  */
-  p = ser_fma(p, r, 1.984126984126984e-04);           /* 1/7!  */
-  p = ser_fma(p, r, 1.388888888888889e-03);           /* 1/6!  */
-  p = ser_fma(p, r, 8.333333333333333e-03);           /* 1/5!  */
-  p = ser_fma(p, r, 4.1666666666666664e-02);          /* 1/4!  */
-  p = ser_fma(p, r, 1.6666666666666666e-01);          /* 1/3!  */
+  double r = ser_fma(kd, k[1], x);
+  r = ser_fma(kd, k[2], r);
+  double p = k[3];
+  p = ser_fma(p, r, k[4]);
+  p = ser_fma(p, r, k[5]);
+  p = ser_fma(p, r, k[6]);
+  p = ser_fma(p, r, k[7]);
+  p = ser_fma(p, r, k[8]);
+  p = ser_fma(p, r, k[9]);
+  p = ser_fma(p, r, k[10]);
+  p = ser_fma(p, r, k[11]);
+  p = ser_fma(p, r, k[12]);
+  p = ser_fma(p, r, k[13]);
   p = ser_fma(p, r, 0.5);
   p = ser_fma(p, r, 1.0);
   p = ser_fma(p, r, 1.0);
-  const int64_t k = (int64_t)(int32_t)(uint32_t)ser_d2u(t); /* low word of the magic sum = k */
-  return ser_u2d(ser_d2u(p) + ((uint64_t)k << 52));
+  const int64_t kk = (int64_t)(int32_t)(uint32_t)ser_d2u(t); /* low word of the magic sum = k */
+  return ser_u2d(ser_d2u(p) + ((uint64_t)kk << 52));
 }
 
 /*
