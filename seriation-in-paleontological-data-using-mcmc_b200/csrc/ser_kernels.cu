@@ -99,6 +99,7 @@ struct Smem {
   double *lmax;     /* C: per-column maximum log-weight of the running step */
   uint16_t *pos;    /* I+1: ascending positions of the ones of every column (postings) */
   uint16_t *st4;    /* 4*C: per-column step geometry: cur, bound, ocur, kb */
+  uint16_t *ones16; /* C: ones per column (static; keeps the dense item loop free of dependent global loads) */
   uint16_t *pre;    /* (W+1)*C: pre[w][col] = ones of the column in words < w */
   uint16_t *hp;     /* N+1: hard positions, ascending */
   double *wcol;     /* manycd only: 4*C per-column weights A, g, 1/g, 1/(1-e^-g) for the dense item phase */
@@ -115,7 +116,7 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t o_H = take(sizeof(double) * (N + 2));
   size_t o_val = take(sizeof(double) * ((Ival < 0 ? I : Ival) + 1)), o_lm = take(sizeof(double) * C);
   size_t o_wc = take(manycd ? sizeof(double) * 4 * C : 0), o_rd = take(manycd ? sizeof(double) * 2 * SER_MAX_WARPS : 0);
-  size_t o_pos = take(sizeof(uint16_t) * (I + 1)), o_st = take(sizeof(uint16_t) * 4 * C);
+  size_t o_pos = take(sizeof(uint16_t) * (I + 1)), o_st = take(sizeof(uint16_t) * 4 * C), o_on = take(sizeof(uint16_t) * C);
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
   size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
@@ -125,7 +126,7 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
     s->H = (double *)(base + o_H);
     s->val = (double *)(base + o_val); s->lmax = (double *)(base + o_lm);
     s->wcol = (double *)(base + o_wc); s->redd = (double *)(base + o_rd);
-    s->pos = (uint16_t *)(base + o_pos); s->st4 = (uint16_t *)(base + o_st);
+    s->pos = (uint16_t *)(base + o_pos); s->st4 = (uint16_t *)(base + o_st); s->ones16 = (uint16_t *)(base + o_on);
     s->V = (uint32_t *)(base + o_v); s->red = (int *)(base + o_r); s->pre = (uint16_t *)(base + o_h); s->hp = (uint16_t *)(base + o_hp);
     s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q); s->perm16 = (uint16_t *)(base + o_m);
   }
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
     b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
     taxon = p.order[tid]; /* the taxon this column holds: indexes the tape, the samples, terms[] */
     off_c = p.off[tid];
+    sm.ones16[tid] = (uint16_t)p.ones[tid];
   }
   __syncthreads();
   build_columns(p, sm);
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             SerStep it;
             it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
             if (kk <= it.kb) {
-              it.nones = p.ones[c]; it.N = N; it.rev = step;
+              it.nones = sm.ones16[c]; it.N = N; it.rev = step;
               sm.val[e - e0] = ser_item_weight(wt, it, sm.pos + (e - kk), kk, sm.lmax[c]);
             }
           }
@@ -741,6 +743,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
     taxon = p.order[tid];
     off_c = p.off[tid];
     ones_c = p.ones[tid];
+    sm.ones16[tid] = (uint16_t)ones_c;
     const double *cd = p.cd4 + (size_t)chain * 4 * p.Mpad + tid;
     c = cd[0]; cc = cd[p.Mpad]; d = cd[2 * p.Mpad]; dd = cd[3 * p.Mpad];
   }
@@ -844,7 +847,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
               SerWeights w;
               w.A = sm.wcol[4 * cix + 0]; w.g = sm.wcol[4 * cix + 1]; w.inv_g = sm.wcol[4 * cix + 2]; w.hs = sm.wcol[4 * cix + 3];
               w.eps = p.eps; w.H = nullptr; w.hmax = N + 1;
-              it.nones = p.ones[cix]; it.N = N; it.rev = step;
+              it.nones = sm.ones16[cix]; it.N = N; it.rev = step;
               sm.val[e - e0] = ser_item_weight(w, it, sm.pos + (e - kk), kk, sm.lmax[cix]);
             }
           }
@@ -1030,9 +1033,12 @@ struct BigSmem {
   double *draws_pi, *logdraw, *draws_cd, *H;
   double *lmax; /* gcap: per column of the running group */
   double *val;  /* icap: item weights / cumulative weights of the running group */
+  double *incl; /* gcap: inclusive chunk totals, one per (column, lane) unit of the running group */
   int *red;
   uint16_t *a16, *b16, *hp, *rpi, *tmp16, *perm16;
   uint16_t *st4; /* 4 * gcap */
+  uint16_t *gones; /* gcap: ones of the running group's columns */
+  int *goff;       /* gcap: first item of each column relative to the group's first item */
   uint16_t *pos; /* icap: postings of the running group's columns */
 };
 __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap)
@@ -1040,11 +1046,12 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_dp = take(8 * SER_PI_DRAWS), o_ld = take(8 * SER_PI_DRAWS), o_dc = take(8 * 8), o_H = take(8 * (size_t)(N + 2));
-  size_t o_lm = take(8 * (size_t)gcap), o_val = take(8 * (size_t)icap), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
+  size_t o_go = take(4 * (size_t)gcap), o_gn = take(2 * (size_t)gcap), o_lm = take(8 * (size_t)gcap), o_in = take(8 * (size_t)gcap), o_val = take(8 * (size_t)icap), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)gcap), o_hp = take(2 * (size_t)(N + 1));
   size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
   if (s) {
-    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos);
+    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos); s->incl = (double *)(base + o_in);
+    s->goff = (int *)(base + o_go); s->gones = (uint16_t *)(base + o_gn);
     s->draws_pi = (double *)(base + o_dp); s->logdraw = (double *)(base + o_ld); s->draws_cd = (double *)(base + o_dc);
     s->H = (double *)(base + o_H); s->lmax = (double *)(base + o_lm); s->red = (int *)(base + o_r);
     s->a16 = (uint16_t *)(base + o_a); s->b16 = (uint16_t *)(base + o_b); s->st4 = (uint16_t *)(base + o_st);
@@ -1203,12 +1210,13 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           const int units = nc << lsh, sub = tid & (lpc - 1);
           __syncthreads(); /* previous group is done with pos / val; first group: publishes H */
           PHASE_MARK(0);
+          for (int cl = tid; cl < nc; cl += C) { sm.goff[cl] = p.off[c0 + cl] - e0; sm.gones[cl] = (uint16_t)p.ones[c0 + cl]; }
           { /* postings: a unit = (column, run of wq words); the prefix table gives the first slot */
             const int wq = (W + lpc - 1) >> lsh;
             for (int u = tid; u < units; u += C) {
               const int c = c0 + (u >> lsh), w0 = sub * wq, w1 = min(W, w0 + wq);
               if (w0 < w1) {
-                uint16_t *out = sm.pos + (p.off[c] - e0) + PRE[w0 * Cs + c];
+                uint16_t *out = sm.pos + (p.off[c] - e0) + PRE[w0 * Cs + c]; /* goff is not published yet */
                 for (int wb = w0; wb < w1; wb += 8) {
                   uint32_t vv[8];
 #pragma unroll
@@ -1232,7 +1240,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
               const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
                                            : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
-              const uint16_t *pos = sm.pos + (p.off[c] - e0);
+              const uint16_t *pos = sm.pos + sm.goff[cl];
               double lm = -1.0e300;
               if (live)
                 for (int kk = sub; kk <= st.kb; kk += lpc) {
@@ -1255,49 +1263,65 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               SerStep it;
               it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
               if (kk <= it.kb) {
-                it.nones = p.ones[c]; it.N = N; it.rev = step;
+                it.nones = sm.gones[cl]; it.N = N; it.rev = step;
                 sm.val[e - e0] = ser_item_weight(wt, it, sm.pos + (e - kk - e0), kk, sm.lmax[cl]);
               }
             }
             __syncthreads();
             PHASE_MARK(3);
-            for (int ub = 0; ub < units; ub += C) {
+            for (int ub = 0; ub < units; ub += C) { /* cumulative weights, chunk-relative: lane `sub` owns items [k0, k1) */
               const int u = ub + tid;
               const bool live = u < units;
               const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
+              const int kb = (int)sm.st4[4 * cl + 3];
+              double *val = sm.val + sm.goff[cl];
+              const int chunk = (kb + lpc) >> lsh, k0 = min(kb + 1, sub * chunk), k1 = min(kb + 1, k0 + chunk);
+              double tot = 0.0;
+              if (live) for (int kk = k0; kk < k1; kk++) { tot = SER_ADD(tot, val[kk]); val[kk] = tot; }
+              /* inclusive totals of the chunks, added left to right so that incl[j] == incl[j-1] + (last
+               * relative prefix of chunk j) bit for bit */
+              double incl = tot;
+              for (int j = 1; j < lpc; j++) {
+                const double t = __shfl_sync(0xffffffffu, incl, (tid & ~(lpc - 1) & 31) + j - 1);
+                if (sub == j) incl = SER_ADD(t, tot);
+              }
+              if (live) sm.incl[u] = incl;
+            }
+            __syncthreads();
+            PHASE_MARK(7);
+            for (int cl = tid; cl < nc; cl += C) { /* inverse CDF: chunk, item inside the chunk, candidate inside the run */
+              const int c = c0 + cl;
               const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
               SerStep st;
               st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = (int)(g4.y >> 16);
-              st.nones = p.ones[c]; st.N = N; st.rev = step;
-              double *val = sm.val + (p.off[c] - e0);
-              /* cumulative weights: lane `sub` owns items [k0, k1) */
-              const int chunk = (st.kb + lpc) >> lsh, k0 = min(st.kb + 1, sub * chunk), k1 = min(st.kb + 1, k0 + chunk);
-              double tot = 0.0;
-              if (live) for (int kk = k0; kk < k1; kk++) tot = SER_ADD(tot, val[kk]);
-              double incl = tot;
-              for (int o = 1; o < lpc; o <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (sub >= o) incl = SER_ADD(t, incl);
+              st.nones = sm.gones[cl]; st.N = N; st.rev = step;
+              const uint16_t *pos = sm.pos + sm.goff[cl];
+              const double *val = sm.val + sm.goff[cl], *incl = sm.incl + (cl << lsh);
+              const int taxon = p.order[c];
+              double uu;
+              if (p.mode == SER_MODE_REPLAY) uu = tape[sc.cursor + 6 + 2 * taxon + step];
+              else {
+                uint32_t o[4];
+                ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+                uu = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
               }
-              double S = __shfl_up_sync(0xffffffffu, incl, 1);
-              if (sub == 0) S = 0.0;
-              if (live) for (int kk = k0; kk < k1; kk++) { S = SER_ADD(S, val[kk]); val[kk] = S; }
-              __syncwarp();
-              if (live && sub == 0) {
-                const int taxon = p.order[c];
-                double uu;
-                if (p.mode == SER_MODE_REPLAY) uu = tape[sc.cursor + 6 + 2 * taxon + step];
-                else {
-                  uint32_t o[4];
-                  ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
-                  uu = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
-                }
-                const int pick = ser_step_pick_scanned(wt, st, sm.pos + (p.off[c] - e0), val, sm.lmax[cl], uu);
-                if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
-                else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
+              const double target = SER_MUL(uu, incl[lpc - 1]);
+              int j = 0;
+              while (j < lpc - 1 && incl[j] < target) j++;
+              const double base = j ? incl[j - 1] : 0.0;
+              const int chunk = (st.kb + lpc) >> lsh, k0 = min(st.kb + 1, j * chunk), k1 = min(st.kb + 1, k0 + chunk);
+              int lo = k0, hi = k1 - 1; /* first item of the chunk whose cumulative weight reaches the target */
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
               }
-              __syncwarp(); /* the b-step's geometry is computed by the same lanes of the same warp */
+              int q, n;
+              const double le = SER_SUB(ser_item_eval(wt, st, pos, lo, &q, &n), sm.lmax[cl]);
+              const int pick = q - n + 1 + ser_run_pick(wt, n, le, lo > k0 ? SER_ADD(base, val[lo - 1]) : base, target);
+              if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
+              else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
             }
+            __syncthreads(); /* the b-step's geometry is computed under a different column -> thread map */
             PHASE_MARK(4);
           }
         }
@@ -1981,7 +2005,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
      * (SER_BIG_SMEM_KB, default 200), at most 1024 columns, never splitting a column */
     int budget_kb = 200;
     if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(227, atoi(v)));
-    const int gcap = std::min(M, 1024);
+    const int gcap = std::max(std::min(M, 1024), run->big_threads); /* also bounds (columns x lanes per column) */
     const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
     long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32;
     icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);

@@ -1,4 +1,5 @@
-python -m pytest tests -x -q -m gpu -k "replay_bit_exact or free_running" 2>&1 | tail -2
+python -m pytest tests -x -q -m gpu -k "big or wide or synthetic or replay_bit_exact or manycd_replay" 2>&1 | tail -2
 echo "== synthetic: $(python tools/quick_tput.py synthetic 1184 2 2>&1 | tail -2 | head -1)"
+echo "== synthetic 512x2: $(SER_BIG_THREADS=512 SER_BIG_SMEM_KB=110 python tools/quick_tput.py synthetic 1184 2 2>&1 | tail -2 | head -1)"
 echo "== g2s2: $(python tools/quick_tput.py g2s2 16384 10 2>&1 | tail -2 | head -1)"
 echo "== g10s10: $(python tools/quick_tput.py g10s10 16384 10 2>&1 | tail -2 | head -1)"
