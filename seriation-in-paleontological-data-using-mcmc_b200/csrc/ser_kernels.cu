@@ -1211,10 +1211,11 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           __syncthreads(); /* previous group is done with pos / val; first group: publishes H */
           PHASE_MARK(0);
           for (int cl = tid; cl < nc; cl += C) { sm.goff[cl] = p.off[c0 + cl] - e0; sm.gones[cl] = (uint16_t)p.ones[c0 + cl]; }
-          { /* postings: a unit = (column, run of wq words); the prefix table gives the first slot */
+          { /* postings: a unit = (run of wq words, column), column fastest so that a warp reads 32
+             * consecutive columns of one word row; the prefix table gives the unit's first slot */
             const int wq = (W + lpc - 1) >> lsh;
             for (int u = tid; u < units; u += C) {
-              const int c = c0 + (u >> lsh), w0 = sub * wq, w1 = min(W, w0 + wq);
+              const int qq = u / nc, cl = u - qq * nc, c = c0 + cl, w0 = qq * wq, w1 = min(W, w0 + wq);
               if (w0 < w1) {
                 uint16_t *out = sm.pos + (p.off[c] - e0) + PRE[w0 * Cs + c]; /* goff is not published yet */
                 for (int wb = w0; wb < w1; wb += 8) {
@@ -2002,8 +2003,8 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   }
   if (run->big) {
     /* column groups of the Gibbs phase: as many items as the shared-memory budget holds
-     * (SER_BIG_SMEM_KB, default 200), at most 1024 columns, never splitting a column */
-    int budget_kb = 200;
+     * (SER_BIG_SMEM_KB, default 220), at most 1024 columns, never splitting a column */
+    int budget_kb = 220;
     if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(227, atoi(v)));
     const int gcap = std::max(std::min(M, 1024), run->big_threads); /* also bounds (columns x lanes per column) */
     const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
