@@ -229,10 +229,14 @@ struct SerWeights {
   int hmax;
 };
 
-/* geometric partial sum H(m) = sum_{u<m} exp(-u g) */
+/* geometric partial sum H(m) = sum_{u<m} exp(-u g).  TAB: 1 = from the per-sweep table (scalar c, d),
+ * 0 = evaluated on the fly (per-taxon c, d), 2 = decided at run time by w.H.  The hot loops pass the
+ * constant so that the other variant's code (a whole exp()) is not even emitted. */
+template <int TAB = 2>
 SER_HD double ser_H(const SerWeights &w, int m)
 {
-  return w.H ? w.H[m] : SER_MUL(SER_SUB(1.0, exp(-SER_MUL(w.g, (double)m))), w.hs);
+  if (TAB == 1 || (TAB == 2 && w.H)) return w.H[m];
+  return SER_MUL(SER_SUB(1.0, exp(-SER_MUL(w.g, (double)m))), w.hs);
 }
 
 /* number of entries (-1) the per-sweep table H needs for a given g and N */
@@ -323,6 +327,7 @@ SER_HD double ser_exp_weight(double x)
  * weight at exp(LOGEPSILON) (mcmc.c:734); m = the candidates that stay above the floor (they
  * are the LAST m of the run).  Returns the run's total weight.
  */
+template <int TAB = 2>
 SER_HD double ser_run_sum(const SerWeights &w, int n, double le, int *m_out, double *ye_out)
 {
   if (le < SER_LOGEPSILON) { *m_out = 0; *ye_out = 0.0; return SER_MUL(ser_i2d(n), w.eps); }
@@ -331,7 +336,7 @@ SER_HD double ser_run_sum(const SerWeights &w, int n, double le, int *m_out, dou
   if (m > w.hmax) m = w.hmax;
   const double ye = ser_exp_weight(le);
   *m_out = m; *ye_out = ye;
-  return ser_fma(ye, ser_H(w, m), SER_MUL(ser_i2d(n - m), w.eps));
+  return ser_fma(ye, ser_H<TAB>(w, m), SER_MUL(ser_i2d(n - m), w.eps));
 }
 
 /*
@@ -411,19 +416,21 @@ SER_HD double ser_step_lmax(const SerWeights &wt, const SerStep &st, const uint1
 }
 
 /* weight of item kk given the step's maximum */
+template <int TAB = 2>
 SER_HD double ser_item_weight(const SerWeights &wt, const SerStep &st, const uint16_t *pos, int kk, double lmax)
 {
   int q, n, m; double ye;
   const double le = SER_SUB(ser_item_eval(wt, st, pos, kk, &q, &n), lmax);
-  return ser_run_sum(wt, n, le, &m, &ye);
+  return ser_run_sum<TAB>(wt, n, le, &m, &ye);
 }
 
 /* inside one run: s = cumulative weight before it; returns t in [0,n): the first candidate of
  * the run whose cumulative weight reaches target (the last one if none does) */
+template <int TAB = 2>
 SER_HD int ser_run_pick(const SerWeights &wt, int n, double le, double s, double target)
 {
   int m; double ye;
-  ser_run_sum(wt, n, le, &m, &ye);
+  ser_run_sum<TAB>(wt, n, le, &m, &ye);
   const int nf = n - m; /* nf floored candidates of weight eps each, then m geometric ones */
   const double sf = ser_fma(ser_i2d(nf), wt.eps, s);
   if (nf > 0 && (sf >= target || m == 0)) {
@@ -434,17 +441,18 @@ SER_HD int ser_run_pick(const SerWeights &wt, int n, double le, double s, double
     return t;
   }
   /* cumulative weight through geometric candidate k (k = 0..m-1): sf + ye (H[m] - H[m-1-k]) */
-  const double hm = ser_H(wt, m);
+  const double hm = ser_H<TAB>(wt, m);
   int lo = 0, hi = m - 1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (ser_fma(ye, SER_SUB(hm, ser_H(wt, m - 1 - mid)), sf) >= target) hi = mid; else lo = mid + 1;
+    if (ser_fma(ye, SER_SUB(hm, ser_H<TAB>(wt, m - 1 - mid)), sf) >= target) hi = mid; else lo = mid + 1;
   }
   return nf + lo;
 }
 
 /* val[0..kb] already holds the CUMULATIVE item weights: inverts the CDF (mcmc_randompick) and
  * returns the picked candidate (logical index) */
+template <int TAB = 2>
 SER_HD int ser_step_pick_scanned(const SerWeights &wt, const SerStep &st, const uint16_t *pos, const double *val, double lmax,
                                  double U)
 {
@@ -456,16 +464,17 @@ SER_HD int ser_step_pick_scanned(const SerWeights &wt, const SerStep &st, const 
   }
   int q, n;
   const double le = SER_SUB(ser_item_eval(wt, st, pos, lo, &q, &n), lmax);
-  return q - n + 1 + ser_run_pick(wt, n, le, lo ? val[lo - 1] : 0.0, target);
+  return q - n + 1 + ser_run_pick<TAB>(wt, n, le, lo ? val[lo - 1] : 0.0, target);
 }
 
 /* the taxon's own part: val[0..kb] holds the item weights; turns them into cumulative sums and picks */
+template <int TAB = 2>
 SER_HD int ser_step_pick(const SerWeights &wt, const SerStep &st, const uint16_t *pos, double *val, double lmax,
                          double U)
 {
   double S = 0.0;
   for (int kk = 0; kk <= st.kb; kk++) { S = SER_ADD(S, val[kk]); val[kk] = S; }
-  return ser_step_pick_scanned(wt, st, pos, val, lmax, U);
+  return ser_step_pick_scanned<TAB>(wt, st, pos, val, lmax, U);
 }
 
 /* ------------------------------------------------------------------ pi proposals */

@@ -512,12 +512,12 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
             if (kk <= it.kb) {
               it.nones = sm.ones16[c]; it.N = N; it.rev = step;
-              sm.val[e - e0] = ser_item_weight(wt, it, sm.pos + (e - kk), kk, sm.lmax[c]);
+              sm.val[e - e0] = ser_item_weight<1>(wt, it, sm.pos + (e - kk), kk, sm.lmax[c]);
             }
           }
           __syncthreads();
           if (is_taxon && tid >= p.grp_c[g] && tid < p.grp_c[g + 1]) {
-            const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
+            const int pick = ser_step_pick<1>(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
             if (step == 0) { changed += pick != a; a = pick; }
             else { changed += (N - pick) != b; b = N - pick; }
           }
@@ -848,12 +848,12 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
               w.A = sm.wcol[4 * cix + 0]; w.g = sm.wcol[4 * cix + 1]; w.inv_g = sm.wcol[4 * cix + 2]; w.hs = sm.wcol[4 * cix + 3];
               w.eps = p.eps; w.H = nullptr; w.hmax = N + 1;
               it.nones = sm.ones16[cix]; it.N = N; it.rev = step;
-              sm.val[e - e0] = ser_item_weight(w, it, sm.pos + (e - kk), kk, sm.lmax[cix]);
+              sm.val[e - e0] = ser_item_weight<0>(w, it, sm.pos + (e - kk), kk, sm.lmax[cix]);
             }
           }
           __syncthreads();
           if (is_taxon && tid >= p.grp_c[g] && tid < p.grp_c[g + 1]) {
-            const int pick = ser_step_pick(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
+            const int pick = ser_step_pick<0>(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
             if (step == 0) { changed += pick != a; a = pick; }
             else { changed += (N - pick) != b; b = N - pick; }
           }
@@ -1265,7 +1265,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
               if (kk <= it.kb) {
                 it.nones = sm.gones[cl]; it.N = N; it.rev = step;
-                sm.val[e - e0] = ser_item_weight(wt, it, sm.pos + (e - kk - e0), kk, sm.lmax[cl]);
+                sm.val[e - e0] = ser_item_weight<1>(wt, it, sm.pos + (e - kk - e0), kk, sm.lmax[cl]);
               }
             }
             __syncthreads();
@@ -1318,7 +1318,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               }
               int q, n;
               const double le = SER_SUB(ser_item_eval(wt, st, pos, lo, &q, &n), sm.lmax[cl]);
-              const int pick = q - n + 1 + ser_run_pick(wt, n, le, lo > k0 ? SER_ADD(base, val[lo - 1]) : base, target);
+              const int pick = q - n + 1 + ser_run_pick<1>(wt, n, le, lo > k0 ? SER_ADD(base, val[lo - 1]) : base, target);
               if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
               else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
             }
