@@ -304,9 +304,18 @@ def main():
         mb = S.microbench(local)
         kernel_sweeps_per_s = n_local * calls * 10 / (sweep_kernel_ms * 1e-3)
         achieved = 10.0 * algo["F"] * kernel_sweeps_per_s / 1e12
+        # DRAM bytes per sweep of the sweep kernel from the committed `ncu --set full` captures
+        # (dram__bytes_read.sum + dram__bytes_write.sum over the chain-sweeps of the profiled launch),
+        # scaled to one of this run's two sweep launches per step
+        ncu_dram_per_sweep = {"g2s2": (10.899968e6 + 414.976e3) / 40960, "synthetic": (2.160332e9 + 1.837035e9) / 2960}
+        traffic = traffic_src = None
+        if args.dataset in ncu_dram_per_sweep:
+            traffic = ncu_dram_per_sweep[args.dataset] * n_local * calls * 10 / 2
+            traffic_src = ("profiles/r01/sweep_%sv7_ncu_raw_selected.txt: %.0f B of DRAM traffic per chain-sweep x the chain-sweeps "
+                           "of one sweep launch" % ("big_" if big else "", ncu_dram_per_sweep[args.dataset]))
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": mb["fp64_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / mb["fp64_tflops"], "traffic": None,
+            "frac": achieved / mb["fp64_tflops"], "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "ser_microbench fp64 FMA on this GPU, measured live (MEASURED_PEAKS.json holds only HBM and bf16)",
             "kernel": "ser_sweep_kernel_big" if big else "ser_sweep_kernel", "kernel_ms_per_step": sweep_kernel_ms,
             "kernel_sweeps_per_s_per_gpu": kernel_sweeps_per_s,

@@ -649,3 +649,27 @@ def test_script_mirror_equals_unmodified_script_py(S):
     want = ((j >= fs["a"][:, None, :]) & (j <= fs["b"][:, None, :])).sum(axis=0)
     assert T == samp and np.array_equal(alive[0], want) and not alive[1].any()
     batch.run.close()
+
+
+def test_65536_chains_one_launch_and_batch_size_independence(S):
+    """BASELINE.json's largest batch: 65 536 chains in one launch (g10s10 to keep it short).  Every chain
+    passes mcmc_consistent, and the last chain of the batch is bit-identical to the same global chain id
+    simulated alone -- a chain never depends on the batch it runs in."""
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    big = S.Run(ds, 65536, seed=99, store=S.STORE_PI, max_samples=2).init().advance(1, False).advance(2, True).sync()
+    assert big.check() == 0
+    e = big.chain_stats()["e_negloglik"]
+    assert e.shape == (65536,) and np.all(e > 0) and np.unique(e).size > 60000
+    for gid in (0, 31337, 65535):
+        one = S.Run(ds, 1, seed=99, chain_offset=gid, store=S.STORE_PI, max_samples=2).init().advance(1, False).advance(2, True).sync()
+        a, b = big.state(gid), one.state(0)
+        for k in ("a", "b", "pi", "tot"):
+            assert np.array_equal(a[k], b[k]), (gid, k)
+        assert a["loglik"] == b["loglik"] and a["c"] == b["c"] and a["d"] == b["d"]
+        assert np.array_equal(big.fetch_samples(gid, full=False)["pi"], one.fetch_samples(0, full=False)["pi"])
+        one.close()
+    chosen = S.select_chains(e, 8)[0]
+    po = S.po_finalize(big.po_counts(chosen), 8, faithful=False)
+    assert po.shape == (124, 124) and np.allclose(po + po.T - np.diag(2 * np.diag(po)), (1 - np.eye(124)) * (2 / 1000), atol=1e-12)
+    big.close()
