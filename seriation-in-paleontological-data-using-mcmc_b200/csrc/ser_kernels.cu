@@ -504,8 +504,10 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
         for (int g = 0; g < p.n_groups; g++) { /* columns grp_c[g]..grp_c[g+1] = items grp_e[g]..grp_e[g+1] */
           const int e0 = p.grp_e[g], e1 = p.grp_e[g + 1];
           if (g) __syncthreads(); /* the previous group's scans are done with val */
+          uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u; /* item -> column map, fetched one iteration ahead */
           for (int e = e0 + tid; e < e1; e += C) {
-            const uint32_t ck = p.item_col[e];
+            const uint32_t ck = ck_next;
+            if (e + C < e1) ck_next = p.item_col[e + C];
             const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
             const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c); /* cur, bound | ocur, kb */
             SerStep it;
@@ -837,8 +839,10 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
         for (int g = 0; g < p.n_groups; g++) {
           const int e0 = p.grp_e[g], e1 = p.grp_e[g + 1];
           if (g) __syncthreads();
+          uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u;
           for (int e = e0 + tid; e < e1; e += C) {
-            const uint32_t ck = p.item_col[e];
+            const uint32_t ck = ck_next;
+            if (e + C < e1) ck_next = p.item_col[e + C];
             const int cix = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
             const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cix);
             SerStep it;
@@ -1257,8 +1261,10 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             }
             __syncthreads();
             PHASE_MARK(2);
+            uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u; /* fetched one iteration ahead */
             for (int e = e0 + tid; e < e1; e += C) {
-              const uint32_t ck = p.item_col[e];
+              const uint32_t ck = ck_next;
+              if (e + C < e1) ck_next = p.item_col[e + C];
               const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu), cl = c - c0;
               const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
               SerStep it;
