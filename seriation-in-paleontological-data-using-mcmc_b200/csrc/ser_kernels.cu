@@ -1214,23 +1214,27 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           const int units = nc << lsh, sub = tid & (lpc - 1);
           __syncthreads(); /* previous group is done with pos / val; first group: publishes H */
           PHASE_MARK(0);
-          for (int cl = tid; cl < nc; cl += C) { sm.goff[cl] = p.off[c0 + cl] - e0; sm.gones[cl] = (uint16_t)p.ones[c0 + cl]; }
           { /* postings: a unit = (run of wq words, column), column fastest so that a warp reads 32
              * consecutive columns of one word row; the prefix table gives the unit's first slot */
             const int wq = (W + lpc - 1) >> lsh;
             for (int u = tid; u < units; u += C) {
               const int qq = u / nc, cl = u - qq * nc, c = c0 + cl, w0 = qq * wq, w1 = min(W, w0 + wq);
-              if (w0 < w1) {
-                uint16_t *out = sm.pos + (p.off[c] - e0) + PRE[w0 * Cs + c]; /* goff is not published yet */
-                for (int wb = w0; wb < w1; wb += 8) {
-                  uint32_t vv[8];
+              /* every load of the unit is issued before the first one is needed */
+              uint32_t vv[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) vv[k] = w0 + k < w1 ? V[(w0 + k) * Cs + c] : 0u;
+              const int first = w0 < w1 ? (int)PRE[w0 * Cs + c] : 0, off_c = p.off[c] - e0;
+              if (qq == 0) { sm.goff[cl] = off_c; sm.gones[cl] = (uint16_t)p.ones[c]; } /* the group's column table */
+              uint16_t *out = sm.pos + off_c + first;
+              for (int wb = w0; wb < w1; wb += 8) {
+                if (wb > w0) {
 #pragma unroll
                   for (int k = 0; k < 8; k++) vv[k] = wb + k < w1 ? V[(wb + k) * Cs + c] : 0u;
+                }
 #pragma unroll
-                  for (int k = 0; k < 8; k++) {
-                    uint32_t v = vv[k];
-                    while (v) { *out++ = (uint16_t)(32 * (wb + k) + SER_FFS(v) - 1); v &= v - 1u; }
-                  }
+                for (int k = 0; k < 8; k++) {
+                  uint32_t v = vv[k];
+                  while (v) { *out++ = (uint16_t)(32 * (wb + k) + SER_FFS(v) - 1); v &= v - 1u; }
                 }
               }
             }
