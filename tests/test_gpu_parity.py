@@ -712,3 +712,13 @@ def test_free_running_statistics_vs_unmodified_reference_pipeline(S):
         d = np.abs(po - g["po"])
         assert d.mean() < 0.02, d.mean()
         assert d.mean() < 1.5 * own, (d.mean(), own)
+
+
+@pytest.mark.parametrize("groups", ["1", "2", "5", "8"])
+def test_column_groups_are_invisible(S, oracle_mod, monkeypatch, groups):
+    """SER_SWEEP_GROUPS only changes how many columns' item weights share the buffer at a time: the
+    replay stays bit-exact for every group count (scalar and per-taxon c, d)."""
+    monkeypatch.setenv("SER_SWEEP_GROUPS", groups)
+    X, hard = load_hex_dataset("g5s5")
+    _replay_case(S, oracle_mod, X, hard, [5, 6], 3, 3)
+    _manycd_replay_case(S, oracle_mod, X, hard, [7], 2, 2)
