@@ -109,8 +109,11 @@ SER_HD void ser_col_fix_pre(const uint32_t *col, uint16_t *pre, int C, int w0, i
   for (int w = w0; w < w1; w++) { acc += SER_POPC(col[w * C]); pre[(w + 1) * C] = (uint16_t)acc; }
 }
 
+/* The three column moves below take an optional prefix table: with `pre` the counts pre[w0+1..w1] are
+ * rewritten from the new words as they are produced (what ser_col_fix_pre would do in a second pass
+ * that re-reads the column). */
 /* in-place: reverse bits [i, j] (new[p] = old[i+j-p]) */
-SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j)
+SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j, uint16_t *pre = 0)
 {
   uint32_t old[SER_MAXW];
   const int w0 = i >> 5, w1 = j >> 5;
@@ -122,6 +125,7 @@ SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j)
   }
   for (int w = w0; w <= w1; w++) old[w] = col[w * C];
   const int s = i + j;
+  int acc = pre ? (int)pre[w0 * C] : 0;
   for (int wn = w0; wn <= w1; wn++) {
     /* new bit p = old[s - p]: 32 old bits ending at s - 32wn, reversed */
     const int q = s - 32 * wn - 31;
@@ -130,18 +134,21 @@ SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j)
     const uint32_t hi = (qw + 1 >= w0 && qw + 1 <= w1) ? old[qw + 1] : 0u;
     const uint32_t bits = SER_BREV(ser_funnel_r(lo, hi, q & 31));
     const uint32_t m = ser_range_mask(wn, i, j + 1);
-    col[wn * C] = (old[wn] & ~m) | (bits & m);
+    const uint32_t nw = (old[wn] & ~m) | (bits & m);
+    col[wn * C] = nw;
+    if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
   }
 }
 
 /* in-place: move bit i to position j, shifting the bits in between by one (pi1) */
-SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j)
+SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j, uint16_t *pre = 0)
 {
   uint32_t old[SER_MAXW];
   const int lo = i < j ? i : j, hi = i < j ? j : i;
   const int w0 = lo >> 5, w1 = hi >> 5;
   for (int w = w0; w <= w1; w++) old[w] = col[w * C];
   const uint32_t moved = (old[i >> 5] >> (i & 31)) & 1u;
+  int acc = pre ? (int)pre[w0 * C] : 0;
   for (int wn = w0; wn <= w1; wn++) {
     uint32_t bits, m;
     const uint32_t cur = old[wn];
@@ -156,15 +163,17 @@ SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j)
     uint32_t nw = (cur & ~m) | (bits & m);
     if (wn == (j >> 5)) nw = (nw & ~(1u << (j & 31))) | (moved << (j & 31));
     col[wn * C] = nw;
+    if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
   }
 }
 
 /* in-place: new[p] = old[perm[p]] for p in [i, j] (pi3; perm is an involution on the window) */
-SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uint16_t *perm)
+SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uint16_t *perm, uint16_t *pre = 0)
 {
   uint32_t old[SER_MAXW];
   const int w0 = i >> 5, w1 = j >> 5;
   for (int w = w0; w <= w1; w++) old[w] = col[w * C];
+  int acc = pre ? (int)pre[w0 * C] : 0;
   for (int wn = w0; wn <= w1; wn++) {
     uint32_t nw = old[wn];
     const int p0 = (32 * wn > i) ? 32 * wn : i, p1 = (32 * wn + 31 < j) ? 32 * wn + 31 : j;
@@ -174,6 +183,7 @@ SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uin
       nw = (nw & ~(1u << (p & 31))) | (bit << (p & 31));
     }
     col[wn * C] = nw;
+    if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
   }
 }
 

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
           if (!mh_decide(p, sm, wt, ps, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
-          if (is_col) { ser_col_rotate(col, C, W, i, j); ser_col_fix_pre(col, pre, C, lo >> 5, hi >> 5); }
+          if (is_col) ser_col_rotate(col, C, W, i, j, pre);
           for (int n = lo + tid; n <= hi; n += C)
             sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
           __syncthreads();
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
           }
-          if (is_col) { ser_col_reverse(col, C, W, i, j); ser_col_fix_pre(col, pre, C, i >> 5, j >> 5); }
+          if (is_col) ser_col_reverse(col, C, W, i, j, pre);
           for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
           __syncthreads();
           for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
@@ -618,8 +618,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           if (is_taxon) {
             const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
-            ser_col_permute(col, C, W, g.i, g.j, sm.perm16);
-            ser_col_fix_pre(col, pre, C, g.i >> 5, g.j >> 5);
+            ser_col_permute(col, C, W, g.i, g.j, sm.perm16, pre);
           }
           for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
           __syncthreads();
@@ -902,7 +901,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
           if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
           if (!mh_decide_many(p, sm, wt, ps, taxon, is_taxon, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
-          if (is_col) { ser_col_rotate(col, C, W, i, j); ser_col_fix_pre(col, pre, C, lo >> 5, hi >> 5); }
+          if (is_col) ser_col_rotate(col, C, W, i, j, pre);
           for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
           __syncthreads();
           for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
@@ -930,7 +929,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
             const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
           }
-          if (is_col) { ser_col_reverse(col, C, W, i, j); ser_col_fix_pre(col, pre, C, i >> 5, j >> 5); }
+          if (is_col) ser_col_reverse(col, C, W, i, j, pre);
           for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
           __syncthreads();
           for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
@@ -953,8 +952,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
           if (is_taxon) {
             const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
-            ser_col_permute(col, C, W, g.i, g.j, sm.perm16);
-            ser_col_fix_pre(col, pre, C, g.i >> 5, g.j >> 5);
+            ser_col_permute(col, C, W, g.i, g.j, sm.perm16, pre);
           }
           for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
           __syncthreads();
@@ -1378,8 +1376,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
             for (int c = tid; c <= M; c += C) {
               if (c < M) { int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b; }
-              ser_col_rotate(V + c, Cs, W, i, j);
-              ser_col_fix_pre(V + c, PRE + c, Cs, lo >> 5, hi >> 5);
+              ser_col_rotate(V + c, Cs, W, i, j, PRE + c);
               if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
             }
             for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
@@ -1412,8 +1409,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                 ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
                 sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
               }
-              ser_col_reverse(V + c, Cs, W, i, j);
-              ser_col_fix_pre(V + c, PRE + c, Cs, i >> 5, j >> 5);
+              ser_col_reverse(V + c, Cs, W, i, j, PRE + c);
               if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
             }
             for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
@@ -1440,8 +1436,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
               ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
               sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
-              ser_col_permute(V + c, Cs, W, g.i, g.j, sm.perm16);
-              ser_col_fix_pre(V + c, PRE + c, Cs, g.i >> 5, g.j >> 5);
+              ser_col_permute(V + c, Cs, W, g.i, g.j, sm.perm16, PRE + c);
             }
             for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
             __syncthreads();

@@ -56,7 +56,13 @@ struct Chain {
     wt.H = H.data();
   }
   void rebuild_hard() { ser_hard_list(V.data() + M, C, W, hp.data()); }
-  void fix_pre(int p0, int p1) { for (int m = 0; m <= M; m++) ser_col_fix_pre(col(m), pcol(m), C, p0 >> 5, p1 >> 5); }
+  /* the column moves maintain the prefix tables themselves; this re-derives them the slow way and
+   * aborts on any difference (the pi3 permutation leaves the hard column alone) */
+  void fix_pre(int p0, int p1) {
+    const std::vector<uint16_t> kept(pre);
+    for (int m = 0; m <= M; m++) ser_col_fix_pre(col(m), pcol(m), C, p0 >> 5, p1 >> 5);
+    if (kept != pre) { fprintf(stderr, "emulator: fused prefix update differs from ser_col_fix_pre\n"); abort(); }
+  }
   void build_columns() {
     std::fill(V.begin(), V.end(), 0u);
     for (int p = 0; p < N; p++) {
@@ -136,7 +142,7 @@ int pi1(Chain &ch) {
   long D0 = 0, D1 = 0;
   for (int m = 0; m < M; m++) { D0 += dt0[m]; D1 += dt1[m]; }
   for (int m = 0; m < M; m++) ser_pi1_apply_ab(&ch.a[m], &ch.b[m], i, j);
-  for (int m = 0; m <= M; m++) ser_col_rotate(ch.col(m), C, W, i, j);
+  for (int m = 0; m <= M; m++) ser_col_rotate(ch.col(m), C, W, i, j, ch.pcol(m));
   const uint16_t t = ch.rpi[i];
   if (i < j) for (int n = i; n < j; n++) ch.rpi[n] = ch.rpi[n + 1];
   else for (int n = i; n > j; n--) ch.rpi[n] = ch.rpi[n - 1];
@@ -167,7 +173,7 @@ int pi2(Chain &ch, int swap) {
     const int ain = ser_in_window(ch.a[m], i, j + 1, inc1, inc2), bin = ser_in_window(ch.b[m], i, j + 1, inc1, inc2);
     ser_mirror_ab(ch.a[m], ch.b[m], ain, bin, i + j + 1, &ch.a[m], &ch.b[m]);
   }
-  for (int m = 0; m <= M; m++) ser_col_reverse(ch.col(m), C, W, i, j);
+  for (int m = 0; m <= M; m++) ser_col_reverse(ch.col(m), C, W, i, j, ch.pcol(m));
   for (int l = i, r = j; l < r; l++, r--) { uint16_t t = ch.rpi[l]; ch.rpi[l] = ch.rpi[r]; ch.rpi[r] = t; }
   ch.fix_pre(i, j);
   ch.rebuild_hard();
@@ -196,7 +202,7 @@ int pi3(Chain &ch) {
     const int ain = ser_in_window(ch.a[m], g.i, g.j + 1, inc1, inc2), bin = ser_in_window(ch.b[m], g.i, g.j + 1, inc1, inc2);
     ser_mirror_ab(ch.a[m], ch.b[m], ain, bin, g.i + g.j + 1, &ch.a[m], &ch.b[m]);
   }
-  for (int m = 0; m < M; m++) ser_col_permute(ch.col(m), C, W, g.i, g.j, perm.data());
+  for (int m = 0; m < M; m++) ser_col_permute(ch.col(m), C, W, g.i, g.j, perm.data(), ch.pcol(m));
   std::vector<uint16_t> tmp(ch.rpi);
   for (int n = g.i; n <= g.j; n++) ch.rpi[n] = tmp[perm[n]];
   ch.fix_pre(g.i, g.j);
