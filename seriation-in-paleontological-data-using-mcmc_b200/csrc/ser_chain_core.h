@@ -425,6 +425,28 @@ SER_HD double ser_step_lmax(const SerWeights &wt, const SerStep &st, const uint1
   return lmax;
 }
 
+/* the same pass, keeping every item's log-weight and run length for the dense pass (which then needs
+ * neither the postings nor the step geometry): Lc[kk], nc[kk] for kk = 0..kb */
+SER_HD double ser_step_lmax_cache(const SerWeights &wt, const SerStep &st, const uint16_t *pos, double *Lc, uint16_t *nc)
+{
+  double lmax = -1.0e300;
+  for (int kk = 0; kk <= st.kb; kk++) {
+    int q, n;
+    const double L = ser_item_eval(wt, st, pos, kk, &q, &n);
+    Lc[kk] = L; nc[kk] = (uint16_t)n;
+    lmax = ser_fmax(lmax, L);
+  }
+  return lmax;
+}
+
+/* weight of an item from its cached log-weight and run length (bit for bit ser_item_weight) */
+template <int TAB = 2>
+SER_HD double ser_item_weight_cached(const SerWeights &wt, double L, int n, double lmax)
+{
+  int m; double ye;
+  return ser_run_sum<TAB>(wt, n, SER_SUB(L, lmax), &m, &ye);
+}
+
 /* weight of item kk given the step's maximum */
 template <int TAB = 2>
 SER_HD double ser_item_weight(const SerWeights &wt, const SerStep &st, const uint16_t *pos, int kk, double lmax)

@@ -1249,11 +1249,15 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                                            : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
               const uint16_t *pos = sm.pos + sm.goff[cl];
               double lm = -1.0e300;
-              if (live)
+              if (live) { /* every item's log-weight stays in val for the dense pass */
+                double *Lc = sm.val + sm.goff[cl];
                 for (int kk = sub; kk <= st.kb; kk += lpc) {
                   int q, n;
-                  lm = ser_fmax(lm, ser_item_eval(wt, st, pos, kk, &q, &n));
+                  const double L = ser_item_eval(wt, st, pos, kk, &q, &n);
+                  Lc[kk] = L;
+                  lm = ser_fmax(lm, L);
                 }
+              }
               for (int o = lpc >> 1; o > 0; o >>= 1) lm = ser_fmax(lm, __shfl_xor_sync(0xffffffffu, lm, o));
               if (live && sub == 0) {
                 sm.lmax[cl] = lm;
@@ -1267,13 +1271,15 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             for (int e = e0 + tid; e < e1; e += C) {
               const uint32_t ck = ck_next;
               if (e + C < e1) ck_next = p.item_col[e + C];
-              const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu), cl = c - c0;
-              const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
-              SerStep it;
-              it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
-              if (kk <= it.kb) {
-                it.nones = sm.gones[cl]; it.N = N; it.rev = step;
-                sm.val[e - e0] = ser_item_weight<1>(wt, it, sm.pos + (e - kk - e0), kk, sm.lmax[cl]);
+              const int cl = (int)(ck >> 16) - c0, kk = (int)(ck & 0xffffu);
+              const int kb = (int)sm.st4[4 * cl + 3];
+              if (kk <= kb) { /* log-weight -> run weight, in place; the run length from the postings */
+                const uint16_t *pos = sm.pos + (e - kk - e0);
+                const int nones = (int)sm.gones[cl], bound = (int)sm.st4[4 * cl + 1];
+                int q, qprev; /* ser_item_eval's q and qprev */
+                if (step) { q = kk < kb ? N - 1 - (int)pos[nones - 1 - kk] : bound; qprev = kk > 0 ? N - 1 - (int)pos[nones - kk] : -1; }
+                else { q = kk < kb ? (int)pos[kk] : bound; qprev = kk > 0 ? (int)pos[kk - 1] : -1; }
+                sm.val[e - e0] = ser_item_weight_cached<1>(wt, sm.val[e - e0], q - qprev, sm.lmax[cl]);
               }
             }
             __syncthreads();
@@ -2013,7 +2019,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(227, atoi(v)));
     const int gcap = std::max(std::min(M, 1024), run->big_threads); /* also bounds (columns x lanes per column) */
     const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
-    long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32;
+    long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32; /* val 8 + pos 2 bytes per item */
     icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);
     if (icap < N + 1) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain before any item", fixed); return SER_E_ARG; }
     std::vector<int> bgrp;

@@ -242,6 +242,7 @@ int sample_ab(Chain &ch) {
   for (int m = 0; m < M; m++) off[m + 1] = off[m] + ch.ones[m] + 1;
   std::vector<uint16_t> pos(off[M] + 1);
   std::vector<double> val(off[M] + 1), lmax(M), ua(M), ub(M);
+  std::vector<uint16_t> nrun(off[M] + 1);
   std::vector<SerStep> st(M);
   for (int m = 0; m < M; m++) { ua[m] = ch.next(); ub[m] = ch.next(); }
   for (int m = 0; m < M; m++) ser_expand_ones(ch.col(m), C, W, pos.data() + off[m]);
@@ -249,11 +250,15 @@ int sample_ab(Chain &ch) {
     for (int m = 0; m < M; m++) {
       st[m] = step == 0 ? ser_step_a(ch.col(m), ch.pcol(m), C, W, N, ch.a[m], ch.b[m])
                         : ser_step_b(ch.col(m), ch.pcol(m), C, W, N, ch.a[m], ch.b[m]);
-      lmax[m] = ser_step_lmax(ch.WT(m), st[m], pos.data() + off[m]);
+      lmax[m] = ser_step_lmax_cache(ch.WT(m), st[m], pos.data() + off[m], val.data() + off[m], nrun.data() + off[m]);
+      if (lmax[m] != ser_step_lmax(ch.WT(m), st[m], pos.data() + off[m])) { fprintf(stderr, "emulator: cached maximum differs\n"); abort(); }
     }
-    for (int m = 0; m < M; m++)          // dense over items in the kernel
-      for (int kk = 0; kk <= st[m].kb; kk++)
-        val[off[m] + kk] = ser_item_weight(ch.WT(m), st[m], pos.data() + off[m], kk, lmax[m]);
+    for (int m = 0; m < M; m++)          // dense over items in the kernel: from the cached log-weight and run length
+      for (int kk = 0; kk <= st[m].kb; kk++) {
+        const double w = ser_item_weight_cached(ch.WT(m), val[off[m] + kk], nrun[off[m] + kk], lmax[m]);
+        if (w != ser_item_weight(ch.WT(m), st[m], pos.data() + off[m], kk, lmax[m])) { fprintf(stderr, "emulator: cached item weight differs\n"); abort(); }
+        val[off[m] + kk] = w;
+      }
     for (int m = 0; m < M; m++) {
       const int pick = ser_step_pick(ch.WT(m), st[m], pos.data() + off[m], val.data() + off[m], lmax[m], step == 0 ? ua[m] : ub[m]);
       if (step == 0) { changed += pick != ch.a[m]; ch.a[m] = pick; }
