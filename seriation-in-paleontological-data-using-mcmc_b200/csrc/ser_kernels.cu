@@ -562,7 +562,8 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           ps.k += 2;
           if (j >= i) j++;
           const int lo = min(i, j), hi = max(i, j);
-          if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
+          const int nhw = ser_hard_count(hd, lo, hi); /* hard sites in the window */
+          if (ser_is_hard(hd, i) && nhw > 1) continue;
           if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
           if (!mh_decide(p, sm, wt, ps, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
           __syncthreads();
           for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
-          if (tid == M) rebuild_hard(p, sm);
+          if (tid == M && nhw) rebuild_hard(p, sm); /* the hard column only changed if the window holds a hard site */
           sc.counters[3]++;
         } else if (kind == 1 || kind == 3) { /* ---------------- mcmc_samplepi2, mcmc.c:1311-1486 */
           int i, j;
@@ -586,7 +587,8 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             ps.k += 1;
             j = i + 1;
           }
-          if (ser_hard_count(hd, i, j) > 1) continue;
+          const int nhw = ser_hard_count(hd, i, j);
+          if (nhw > 1) continue;
           const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
           ps.k += 2;
           if (is_taxon) ser_pi2_delta(col, pre, C, a, b, i, j, inc1, inc2, &dt0, &dt1);
@@ -596,10 +598,11 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
           }
           if (is_col) ser_col_reverse(col, C, W, i, j, pre);
-          for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
-          __syncthreads();
-          for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
-          if (tid == M) rebuild_hard(p, sm);
+          for (int n = i + tid; 2 * n < i + j; n += C) { /* mirror the site order: disjoint pairs, no staging */
+            const uint16_t t = sm.rpi[n];
+            sm.rpi[n] = sm.rpi[i + j - n]; sm.rpi[i + j - n] = t;
+          }
+          if (tid == M && nhw) rebuild_hard(p, sm);
           sc.counters[kind == 1 ? 4 : 5]++;
         } else { /* ---------------- mcmc_samplepi3, mcmc.c:1489-1682 */
           const int nfree = N - p.nh;
@@ -620,9 +623,10 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
             ser_col_permute(col, C, W, g.i, g.j, sm.perm16, pre);
           }
-          for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
-          __syncthreads();
-          for (int n = g.i + tid; n <= g.j; n += C) sm.rpi[n] = sm.tmp16[n];
+          for (int n = g.i + tid; n <= g.j; n += C) { /* the permutation is an involution: disjoint pairs */
+            const int m2 = sm.perm16[n];
+            if (m2 > n) { const uint16_t t = sm.rpi[n]; sm.rpi[n] = sm.rpi[m2]; sm.rpi[m2] = t; }
+          }
           sc.counters[6]++;
         }
         /* accepted: fold the integer deltas into the totals (the reference recounts, mcmc.c:1303) */
@@ -897,7 +901,8 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
           ps.k += 2;
           if (j >= i) j++;
           const int lo = min(i, j), hi = max(i, j);
-          if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
+          const int nhw = ser_hard_count(hd, lo, hi);
+          if (ser_is_hard(hd, i) && nhw > 1) continue;
           if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
           if (!mh_decide_many(p, sm, wt, ps, taxon, is_taxon, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
@@ -905,7 +910,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
           for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
           __syncthreads();
           for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
-          if (tid == M) rebuild_hard(p, sm);
+          if (tid == M && nhw) rebuild_hard(p, sm);
           sc.counters[3]++;
         } else if (kind == 1 || kind == 3) {
           int i, j;
@@ -920,7 +925,8 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
             ps.k += 1;
             j = i + 1;
           }
-          if (ser_hard_count(hd, i, j) > 1) continue;
+          const int nhw = ser_hard_count(hd, i, j);
+          if (nhw > 1) continue;
           const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
           ps.k += 2;
           if (is_taxon) ser_pi2_delta(col, pre, C, a, b, i, j, inc1, inc2, &dt0, &dt1);
@@ -930,10 +936,11 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
             ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
           }
           if (is_col) ser_col_reverse(col, C, W, i, j, pre);
-          for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
-          __syncthreads();
-          for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
-          if (tid == M) rebuild_hard(p, sm);
+          for (int n = i + tid; 2 * n < i + j; n += C) {
+            const uint16_t t = sm.rpi[n];
+            sm.rpi[n] = sm.rpi[i + j - n]; sm.rpi[i + j - n] = t;
+          }
+          if (tid == M && nhw) rebuild_hard(p, sm);
           sc.counters[kind == 1 ? 4 : 5]++;
         } else {
           const int nfree = N - p.nh;
@@ -954,9 +961,10 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel_manycd(KParams p)
             ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
             ser_col_permute(col, C, W, g.i, g.j, sm.perm16, pre);
           }
-          for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
-          __syncthreads();
-          for (int n = g.i + tid; n <= g.j; n += C) sm.rpi[n] = sm.tmp16[n];
+          for (int n = g.i + tid; n <= g.j; n += C) {
+            const int m2 = sm.perm16[n];
+            if (m2 > n) { const uint16_t t = sm.rpi[n]; sm.rpi[n] = sm.rpi[m2]; sm.rpi[m2] = t; }
+          }
           sc.counters[6]++;
         }
         sc.t0a += D0; sc.f0a -= D0; sc.t1a += D1; sc.f1a -= D1;
