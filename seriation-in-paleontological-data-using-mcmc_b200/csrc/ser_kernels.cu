@@ -337,6 +337,20 @@ struct PropState { /* thread-uniform bookkeeping of the pi part */
   int buf;         /* reduction double-buffer index */
 };
 
+/* sum of the M per-taxon terms in taxon order (the reference's own order of additions).  One warp walks
+ * the dependent chain and publishes the result; the others wait at the barrier instead of issuing the same
+ * M additions (the kernel is issue-bound and shares the SM with other chains).  terms[] is published. */
+__device__ __forceinline__ double sequential_term_sum(const Smem &sm, int M)
+{
+  if (threadIdx.x < 32) {
+    double acc = 0.0;
+    for (int m = 0; m < M; m++) acc = SER_ADD(acc, sm.terms[m]);
+    if (threadIdx.x == 0) sm.draws_cd[7] = acc;
+  }
+  __syncthreads();
+  return sm.draws_cd[7];
+}
+
 /* block sum of three ints and one double behind one barrier (per-taxon c, d) */
 __device__ __forceinline__ void block_sum3d(int v0, int v1, int v2, double x, int *red, double *redd, int &buf, int *o0, int *o1,
                                             int *o2, double *ox)
@@ -383,7 +397,7 @@ __device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, cons
     __syncthreads(); /* terms[] may still be read from an earlier call */
     if (is_taxon) sm.terms[taxon] = ser_term(wt, dt0, dt1);
     __syncthreads();
-    for (int m = 0; m < p.M; m++) acc = SER_ADD(acc, sm.terms[m]);
+    acc = sequential_term_sum(sm, p.M);
     return acc;
   };
   if constexpr (MANY) {
@@ -651,9 +665,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           if (exact) { /* mcmc_logl's own order */
             if (is_taxon) sm.terms[taxon] = term;
             __syncthreads();
-            double acc = 0.0;
-            for (int m = 0; m < M; m++) acc = SER_ADD(acc, sm.terms[m]);
-            sc.loglik = acc;
+            sc.loglik = sequential_term_sum(sm, M);
           }
         }
       } else {
@@ -671,9 +683,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
                                         SER_MUL((double)f1, wt.c));
             }
             __syncthreads();
-            double acc = 0.0;
-            for (int m = 0; m < M; m++) acc = SER_ADD(acc, sm.terms[m]);
-            sc.loglik = acc;
+            sc.loglik = sequential_term_sum(sm, M);
           }
         }
       }
