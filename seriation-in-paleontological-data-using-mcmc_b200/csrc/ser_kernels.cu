@@ -61,7 +61,6 @@ struct KParams {
   uint16_t *gpre;           /* [slot][W+1][Cs] */
   const int *bgrp;          /* large-shape column groups: [g] = {first column, first item}, big_ng + 1 entries */
   int big_ng, big_icap, big_gcap;
-  double *gterms;           /* [slot][M] */
   int n_chains;
   uint16_t *ab;        /* [chain][2][Mpad] */
   uint16_t *rpi;       /* [chain][Npad] */
@@ -922,8 +921,12 @@ __device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &s
       terms[p.order[c]] = ser_term(wt, x0, x1);
     }
     __syncthreads();
-    for (int m = 0; m < p.M; m++) acc = SER_ADD(acc, terms[m]);
-    return acc;
+    if (threadIdx.x < 32) { /* one warp walks the dependent chain, the others wait (see sequential_term_sum) */
+      for (int m = 0; m < p.M; m++) acc = SER_ADD(acc, terms[m]);
+      if (threadIdx.x == 0) sm.draws_cd[7] = acc;
+    }
+    __syncthreads();
+    return sm.draws_cd[7];
   };
   double delta;
   bool seq = false;
@@ -948,7 +951,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
   const int tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, W = p.W, Cs = p.Cs;
   uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
   uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
-  double *TERMS = p.gterms + (size_t)blockIdx.x * M;
+  double *TERMS = sm.val; /* per-taxon terms of the exact sums: the item-weight buffer is idle outside the Gibbs phase (icap >= M) */
 
   for (int chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
     const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
@@ -1198,9 +1201,13 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
           sc.counters[2] += CH;
           if (exact) {
-            double acc = 0.0;
-            for (int m = 0; m < M; m++) acc = SER_ADD(acc, TERMS[m]);
-            sc.loglik = acc;
+            if (tid < 32) {
+              double acc = 0.0;
+              for (int m = 0; m < M; m++) acc = SER_ADD(acc, TERMS[m]);
+              if (tid == 0) sm.draws_cd[7] = acc;
+            }
+            __syncthreads();
+            sc.loglik = sm.draws_cd[7];
           }
         }
 
@@ -1636,7 +1643,6 @@ struct ser_run {
   uint32_t *d_gV;
   uint16_t *d_gpre;
   int *d_bgrp;
-  double *d_gterms;
   int initialized, have_tapes;
 };
 
@@ -1862,7 +1868,10 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
     long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32; /* val 8 + pos 2 bytes per item */
     icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);
-    if (icap < N + 1) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain before any item", fixed); return SER_E_ARG; }
+    if (icap < std::max(N + 1, M)) { /* one whole column, and the M per-taxon terms of the exact sums */
+      ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain before any item", fixed);
+      return SER_E_ARG;
+    }
     std::vector<int> bgrp;
     {
       int c0 = 0;
@@ -1890,8 +1899,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     const size_t sl = (size_t)run->big_slots;
     CUDA_TRY(POOL_ALLOC(&run->d_gV, sl * run->W * kp.Cs * sizeof(uint32_t)));
     CUDA_TRY(POOL_ALLOC(&run->d_gpre, sl * (run->W + 1) * kp.Cs * sizeof(uint16_t)));
-    CUDA_TRY(POOL_ALLOC(&run->d_gterms, sl * M * sizeof(double)));
-    kp.gV = run->d_gV; kp.gpre = run->d_gpre; kp.gterms = run->d_gterms;
+    kp.gV = run->d_gV; kp.gpre = run->d_gpre;
   }
   kp.n_chains = cfg->n_chains;
   *out = run;
@@ -1904,7 +1912,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   cudaSetDevice(run->cfg.device);
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
-                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp, run->d_gterms};
+                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   cudaStreamSynchronize(run->stream);
   cudaEventDestroy(run->ev_start); cudaEventDestroy(run->ev_stop);
