@@ -1,3 +1,6 @@
+"""Per-phase cycle shares of the large-shape sweep kernel on the 1024 x 4096 synthetic matrix.
+Needs a timing build:  NVCC_EXTRA=-DSER_PHASE_TIMING sh seriation-in-paleontological-data-using-mcmc_b200/build.sh
+(thread 0 of every CTA accumulates clock64() deltas between phase marks; rebuild without the flag afterwards)."""
 import sys, ctypes as C; sys.path.insert(0,'.')
 import seriation_b200 as S
 ds = S.Dataset.synthetic(1024, 4096, 16)
