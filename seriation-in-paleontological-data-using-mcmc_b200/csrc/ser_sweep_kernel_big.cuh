@@ -1,0 +1,473 @@
+/* ser_sweep_kernel_big.cuh -- the large-shape sweep kernel: persistent CTAs, columns in a global scratch slot, Gibbs phase staged through shared memory.
+ * Part of the single translation unit ser_kernels.cu (included there, in this order). */
+
+/* ------------------------------------------------------------------ the sweep kernel, large shapes
+ * Same algorithm and building blocks as ser_sweep_kernel, for matrices whose bit columns, prefix
+ * tables and item buffers exceed shared memory (e.g. 1024 sites x 4096 taxa: 0.7 MB + 0.3 MB +
+ * 3.2 MB per chain).  A CTA owns a slot of L2-resident global scratch and walks over chains
+ * (persistent grid); every thread owns the columns tid, tid+C, ...; a/b live in shared memory. */
+struct BigSmem {
+  double *draws_pi, *logdraw, *draws_cd, *H;
+  double *lmax; /* gcap: per column of the running group */
+  double *val;  /* icap: item weights / cumulative weights of the running group */
+  double *incl; /* gcap: inclusive chunk totals, one per (column, lane) unit of the running group */
+  int *red;
+  uint16_t *a16, *b16, *hp, *rpi, *tmp16, *perm16;
+  uint16_t *st4; /* 4 * gcap */
+  uint16_t *gones; /* gcap: ones of the running group's columns */
+  int *goff;       /* gcap: first item of each column relative to the group's first item */
+  uint16_t *pos; /* icap: postings of the running group's columns */
+};
+__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap)
+{
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  size_t o_dp = take(8 * SER_PI_DRAWS), o_ld = take(8 * SER_PI_DRAWS), o_dc = take(8 * 8), o_H = take(8 * (size_t)(N + 2));
+  size_t o_go = take(4 * (size_t)gcap), o_gn = take(2 * (size_t)gcap), o_lm = take(8 * (size_t)gcap), o_in = take(8 * (size_t)gcap), o_val = take(8 * (size_t)icap), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
+  size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)gcap), o_hp = take(2 * (size_t)(N + 1));
+  size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
+  if (s) {
+    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos); s->incl = (double *)(base + o_in);
+    s->goff = (int *)(base + o_go); s->gones = (uint16_t *)(base + o_gn);
+    s->draws_pi = (double *)(base + o_dp); s->logdraw = (double *)(base + o_ld); s->draws_cd = (double *)(base + o_dc);
+    s->H = (double *)(base + o_H); s->lmax = (double *)(base + o_lm); s->red = (int *)(base + o_r);
+    s->a16 = (uint16_t *)(base + o_a); s->b16 = (uint16_t *)(base + o_b); s->st4 = (uint16_t *)(base + o_st);
+    s->hp = (uint16_t *)(base + o_hp); s->rpi = (uint16_t *)(base + o_p); s->tmp16 = (uint16_t *)(base + o_q);
+    s->perm16 = (uint16_t *)(base + o_m);
+  }
+  return off;
+}
+
+/* MH tail for the large-shape kernel: the thread's deltas are already summed over its columns;
+ * the degenerate case re-evaluates the per-taxon deltas through `redo` (a lambda) */
+template <typename Redo>
+__device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &sm, const SerWeights &wt, PropState &ps,
+                                              double *terms, int dt0, int dt1, int nz, bool exact, int *D0, int *D1,
+                                              double *delta_out, Redo redo)
+{
+  int NZ;
+  block_sum3(dt0, dt1, nz, sm.red, ps.buf, D0, D1, &NZ);
+  auto reference_sum = [&]() { /* see mh_decide */
+    double acc = 0.0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.M; c += blockDim.x) {
+      int x0, x1;
+      redo(c, &x0, &x1);
+      terms[p.order[c]] = ser_term(wt, x0, x1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { /* one warp walks the dependent chain, the others wait (see sequential_term_sum) */
+      for (int m = 0; m < p.M; m++) acc = SER_ADD(acc, terms[m]);
+      if (threadIdx.x == 0) sm.draws_cd[7] = acc;
+    }
+    __syncthreads();
+    return sm.draws_cd[7];
+  };
+  double delta;
+  bool seq = false;
+  if (*D0 == 0 && *D1 == 0) {
+    delta = 0.0;
+    if (NZ) { delta = reference_sum(); seq = true; }
+  } else {
+    delta = ser_term(wt, *D0, *D1);
+  }
+  bool accept = delta >= 0.0;
+  if (!accept) accept = delta > sm.logdraw[ps.k++];
+  if (accept && exact && !seq && NZ) delta = reference_sum();
+  *delta_out = delta;
+  return accept;
+}
+
+__global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BigSmem sm;
+  big_layout(&sm, smem_raw, p.N, p.M, p.big_icap, p.big_gcap);
+  const int tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, W = p.W, Cs = p.Cs;
+  uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
+  uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
+  double *TERMS = sm.val; /* per-taxon terms of the exact sums: the item-weight buffer is idle outside the Gibbs phase (icap >= M) */
+
+  for (int chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
+    const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+    __syncthreads(); /* previous chain's state fully saved before the scratch is reused */
+    ChainScalars sc = p.scal[chain];
+    for (int n = tid; n < N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
+    for (int c = tid; c < M; c += C) {
+      sm.a16[c] = p.ab[(size_t)chain * 2 * p.Mpad + c];
+      sm.b16[c] = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c];
+    }
+    __syncthreads();
+    /* position-ordered columns + prefix tables of the owned columns */
+    for (int c = tid; c <= M; c += C) {
+      for (int w = 0; w < W; w++) {
+        uint32_t word = 0;
+        const int pend = min(32 * w + 32, N);
+        if (c < M) { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)cell(p, sm.rpi, pos, c) << (pos & 31); }
+        else { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)(p.hard[sm.rpi[pos]] != 0) << (pos & 31); }
+        V[w * Cs + c] = word;
+      }
+      ser_col_build_pre(V + c, PRE + c, Cs, W);
+      if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+    }
+    __syncthreads();
+
+    const double *tape = nullptr;
+    long long tape_len = 0;
+    if (p.mode == SER_MODE_REPLAY) {
+      tape = p.tape + p.tape_off[chain];
+      tape_len = (long long)(p.tape_off[chain + 1] - p.tape_off[chain]);
+    }
+    SerWeights wt;
+    wt.eps = p.eps; wt.H = sm.H; wt.hmax = 0;
+    set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+    SerHard hd;
+    hd.hcol = V + M; hd.hpre = PRE + M; hd.hp = sm.hp; hd.C = Cs; hd.W = W; hd.N = N; hd.nh = p.nh;
+    PropState ps;
+    ps.k = 0; ps.buf = 0;
+
+    for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
+      for (int s = 0; s < p.sweeps_per_call; s++) {
+        /* ================= stage this sweep's draws ================= */
+        __syncthreads();
+        PHASE_T0();
+        if (p.mode == SER_MODE_REPLAY) {
+          const long long need = sc.cursor + 6 + 2 * (long long)M;
+          if (need > tape_len) { sc.flags |= 1; break; }
+          if (tid < 6) sm.draws_cd[tid] = tape[sc.cursor + tid];
+          for (int t = tid; t < SER_PI_DRAWS; t += C) {
+            const long long idx = need + t;
+            const double u = idx < tape_len ? tape[idx] : 0.5;
+            sm.draws_pi[t] = u; sm.logdraw[t] = log(u);
+          }
+        } else {
+          if (tid < 4) {
+            const int cnt = tid == 0 ? sc.f1a : tid == 1 ? sc.t0a : tid == 2 ? sc.f0a : sc.t1a;
+            const double g = ser_gamma_ge1(1.0 + (double)cnt, p.seed, gchain, sc.sweep, (uint32_t)tid);
+            const double go = __shfl_xor_sync(0xfu, g, 1);
+            if (tid == 0 || tid == 2) {
+              const double y = ser_beta_from_gammas(g, go);
+              double val = tid == 0 ? sc.c : sc.d, l1m = tid == 0 ? sc.cc : sc.dd;
+              const double lo = tid == 0 ? SER_MINC : SER_MIND, hi = tid == 0 ? SER_MAXC : SER_MAXD;
+              if (y > 0.0) {
+                const double ly = ser_log(y);
+                if (lo <= ly && ly <= hi) { val = ly; l1m = ser_log(SER_SUB(1.0, ser_exp(ly))); }
+              }
+              sm.draws_cd[tid] = val; sm.draws_cd[tid + 1] = l1m;
+            }
+          }
+          for (int t = tid; t < SER_PI_DRAWS; t += C) {
+            const double u = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+            sm.draws_pi[t] = u; sm.logdraw[t] = log(ser_pos(u));
+          }
+        }
+        __syncthreads();
+        if (p.mode == SER_MODE_REPLAY) {
+          const double yc = sm.draws_cd[0], lyc = sm.draws_cd[1], l1c = sm.draws_cd[2];
+          const double yd = sm.draws_cd[3], lyd = sm.draws_cd[4], l1d = sm.draws_cd[5];
+          if (yc > 0.0 && SER_MINC <= lyc && lyc <= SER_MAXC) { sc.c = lyc; sc.cc = l1c; }
+          if (yd > 0.0 && SER_MIND <= lyd && lyd <= SER_MAXD) { sc.d = lyd; sc.dd = l1d; }
+        } else {
+          sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3];
+        }
+        set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+        sc.counters[0]++; sc.counters[1]++;
+        wt.hmax = ser_hmax(wt.g, N);
+        for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
+
+        /* ================= a/b Gibbs, item formulation, one column group at a time =================
+         * The group's postings and item weights live in shared memory (icap items), so the per-column
+         * loops run at shared-memory latency.  A column is served by `lpc` adjacent lanes (1..8, as many as
+         * the block can spare for the group), which split its loops: the maximum is a lane-strided partial
+         * maximum + shuffle, the cumulative weights are a per-lane serial sum over a contiguous chunk + a
+         * shuffle scan of the lane totals.  Per group: postings; then for the a-step and the b-step:
+         * geometry + maximum, run weights (dense over the group's items), scan + inverse CDF. */
+        int changed = 0;
+#pragma unroll 1
+        for (int g = 0; g < p.big_ng; g++) {
+          const int c0 = p.bgrp[2 * g], e0 = p.bgrp[2 * g + 1], c1 = p.bgrp[2 * g + 2], e1 = p.bgrp[2 * g + 3], nc = c1 - c0;
+          int lpc = 1, lsh = 0;
+          while (lpc < 8 && nc * lpc * 2 <= C) { lpc <<= 1; lsh++; }
+          const int units = nc << lsh, sub = tid & (lpc - 1);
+          __syncthreads(); /* previous group is done with pos / val; first group: publishes H */
+          PHASE_MARK(0);
+          { /* postings: a unit = (run of wq words, column), column fastest so that a warp reads 32
+             * consecutive columns of one word row; the prefix table gives the unit's first slot */
+            const int wq = (W + lpc - 1) >> lsh;
+            for (int u = tid; u < units; u += C) {
+              const int qq = u / nc, cl = u - qq * nc, c = c0 + cl, w0 = qq * wq, w1 = min(W, w0 + wq);
+              /* every load of the unit is issued before the first one is needed */
+              uint32_t vv[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) vv[k] = w0 + k < w1 ? V[(w0 + k) * Cs + c] : 0u;
+              const int first = w0 < w1 ? (int)PRE[w0 * Cs + c] : 0, off_c = p.off[c] - e0;
+              if (qq == 0) { sm.goff[cl] = off_c; sm.gones[cl] = (uint16_t)p.ones[c]; } /* the group's column table */
+              uint16_t *out = sm.pos + off_c + first;
+              for (int wb = w0; wb < w1; wb += 8) {
+                if (wb > w0) {
+#pragma unroll
+                  for (int k = 0; k < 8; k++) vv[k] = wb + k < w1 ? V[(wb + k) * Cs + c] : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                  uint32_t v = vv[k];
+                  while (v) { *out++ = (uint16_t)(32 * (wb + k) + SER_FFS(v) - 1); v &= v - 1u; }
+                }
+              }
+            }
+          }
+          __syncthreads();
+          PHASE_MARK(1);
+#pragma unroll 1
+          for (int step = 0; step < 2; step++) {
+            for (int ub = 0; ub < units; ub += C) { /* warp-uniform trip count: the shuffles need every lane */
+              const int u = ub + tid;
+              const bool live = u < units;
+              const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
+              const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
+                                           : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
+              const uint16_t *pos = sm.pos + sm.goff[cl];
+              double lm = -1.0e300;
+              if (live) { /* every item's log-weight stays in val for the dense pass */
+                double *Lc = sm.val + sm.goff[cl];
+                for (int kk = sub; kk <= st.kb; kk += lpc) {
+                  int q, n;
+                  const double L = ser_item_eval(wt, st, pos, kk, &q, &n);
+                  Lc[kk] = L;
+                  lm = ser_fmax(lm, L);
+                }
+              }
+              for (int o = lpc >> 1; o > 0; o >>= 1) lm = ser_fmax(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+              if (live && sub == 0) {
+                sm.lmax[cl] = lm;
+                *reinterpret_cast<uint2 *>(sm.st4 + 4 * cl) =
+                    make_uint2((uint32_t)st.cur | ((uint32_t)st.bound << 16), (uint32_t)st.ocur | ((uint32_t)st.kb << 16));
+              }
+            }
+            __syncthreads();
+            PHASE_MARK(2);
+            uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u; /* fetched one iteration ahead */
+            for (int e = e0 + tid; e < e1; e += C) {
+              const uint32_t ck = ck_next;
+              if (e + C < e1) ck_next = p.item_col[e + C];
+              const int cl = (int)(ck >> 16) - c0, kk = (int)(ck & 0xffffu);
+              const int kb = (int)sm.st4[4 * cl + 3];
+              if (kk <= kb) { /* log-weight -> run weight, in place; the run length from the postings */
+                const uint16_t *pos = sm.pos + (e - kk - e0);
+                const int nones = (int)sm.gones[cl], bound = (int)sm.st4[4 * cl + 1];
+                int q, qprev; /* ser_item_eval's q and qprev */
+                if (step) { q = kk < kb ? N - 1 - (int)pos[nones - 1 - kk] : bound; qprev = kk > 0 ? N - 1 - (int)pos[nones - kk] : -1; }
+                else { q = kk < kb ? (int)pos[kk] : bound; qprev = kk > 0 ? (int)pos[kk - 1] : -1; }
+                sm.val[e - e0] = ser_item_weight_cached<1>(wt, sm.val[e - e0], q - qprev, sm.lmax[cl]);
+              }
+            }
+            __syncthreads();
+            PHASE_MARK(3);
+            for (int ub = 0; ub < units; ub += C) { /* cumulative weights, chunk-relative: lane `sub` owns items [k0, k1) */
+              const int u = ub + tid;
+              const bool live = u < units;
+              const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
+              const int kb = (int)sm.st4[4 * cl + 3];
+              double *val = sm.val + sm.goff[cl];
+              const int chunk = (kb + lpc) >> lsh, k0 = min(kb + 1, sub * chunk), k1 = min(kb + 1, k0 + chunk);
+              double tot = 0.0;
+              if (live) for (int kk = k0; kk < k1; kk++) { tot = SER_ADD(tot, val[kk]); val[kk] = tot; }
+              /* inclusive totals of the chunks, added left to right so that incl[j] == incl[j-1] + (last
+               * relative prefix of chunk j) bit for bit */
+              double incl = tot;
+              for (int j = 1; j < lpc; j++) {
+                const double t = __shfl_sync(0xffffffffu, incl, (tid & ~(lpc - 1) & 31) + j - 1);
+                if (sub == j) incl = SER_ADD(t, tot);
+              }
+              if (live) sm.incl[u] = incl;
+            }
+            __syncthreads();
+            PHASE_MARK(7);
+            for (int cl = tid; cl < nc; cl += C) { /* inverse CDF: chunk, item inside the chunk, candidate inside the run */
+              const int c = c0 + cl;
+              const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
+              SerStep st;
+              st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = (int)(g4.y >> 16);
+              st.nones = sm.gones[cl]; st.N = N; st.rev = step;
+              const uint16_t *pos = sm.pos + sm.goff[cl];
+              const double *val = sm.val + sm.goff[cl], *incl = sm.incl + (cl << lsh);
+              const int taxon = p.order[c];
+              double uu;
+              if (p.mode == SER_MODE_REPLAY) uu = tape[sc.cursor + 6 + 2 * taxon + step];
+              else {
+                uint32_t o[4];
+                ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+                uu = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
+              }
+              const double target = SER_MUL(uu, incl[lpc - 1]);
+              int j = 0;
+              while (j < lpc - 1 && incl[j] < target) j++;
+              const double base = j ? incl[j - 1] : 0.0;
+              const int chunk = (st.kb + lpc) >> lsh, k0 = min(st.kb + 1, j * chunk), k1 = min(st.kb + 1, k0 + chunk);
+              int lo = k0, hi = k1 - 1; /* first item of the chunk whose cumulative weight reaches the target */
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
+              }
+              int q, n;
+              const double le = SER_SUB(ser_item_eval(wt, st, pos, lo, &q, &n), sm.lmax[cl]);
+              const int pick = q - n + 1 + ser_run_pick<1>(wt, n, le, lo > k0 ? SER_ADD(base, val[lo - 1]) : base, target);
+              if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
+              else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
+            }
+            __syncthreads(); /* the b-step's geometry is computed under a different column -> thread map */
+            PHASE_MARK(4);
+          }
+        }
+        __syncthreads();
+        const bool exact = p.sampling && s == p.sweeps_per_call - 1;
+        {
+          int t1 = 0, len = 0, T1, LEN, CH;
+          for (int c = tid; c < M; c += C) {
+            const int t1c = ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), lenc = sm.b16[c] - sm.a16[c];
+            t1 += t1c; len += lenc;
+            if (exact) { /* mcmc_logl's per-taxon term, mcmc.c:643-644 */
+              const int f1 = p.ones[c] - t1c, f0 = lenc - t1c, t0 = N - lenc - f1;
+              TERMS[p.order[c]] = SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)t0, wt.cc), SER_MUL((double)f0, wt.d)), SER_MUL((double)t1c, wt.dd)),
+                                          SER_MUL((double)f1, wt.c));
+            }
+          }
+          block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
+          totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
+          sc.counters[2] += CH;
+          if (exact) {
+            if (tid < 32) {
+              double acc = 0.0;
+              for (int m = 0; m < M; m++) acc = SER_ADD(acc, TERMS[m]);
+              if (tid == 0) sm.draws_cd[7] = acc;
+            }
+            __syncthreads();
+            sc.loglik = sm.draws_cd[7];
+          }
+        }
+
+        PHASE_MARK(5);
+        /* ================= 16 proposals for pi ================= */
+        ps.k = 0;
+        for (int prop = 0; prop < 16; prop++) {
+          const int kind = prop == 0 ? 3 : ((prop - 1) % 3);
+          int dt0 = 0, dt1 = 0, nz = 0, D0, D1;
+          double delta;
+          if (kind == 0) { /* pi1 */
+            const int i = ser_draw_int(sm.draws_pi[ps.k], N);
+            int j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+            ps.k += 2;
+            if (j >= i) j++;
+            const int lo = min(i, j), hi = max(i, j);
+            if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
+            auto redo = [&](int c, int *x0, int *x1) { ser_pi1_delta(V + c, Cs, sm.a16[c], sm.b16[c], i, j, x0, x1); };
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
+            for (int c = tid; c <= M; c += C) {
+              if (c < M) { int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b; }
+              ser_col_rotate(V + c, Cs, W, i, j, PRE + c);
+              if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+            }
+            for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
+            __syncthreads();
+            for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
+            sc.counters[3]++;
+          } else if (kind == 1 || kind == 3) { /* pi2 */
+            int i, j;
+            if (kind == 1) {
+              i = ser_draw_int(sm.draws_pi[ps.k], N);
+              j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
+              ps.k += 2;
+              if (j >= i) j++;
+              else { const int t = i; i = j; j = t; }
+            } else {
+              i = ser_draw_int(sm.draws_pi[ps.k], N - 1);
+              ps.k += 1;
+              j = i + 1;
+            }
+            if (ser_hard_count(hd, i, j) > 1) continue;
+            const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+            ps.k += 2;
+            auto redo = [&](int c, int *x0, int *x1) { ser_pi2_delta(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c], i, j, inc1, inc2, x0, x1); };
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
+            for (int c = tid; c <= M; c += C) {
+              if (c < M) {
+                int a = sm.a16[c], b = sm.b16[c];
+                const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
+                ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
+                sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
+              }
+              ser_col_reverse(V + c, Cs, W, i, j, PRE + c);
+              if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+            }
+            for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
+            __syncthreads();
+            for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
+            sc.counters[kind == 1 ? 4 : 5]++;
+          } else { /* pi3 */
+            const int nfree = N - p.nh;
+            if (nfree < 2) continue;
+            const int r1 = ser_draw_int(sm.draws_pi[ps.k], nfree), r2 = ser_draw_int(sm.draws_pi[ps.k + 1], nfree - 1);
+            ps.k += 2;
+            int ir, jr;
+            if (r1 <= r2) { ir = r1; jr = r2 + 1; } else { ir = r2; jr = r1; }
+            const SerPi3 g = ser_pi3_window(hd, ir, jr);
+            const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
+            ps.k += 2;
+            auto redo = [&](int c, int *x0, int *x1) { ser_pi3_delta(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1); };
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
+            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
+            for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
+            __syncthreads();
+            for (int c = tid; c < M; c += C) {
+              int a = sm.a16[c], b = sm.b16[c];
+              const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
+              ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
+              sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
+              ser_col_permute(V + c, Cs, W, g.i, g.j, sm.perm16, PRE + c);
+            }
+            for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
+            __syncthreads();
+            for (int n = g.i + tid; n <= g.j; n += C) sm.rpi[n] = sm.tmp16[n];
+            sc.counters[6]++;
+          }
+          sc.t0a += D0; sc.f0a -= D0; sc.t1a += D1; sc.f1a -= D1;
+          sc.loglik = SER_ADD(sc.loglik, delta);
+          __syncthreads();
+        }
+
+        if (p.mode == SER_MODE_REPLAY) sc.cursor += 6 + 2 * (long long)M + ps.k;
+        else sc.sweep++;
+        sc.counters[7]++;
+        PHASE_MARK(6);
+      }
+      if (sc.flags & 1) break;
+
+      if (p.sampling) {
+        const int sidx = sc.n_samples;
+        if (sidx < p.max_samples) {
+          const size_t row = (size_t)chain * p.max_samples + sidx;
+          if (p.store >= SER_STORE_PI)
+            for (int pos = tid; pos < N; pos += C) p.samp_pi[row * N + sm.rpi[pos]] = (uint16_t)pos;
+          if (p.store >= SER_STORE_FULL) {
+            for (int c = tid; c < M; c += C) { p.samp_a[row * M + p.order[c]] = sm.a16[c]; p.samp_b[row * M + p.order[c]] = sm.b16[c]; }
+            if (tid == 0) { p.samp_cdl[row * 3 + 0] = sc.c; p.samp_cdl[row * 3 + 1] = sc.d; p.samp_cdl[row * 3 + 2] = sc.loglik; }
+          }
+        }
+        sc.sum_negll = SER_ADD(sc.sum_negll, -sc.loglik);
+        sc.sum_ec = SER_ADD(sc.sum_ec, exp(sc.c));
+        sc.sum_ed = SER_ADD(sc.sum_ed, exp(sc.d));
+        sc.n_samples++;
+      }
+    }
+
+    __syncthreads();
+    for (int c = tid; c < M; c += C) {
+      p.ab[(size_t)chain * 2 * p.Mpad + c] = sm.a16[c];
+      p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c] = sm.b16[c];
+    }
+    for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
+    if (tid == 0) p.scal[chain] = sc;
+  }
+}

@@ -17,7 +17,8 @@ def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kernel, "100000"], capture_output=True, text=True).stdout.split("\n")
     print(txt[0])
-    ranges = {f: func_ranges(os.path.join(CS, f)) for f in ("ser_chain_core.h", "ser_kernels.cu", "ser_detmath.h")}
+    ranges = {f: func_ranges(os.path.join(CS, f)) for f in ("ser_chain_core.h", "ser_kernels.cu", "ser_detmath.h", "ser_device_common.cuh", "ser_sweep_kernel.cuh",
+                                                                     "ser_sweep_kernel_big.cuh", "ser_aux_kernels.cuh")}
     agg = {}
     for ln in txt[1:]:
         m = re.match(r"\s*([\d.]+)% inst\s+([\d.]+)% stall\s+(\S+):(\d+)", ln)
