@@ -149,3 +149,38 @@ def test_posterior_summary_finalisers_match_script_semantics(S, oracle_mod):
     assert np.allclose(got_a, oracle_mod.exp_a(a_s, k), rtol=0, atol=1e-12)
     clean = S.carry_over_mean([p.sum(axis=0) for p in pis], k, keep_total=False, faithful=False)
     assert np.allclose(clean, sum(p.sum(axis=0) for p in pis) / 1000 / k)
+
+
+def test_probability_map_finalisers_match_script_semantics(S, oracle_mod):
+    """taxa_occurence_ / false_taxa_occurence_ / false_ones_probability_matrix (script.py:306-448) from per-chain
+    alive counts: the host finalisers (carry-over, E[pi] / E[a] reordering) against the numpy restatements
+    that are pinned to the unmodified script.py.  The device reductions are replaced by numpy here."""
+    rng = np.random.default_rng(17)
+    N, M, T, k = 23, 13, 40, 3
+    X = (rng.random((N, M)) < 0.3).astype(np.uint8)
+    pis = [np.array([rng.permutation(N) for _ in range(T)]) for _ in range(k)]
+    a_s = [rng.integers(0, N // 2, size=(T, M)) for _ in range(k)]
+    b_s = [a + rng.integers(0, N // 2, size=(T, M)) for a in a_s]
+
+    class FakeRun:
+        N, M = 23, 13
+        ds = S.Dataset.from_bits(X)
+
+        def alive_counts(self, chosen):
+            j = np.arange(N)[None, :, None]
+            return np.stack([((j >= a_s[c][:, None, :]) & (j <= b_s[c][:, None, :])).sum(axis=0) for c in chosen]).astype(np.int32), T
+
+        def posterior_sums(self, chosen, with_ab=False):
+            out = dict(corr_num=np.array([int((pis[c] * np.arange(N)).sum()) for c in chosen]), n_samples=T,
+                       pi_sum=np.stack([pis[c].sum(axis=0) for c in chosen]))
+            if with_ab:
+                out.update(a_sum=np.stack([a_s[c].sum(axis=0) for c in chosen]), b_sum=np.stack([b_s[c].sum(axis=0) for c in chosen]))
+            return out
+
+    batch = S.ChainBatch(FakeRun(), 0, T)
+    chains = [0, 1, 2]
+    assert np.allclose(S.taxa_occurence_probability_matrix(batch, chains, k), oracle_mod.alive_matrix(a_s, b_s, pis, k), rtol=0, atol=1e-13)
+    assert np.allclose(S.false_taxa_occurence_probability_matrix(batch, chains, k), oracle_mod.false_taxa_matrix(a_s, b_s, pis, k), rtol=0, atol=1e-13)
+    assert np.allclose(S.false_ones_probability_matrix(batch, chains, k), oracle_mod.false_ones_matrix(a_s, b_s, pis, k, X), rtol=0, atol=1e-13)
+    Y = S.new_data_matrix(batch, chains, k)
+    assert Y.shape == (N, M) and Y.sum() == X.sum()
