@@ -108,6 +108,29 @@ static void mark_launch(ser_run *run)
   run->launches++;
 }
 
+/* Every kernel with dynamic shared memory may use up to the sm_100 opt-in maximum.  The attribute is a
+ * property of the FUNCTION (not of a run): sized per run it would be lowered by the next run of a smaller
+ * dataset and make the launches of a live larger one fail, so it is set to the maximum once and the launches
+ * pass each run's own size. */
+#define SER_SMEM_OPTIN (227 * 1024)
+#define SER_SMEM_DYN_MAX (SER_SMEM_OPTIN - 1024) /* the sweep kernels hold 1 KB of static shared memory */
+static cudaError_t allow_max_dynamic_smem(void)
+{
+  cudaError_t e = cudaSuccess;
+  auto allow = [&](const void *f) { /* static + dynamic shared memory share the opt-in limit */
+    cudaFuncAttributes fa;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, f);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_SMEM_OPTIN - (int)fa.sharedSizeBytes);
+  };
+  allow((const void *)ser_init_kernel);
+  allow((const void *)ser_sweep_kernel<1024, 1, false>);
+  allow((const void *)ser_sweep_kernel<384, 2, false>);
+  allow((const void *)ser_sweep_kernel<1024, 1, true>);
+  allow((const void *)ser_sweep_kernel<384, 2, true>);
+  allow((const void *)ser_sweep_kernel_big);
+  return e;
+}
+
 /* Column groups of the Gibbs step: the item weights of a step go through a buffer of Ival doubles,
  * one group of columns at a time.  Fewer, larger groups = fewer barriers; a smaller buffer = more
  * resident chains per SM (measured on B200: +15-20 % per extra resident CTA, -4 % per extra group).
@@ -127,10 +150,9 @@ static int choose_groups(KParams &kp, const std::vector<int> &off, int M, int N,
         ival = std::max(ival, ge[ng] - ge[ng - 1]);
       }
     const size_t sz = smem_layout(nullptr, nullptr, N, W, C, kp.I, manycd, ival);
-    if (sz > 227 * 1024) continue;
+    if (sz > SER_SMEM_DYN_MAX) continue;
     int occ = 0;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, C, sz) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, C, sz) != cudaSuccess) {
       ser_set_error("ser_run_create: occupancy query failed: %s", cudaGetErrorString(cudaGetLastError()));
       return SER_E_CUDA;
     }
@@ -256,21 +278,19 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
 
   run->smem_small = aux_layout(nullptr, nullptr, N);
   run->smem_init = run->smem_small + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
-  CUDA_TRY(cudaFuncSetAttribute(ser_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_init));
+  CUDA_TRY(allow_max_dynamic_smem());
   if (cfg->manycd) {
     run->smem_many = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I, 1);
     /* the per-taxon kernel needs its 80 registers (2.7 M vs 2.5 M sweeps/s on g2s2 with 64): size the
      * groups for the instantiation that will run */
-    if (!run->big && run->smem_many <= 227 * 1024 &&
+    if (!run->big && run->smem_many <= SER_SMEM_DYN_MAX &&
         (run->C <= 384 ? choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<384, 2, true>, &run->smem_many)
                        : choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<1024, 1, true>, &run->smem_many)))
       return SER_E_ARG;
-    if (run->big || run->smem_many > 227 * 1024) {
+    if (run->big || run->smem_many > SER_SMEM_DYN_MAX) {
       ser_set_error("ser_run_create: manycd=1 needs one thread per taxon and %zu B of shared memory per chain (M <= 1023)", run->smem_many);
       return SER_E_ARG;
     }
-    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_many));
-    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<384, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_many));
     int occ64 = 0, occ85 = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel<1024, 1, true>, run->C, run->smem_many));
     if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel<384, 2, true>, run->C, run->smem_many));
@@ -278,13 +298,11 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   }
   if (!run->big) {
     run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
-    if (run->smem_sweep > 227 * 1024) run->big = 1; /* columns + items do not fit: use the L2-resident variant */
+    if (run->smem_sweep > SER_SMEM_DYN_MAX) run->big = 1; /* columns + items do not fit: use the L2-resident variant */
     else {
       /* two register budgets: 64 regs (any block size) and 85 regs (blocks <= 384 threads, two of
        * them resident); take the one with more resident CTAs, the roomier one on a tie */
       if (!cfg->manycd && choose_groups(kp, off, M, N, run->W, run->C, 0, ser_sweep_kernel<1024, 1, false>, &run->smem_sweep)) return SER_E_ARG;
-      CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<1024, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
-      CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel<384, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_sweep));
       int occ64 = 0, occ85 = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel<1024, 1, false>, run->C, run->smem_sweep));
       if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel<384, 2, false>, run->C, run->smem_sweep));
@@ -296,7 +314,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     /* column groups of the Gibbs phase: as many items as the shared-memory budget holds
      * (SER_BIG_SMEM_KB, default 220), at most 1024 columns, never splitting a column */
     int budget_kb = 220;
-    if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(227, atoi(v)));
+    if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(224, atoi(v)));
     const int gcap = std::max(std::min(M, 1024), run->big_threads); /* also bounds (columns x lanes per column) */
     const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
     long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32; /* val 8 + pos 2 bytes per item */
@@ -322,8 +340,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     CUDA_TRY(cudaStreamSynchronize(run->stream));
     kp.bgrp = run->d_bgrp;
     run->smem_big = big_layout(nullptr, nullptr, N, M, (int)icap, gcap);
-    if (run->smem_big > 227 * 1024) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_big); return SER_E_ARG; }
-    CUDA_TRY(cudaFuncSetAttribute(ser_sweep_kernel_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)run->smem_big));
+    if (run->smem_big > SER_SMEM_DYN_MAX) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_big); return SER_E_ARG; }
     int per_sm = 1, n_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big, run->big_threads, run->smem_big));
     CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));

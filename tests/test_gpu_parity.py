@@ -722,3 +722,21 @@ def test_column_groups_are_invisible(S, oracle_mod, monkeypatch, groups):
     X, hard = load_hex_dataset("g5s5")
     _replay_case(S, oracle_mod, X, hard, [5, 6], 3, 3)
     _manycd_replay_case(S, oracle_mod, X, hard, [7], 2, 2)
+
+
+def test_live_runs_of_different_shapes_interleave(S):
+    """The dynamic shared-memory opt-in belongs to the kernel function, not to a run: a second run on a
+    smaller dataset must not break the launches of a live run on a larger one (and vice versa)."""
+    runs = []
+    for name in ("g2s2", "g10s10", "g5s5"):
+        X, hard = load_hex_dataset(name)
+        runs.append(S.Run(S.Dataset.from_bits(X, hard), 8, seed=5).init())
+    Xm, hm = load_hex_dataset("g10s10")
+    runs.append(S.Run(S.Dataset.from_bits(Xm, hm), 4, seed=5, manycd=True).init())
+    for _ in range(2):
+        for r in runs:
+            r.advance(1, True)
+    for r in runs:
+        r.sync()
+        assert r.check() == 0
+        r.close()
