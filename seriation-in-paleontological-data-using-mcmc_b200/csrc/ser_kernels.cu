@@ -280,29 +280,36 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   run->smem_init = run->smem_small + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
   CUDA_TRY(allow_max_dynamic_smem());
   if (cfg->manycd) {
-    run->smem_many = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I, 1);
-    /* the per-taxon kernel needs its 80 registers (2.7 M vs 2.5 M sweeps/s on g2s2 with 64): size the
-     * groups for the instantiation that will run */
-    if (!run->big && run->smem_many <= SER_SMEM_DYN_MAX &&
-        (run->C <= 384 ? choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<384, 2, true>, &run->smem_many)
-                       : choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<1024, 1, true>, &run->smem_many)))
-      return SER_E_ARG;
-    if (run->big || run->smem_many > SER_SMEM_DYN_MAX) {
-      ser_set_error("ser_run_create: manycd=1 needs one thread per taxon and %zu B of shared memory per chain (M <= 1023)", run->smem_many);
+    /* per-taxon c, d: one thread per taxon, columns and postings in shared memory -- there is no large-shape
+     * variant.  The per-taxon kernel needs its 80 registers (2.7 M vs 2.5 M sweeps/s on g2s2 with 64): the
+     * groups are sized for the instantiation that will run. */
+    int rc = SER_E_ARG;
+    if (!run->big)
+      rc = run->C <= 384 ? choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<384, 2, true>, &run->smem_many)
+                         : choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<1024, 1, true>, &run->smem_many);
+    if (rc == SER_E_CUDA) return rc;
+    if (rc != SER_OK) {
+      ser_set_error("ser_run_create: manycd=1 needs one thread per taxon (M <= 1023) and the chain's columns and postings in "
+                    "shared memory (%zu B here, at most %d)", smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I, 1, N + 1), SER_SMEM_DYN_MAX);
       return SER_E_ARG;
     }
     int occ64 = 0, occ85 = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel<1024, 1, true>, run->C, run->smem_many));
     if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel<384, 2, true>, run->C, run->smem_many));
     run->variant_many = (occ85 >= occ64 && occ85 > 0) ? 1 : 0;
-  }
-  if (!run->big) {
-    run->smem_sweep = smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I);
-    if (run->smem_sweep > SER_SMEM_DYN_MAX) run->big = 1; /* columns + items do not fit: use the L2-resident variant */
+    run->big = 0;
+  } else if (!run->big) {
+    /* one thread per column while the columns, postings and one group's item weights fit shared memory
+     * (SER_PREFER_BIG=1: only while ALL item weights fit, the pre-grouping rule); else the large-shape kernel */
+    const bool prefer_big = getenv("SER_PREFER_BIG") && atoi(getenv("SER_PREFER_BIG")) != 0;
+    int rc = SER_E_ARG;
+    if (!prefer_big || smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I) <= SER_SMEM_DYN_MAX)
+      rc = choose_groups(kp, off, M, N, run->W, run->C, 0, ser_sweep_kernel<1024, 1, false>, &run->smem_sweep);
+    if (rc == SER_E_CUDA) return rc;
+    if (rc != SER_OK) run->big = 1;
     else {
-      /* two register budgets: 64 regs (any block size) and 85 regs (blocks <= 384 threads, two of
+      /* two register budgets: 64 regs (any block size) and 80 regs (blocks <= 384 threads, two of
        * them resident); take the one with more resident CTAs, the roomier one on a tie */
-      if (!cfg->manycd && choose_groups(kp, off, M, N, run->W, run->C, 0, ser_sweep_kernel<1024, 1, false>, &run->smem_sweep)) return SER_E_ARG;
       int occ64 = 0, occ85 = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel<1024, 1, false>, run->C, run->smem_sweep));
       if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel<384, 2, false>, run->C, run->smem_sweep));
