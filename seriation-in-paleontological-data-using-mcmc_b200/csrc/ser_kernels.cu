@@ -207,6 +207,13 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
   /* initial c, d and the flooring constant with the HOST libm: the bits the reference gets */
   kp.c0 = log(.01); kp.d0 = log(.3);
   kp.cc0 = log(1. - exp(kp.c0)); kp.dd0 = log(1. - exp(kp.d0));
+  if (cfg->mode == SER_MODE_FREE) {
+    /* free-running chains derive log(1 - e^c) with the bit-reproducible log / exp everywhere, also for the
+     * initial values (a d that never moves keeps this companion for the whole run): what the oracle's
+     * reproduction of the stream evaluates.  Replay keeps the host libm's bits, i.e. the reference's. */
+    kp.cc0 = ser_log(SER_SUB(1.0, ser_exp(kp.c0)));
+    kp.dd0 = ser_log(SER_SUB(1.0, ser_exp(kp.d0)));
+  }
   kp.eps = exp(-32.236191301916641); /* exp(LOGEPSILON), mcmc.h:26 */
 
   /* Columns = taxa sorted by number of occurrences (descending), so that the threads of a warp

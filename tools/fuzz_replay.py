@@ -1,6 +1,7 @@
 """Randomised differential test on the GPU box: random shapes / densities / hard-site counts / seeds, every
 case replayed through the three sweep kernels (one thread per column, per-taxon c/d, large-shape with a random
-block size and group-buffer budget) and compared bit for bit with the oracle on the same tape.
+block size and group-buffer budget) and compared bit for bit with the oracle on the same tape; then three free-running variants against the oracle
+reproducing the Philox stream (detmath).
 
     python tools/fuzz_replay.py [cases=60] [seed=1]      -> gpurun_out/fuzz_replay.json
 """
@@ -91,7 +92,40 @@ def main():
                     os.environ.pop(k, None)
             if bad:
                 failures.append(dict(case=case, variant=name, N=N, M=M, density=dens, nh=nh, seed=seed, env=env, bad=[str(b) for b in bad[:6]]))
-    out = dict(cases=cases, variants_per_case=4, failures=failures, refused=log, passed=not failures)
+        # free-running mode: the oracle reproduces the GPU's Philox stream bit for bit (detmath)
+        for name, env, manycd in (("free", {}, False), ("free-manycd", {}, True), ("free-big", {"SER_FORCE_BIG": "128"}, False)):
+            for k, v in env.items():
+                os.environ[k] = v
+            try:
+                fseed, gid = int(rng.integers(0, 1 << 31)), int(rng.integers(0, 70000))
+                o = O.Oracle(X, hard)
+                if manycd:
+                    o.manycd()
+                o.source_philox(fseed, gid).detmath(True)
+                o.randomize()
+                for _ in range(3):
+                    o.sample()
+                want = o.state()
+                run = S.Run(ds, 1, seed=fseed, chain_offset=gid, manycd=manycd)
+                run.init().advance(1, False).advance(2, True).sync()
+                got = run.state(0)
+                bad = [k for k in ("a", "b", "pi", "tot") if not np.array_equal(got[k], getattr(want, k))]
+                if got["loglik"] != want.loglik:
+                    bad.append("loglik")
+                if manycd and run.cd(0)[0].tobytes() != want.c_all.tobytes():
+                    bad.append("cd")
+                if run.check() != 0:
+                    bad.append("check")
+                run.close()
+            except S.SeriationError as e:
+                bad = [] if ("manycd" in str(e) or "shared memory" in str(e)) else [("error", str(e))]
+                log.append(dict(case=case, variant=name, refused=str(e)))
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+            if bad:
+                failures.append(dict(case=case, variant=name, N=N, M=M, density=dens, nh=nh, bad=[str(b_) for b_ in bad[:6]]))
+    out = dict(cases=cases, variants_per_case=7, failures=failures, refused=log, passed=not failures)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "fuzz_replay.json"), "w") as f:
         json.dump(out, f, indent=1)
