@@ -86,3 +86,21 @@ def test_emulator_edge_shapes(oracle_mod, emul, shape):
 def test_emulator_now_subsets(oracle_mod, emul, name, sweeps):
     X, hard = load_hex_dataset(name)
     _run_case(oracle_mod, emul, X, hard, 9, sweeps)
+
+
+def test_emulator_random_shapes_and_densities(oracle_mod, emul):
+    """The fuzz generator of tools/fuzz_replay.py on the CPU: random shapes, densities up to 95 %, all-zero /
+    full columns, 0..N hard sites -- the kernel's building blocks against the oracle, sweep by sweep."""
+    rng = np.random.default_rng(2024)
+    for _ in range(25):
+        N, M = int(rng.integers(2, 160)), int(rng.integers(1, 120))
+        dens = float(rng.choice([0.02, 0.1, 0.3, 0.6, 0.95]))
+        X = (rng.random((N, M)) < dens).astype(np.uint8)
+        if rng.random() < 0.3:
+            X[:, rng.integers(0, M)] = 0
+        if rng.random() < 0.2:
+            X[:, rng.integers(0, M)] = 1
+        nh = int(rng.choice([0, 1, 2, min(N, 7), N - 1, N]))
+        hard = np.zeros(N, np.uint8)
+        hard[rng.choice(N, size=min(nh, N), replace=False)] = 1
+        _run_case(oracle_mod, emul, X, hard, int(rng.integers(0, 1 << 30)), 12)
