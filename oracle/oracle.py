@@ -8,8 +8,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
   the GSL-API shim (present when built in a container that has
   ``/root/reference``; the prebuilt binary travels to the GPU box).
 
-It also restates, in numpy, the two cross-chain steps of ``script.py``
-(``choose_chains`` :70-99 and ``compute_pair_order_matrix`` :155-189).
+It also restates, in numpy, the analysis side of ``script.py``: ``choose_chains`` :70-99,
+``compute_exp_cd`` :102-126, ``compute_exp_ages`` :129-152, ``compute_pair_order_matrix`` :155-189,
+``compute_exp_pi`` / ``compute_exp_a`` :230-276 and the three probability maps :306-448.
+Parity status of these restatements: PINNED -- ``tests/golden/script_g10s10.npz`` holds the outputs of the
+unmodified ``script.py`` (imported here by ``tools/make_golden_script.py``) and
+``tests/test_oracle_golden.py`` compares every one of them.
 """
 from __future__ import annotations
 
