@@ -10,6 +10,8 @@
  * requires bit-identical a, b, pi, rpi, counts, c, d and loglik after every
  * mcmc_sample() call and after every sub-sampler call; committed fixtures under
  * tests/golden/ hold the same comparison for boxes without /root/reference.
+ * The per-taxon c, d variant (manycd = 1) is pinned the same way (ref_mcmc trace ... manycd,
+ * tests/golden/ref_g10s10_manycd.npz).  Unpinned: GSL's MT19937 stream itself (no GSL here).
  */
 #ifndef SERIATION_ORACLE_H
 #define SERIATION_ORACLE_H
