@@ -25,8 +25,10 @@
  *   ser_run_posterior_sums    compute_exp_ages / compute_exp_pi / compute_exp_a
  *                                                       script.py:129-152, :230-276
  *   ser_run_alive_counts      plot_taxa_occurence_probability_matrix / plot_false_*  script.py:306-448
+ *   ser_run_site_age_corr     CORR_MN of Docs/Report.pdf Table 1 (E[pi] against the .sites MN ages)
  *   run_all_chains' Pool(8) over 100 processes (script.py:48-67) is replaced by
- *   n_chains in ser_run_config: one CTA per chain in one launch.
+ *   n_chains in ser_run_config: one persistent launch over all chains of a GPU, and by
+ *   ser_multi_* / ser_comm_*: the chains of one call sharded over the GPUs of a box.
  */
 #ifndef SERIATION_B200_H
 #define SERIATION_B200_H
@@ -63,6 +65,7 @@ typedef struct ser_dataset ser_dataset;
 typedef struct ser_run ser_run;
 
 typedef struct ser_run_config {
+  uint32_t struct_size;    /* = sizeof(ser_run_config): ser_run_create refuses a caller built against another layout */
   int32_t n_chains;        /* chains simulated by THIS process / device                        */
   int32_t chain_offset;    /* global id of local chain 0 (sharding across ranks)              */
   int32_t sweeps_per_call; /* sweeps per thinned sample; the reference hard-codes 10           */
@@ -105,6 +108,9 @@ int ser_run_init(ser_run *run);
 /* n_calls x sweeps_per_call sweeps on every chain; if `sampling` a thinned sample is emitted
  * (and the exp_data sums advanced) after every call.  Asynchronous on the run's stream. */
 int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling);
+/* burn-in calls followed by sampling calls in ONE launch (main's two loops, mcmc.c:140-143 + :180-185):
+ * the persistent grid balances (chain, call) work items over the SMs across both phases */
+int ser_run_advance_both(ser_run *run, int32_t burn_calls, int32_t sample_calls);
 int ser_run_sync(ser_run *run);
 /* CUDA-event time of all kernels launched by this run since creation / last reset, in ms */
 int ser_run_elapsed_ms(ser_run *run, double *ms, int32_t reset);
@@ -173,6 +179,69 @@ int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32_t k, int64
  * The counts behind plot_taxa_occurence_probability_matrix, plot_false_taxa_occurence_probability
  * and plot_false_ones_probability (script.py:306-448): alive, T - alive, X * (T - alive). */
 int ser_run_alive_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *alive, int32_t *n_samples);
+
+/* CORR_MN (Docs/Report.pdf Table 1): Pearson correlation of the posterior mean
+ * position E[pi(site)] over the stored samples of the chosen chains owned by this run with the MN age
+ * of the site read from the .sites file (ser_dataset_read_names): the mean over the stored samples of
+ * pearsonr(pi_t, x) -- compute_exp_ages (script.py:129-152) with the real chronology in place of the file
+ * order -- averaged over the chosen chains this run owns.  sum_t pi_t is reduced on the device (the
+ * posterior kernel); every site needs an age.  corr_age: x = -age_ma ("older = earlier position" is
+ * positive, like the report), corr_mn: x = the integer MN unit.  Host doubles; needs SER_STORE_PI. */
+int ser_run_site_age_corr(ser_run *run, const ser_dataset *ds, const int32_t *chosen, int32_t k, double *corr_age,
+                          double *corr_mn, int32_t *n_sites_used);
+
+/* ---------------------------------------------------------------- cross-chain step, one call
+ * E[-logL] of every chain -> (all-gather) -> choose_chains(k) -> pair-order counts of the chosen chains
+ * -> (all-reduce), enqueued back to back on the run's stream: no host synchronisation between the
+ * kernels and the collectives.  comm == NULL: this run holds all the chains.  With a communicator the
+ * chains of rank r are the global ids [r * n_chains, (r+1) * n_chains) (every rank the same n_chains).
+ * ser_run_cross_chain_async only enqueues; ser_run_cross_chain_result waits and copies to the host:
+ * chosen[k] (GLOBAL ids, ascending, -1 padded), counts [k][N][N] (may be NULL).
+ * Replaces script.py:70-99 + :155-189 over the chains of run_all_chains (:48-67). */
+typedef struct ser_comm ser_comm;
+int ser_run_cross_chain_async(ser_run *run, ser_comm *comm, int32_t k);
+int ser_run_cross_chain_result(ser_run *run, int32_t *chosen, int32_t *n_chosen, double *min_out, double *sigma_out,
+                               int32_t *counts);
+/* device-side results of the last ser_run_cross_chain_async (valid until the next one / destroy):
+ * d_e_all [n_total] doubles, d_chosen [k] ints, d_info [3] doubles, d_counts [k][N][N] ints */
+int ser_run_cross_chain_buffers(ser_run *run, double **d_e_all, int32_t **d_chosen, double **d_info, int32_t **d_counts);
+
+/* ---------------------------------------------------------------- multi-GPU, one process per GPU
+ * NCCL communicator owned by the library (libnccl.so.2 is loaded on first use).  Rank 0 makes the
+ * id, the launcher (torchrun / MPI / a file) broadcasts its SER_COMM_ID_BYTES bytes, every rank
+ * calls ser_comm_create.  The collectives of ser_run_cross_chain_async run on the run's stream. */
+#define SER_COMM_ID_BYTES 128
+int ser_comm_unique_id(uint8_t id[SER_COMM_ID_BYTES]);
+int ser_comm_create(const uint8_t id[SER_COMM_ID_BYTES], int32_t n_ranks, int32_t rank, int32_t device, ser_comm **out);
+int ser_comm_info(const ser_comm *comm, int32_t *n_ranks, int32_t *rank);
+void ser_comm_destroy(ser_comm *comm);
+
+/* ---------------------------------------------------------------- multi-GPU, one process for the box
+ * run_all_chains' Pool (script.py:48-67) as ONE call over n_gpus devices: cfg->n_chains is the TOTAL,
+ * chains are sharded in contiguous blocks by global id (cfg->chain_offset = id of the first), one host
+ * thread drives all devices asynchronously.  The cross-chain step needs no collective library when the
+ * devices have peer access (NVLink / NVSwitch): ser_stats kernels store their E[-logL] slice straight
+ * into every peer's gather buffer, every device runs the same selection, and the owner of a chosen
+ * chain stores its pair-order slab straight into every peer's count buffer; cross-device ordering by
+ * CUDA events only.  Without peer access (or SER_MULTI_NCCL=1) the same step runs over
+ * ncclCommInitAll communicators.  devices == NULL: 0 .. n_gpus-1. */
+typedef struct ser_multi ser_multi;
+int ser_multi_create(const ser_dataset *ds, const ser_run_config *cfg, int32_t n_gpus, const int32_t *devices, ser_multi **out);
+void ser_multi_destroy(ser_multi *m);
+int ser_multi_init(ser_multi *m);
+int ser_multi_advance(ser_multi *m, int32_t burn_calls, int32_t sample_calls);
+int ser_multi_sync(ser_multi *m);
+/* max over the devices of the CUDA-event time of the kernels launched since creation / last reset */
+int ser_multi_elapsed_ms(ser_multi *m, double *ms, int32_t reset);
+int ser_multi_layout(const ser_multi *m, int32_t *n_gpus, int32_t *chains_per_gpu, int32_t *uses_peer_stores);
+/* the run that owns a GLOBAL chain id, and the chain's local index there (for ser_run_get_state, the writers, ...) */
+int ser_multi_locate(ser_multi *m, int32_t global_chain, ser_run **run, int32_t *local_chain);
+int ser_multi_check(ser_multi *m, int32_t *n_bad);
+/* per chain (global order): mean(-loglik), mean(exp c), mean(exp d); host arrays of n_chains doubles (may be NULL) */
+int ser_multi_chain_stats(ser_multi *m, double *e_negloglik, double *e_c, double *e_d, int32_t *n_samples);
+/* the whole cross-chain step; results as ser_run_cross_chain_result */
+int ser_multi_cross_chain(ser_multi *m, int32_t k, int32_t *chosen, int32_t *n_chosen, double *min_out, double *sigma_out,
+                          int32_t *counts);
 
 /* ---------------------------------------------------------------- reference-compatible files */
 /* Writes Chains-style files for one local chain into `dir` (which must exist, like the

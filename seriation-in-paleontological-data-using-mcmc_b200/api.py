@@ -28,7 +28,7 @@ class SeriationError(RuntimeError):
 
 
 class RunConfig(C.Structure):
-    _fields_ = [("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("sweeps_per_call", C.c_int32),
+    _fields_ = [("struct_size", C.c_uint32), ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("sweeps_per_call", C.c_int32),
                 ("mode", C.c_int32), ("seed", C.c_uint32), ("store", C.c_int32), ("max_samples", C.c_int32),
                 ("device", C.c_int32), ("manycd", C.c_int32)]
 
@@ -54,6 +54,7 @@ SYMBOLS = [
     ("ser_run_set_tapes", C.c_int, [_vp, _dp, _u64p]),
     ("ser_run_init", C.c_int, [_vp]),
     ("ser_run_advance", C.c_int, [_vp, C.c_int32, C.c_int32]),
+    ("ser_run_advance_both", C.c_int, [_vp, C.c_int32, C.c_int32]),
     ("ser_run_sync", C.c_int, [_vp]),
     ("ser_run_elapsed_ms", C.c_int, [_vp, _dp, C.c_int32]),
     ("ser_run_kernel_launches", C.c_int, [_vp, _i64p]),
@@ -76,7 +77,27 @@ SYMBOLS = [
     ("ser_write_chain_files", C.c_int, [_vp, C.c_int32, C.c_char_p]),
     ("ser_write_labelled_files", C.c_int, [_vp, C.c_int32, _vp, C.c_char_p]),
     ("ser_microbench", C.c_int, [C.c_int32, _dp]),
+    ("ser_run_site_age_corr", C.c_int, [_vp, _vp, _i32p, C.c_int32, _dp, _dp, _i32p]),
+    ("ser_run_cross_chain_async", C.c_int, [_vp, _vp, C.c_int32]),
+    ("ser_run_cross_chain_result", C.c_int, [_vp, _i32p, _i32p, _dp, _dp, _i32p]),
+    ("ser_run_cross_chain_buffers", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    ("ser_comm_unique_id", C.c_int, [_u8p]),
+    ("ser_comm_create", C.c_int, [_u8p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    ("ser_comm_info", C.c_int, [_vp, _i32p, _i32p]),
+    ("ser_comm_destroy", None, [_vp]),
+    ("ser_multi_create", C.c_int, [_vp, C.POINTER(RunConfig), C.c_int32, _i32p, C.POINTER(_vp)]),
+    ("ser_multi_destroy", None, [_vp]),
+    ("ser_multi_init", C.c_int, [_vp]),
+    ("ser_multi_advance", C.c_int, [_vp, C.c_int32, C.c_int32]),
+    ("ser_multi_sync", C.c_int, [_vp]),
+    ("ser_multi_elapsed_ms", C.c_int, [_vp, _dp, C.c_int32]),
+    ("ser_multi_layout", C.c_int, [_vp, _i32p, _i32p, _i32p]),
+    ("ser_multi_locate", C.c_int, [_vp, C.c_int32, C.POINTER(_vp), _i32p]),
+    ("ser_multi_check", C.c_int, [_vp, _i32p]),
+    ("ser_multi_chain_stats", C.c_int, [_vp, _dp, _dp, _dp, _i32p]),
+    ("ser_multi_cross_chain", C.c_int, [_vp, C.c_int32, _i32p, _i32p, _dp, _dp, _i32p]),
 ]
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -176,7 +197,8 @@ class Run:
         self.ds = ds
         self.N, self.M, self.n_chains = ds.N, ds.M, n_chains
         self.manycd = bool(manycd)
-        self.cfg = RunConfig(n_chains, chain_offset, sweeps_per_call, mode, seed, store, max_samples, device, int(self.manycd))
+        self.cfg = RunConfig(C.sizeof(RunConfig), n_chains, chain_offset, sweeps_per_call, mode, seed, store, max_samples, device,
+                             int(self.manycd))
         h = _vp()
         _check(lib().ser_run_create(ds._h, C.byref(self.cfg), C.byref(h)))
         self._h = h
@@ -202,6 +224,11 @@ class Run:
 
     def advance(self, n_calls: int, sampling: bool):
         _check(lib().ser_run_advance(self._h, n_calls, int(sampling)))
+        return self
+
+    def advance_both(self, burn_calls: int, sample_calls: int):
+        """burn-in calls, then sampling calls, in one launch (main's two loops, mcmc.c:140-143 + :180-185)"""
+        _check(lib().ser_run_advance_both(self._h, burn_calls, sample_calls))
         return self
 
     def sync(self):
@@ -307,11 +334,144 @@ class Run:
     def po_counts_device(self, chosen_ptr: int, k: int, counts_ptr: int):
         _check(lib().ser_run_po_counts_device(self._h, chosen_ptr, k, counts_ptr))
 
+    def cross_chain_async(self, k: int, comm=None):
+        """E[-logL] -> (all-gather) -> choose_chains(k) -> pair-order counts -> (all-reduce), enqueued on the
+        run's stream without any host synchronisation; ``comm``: a Comm when the chains are sharded over ranks"""
+        _check(lib().ser_run_cross_chain_async(self._h, comm._h if comm is not None else None, k))
+        self._cc_k = k
+        return self
+
+    def cross_chain_result(self, with_counts: bool = True):
+        k = self._cc_k
+        chosen, n = np.empty(k, np.int32), C.c_int32()
+        mn, sd = C.c_double(), C.c_double()
+        counts = np.empty((k, self.N, self.N), np.int32) if with_counts else None
+        _check(lib().ser_run_cross_chain_result(self._h, _p(chosen, C.c_int32), C.byref(n), C.byref(mn), C.byref(sd),
+                                                _p(counts, C.c_int32)))
+        return dict(chosen=chosen[:n.value].copy(), min=mn.value, sigma=sd.value, counts=counts)
+
+    def cross_chain(self, k: int, comm=None, with_counts: bool = True):
+        return self.cross_chain_async(k, comm).cross_chain_result(with_counts)
+
+    def site_age_corr(self, chosen):
+        """CORR_MN: mean over the stored samples of pearsonr(pi_t, x), x = -age_ma and x = MN unit of the
+        .sites file (the dataset needs read_names); returns (corr_age, corr_mn)"""
+        chosen = np.ascontiguousarray(chosen, dtype=np.int32)
+        ca, cm, n = C.c_double(), C.c_double(), C.c_int32()
+        _check(lib().ser_run_site_age_corr(self._h, self.ds._h, _p(chosen, C.c_int32), len(chosen), C.byref(ca), C.byref(cm), C.byref(n)))
+        return ca.value, cm.value
+
     def write_chain_files(self, chain: int, directory: str):
         _check(lib().ser_write_chain_files(self._h, chain, directory.encode()))
 
     def write_labelled_files(self, chain: int, directory: str):
         _check(lib().ser_write_labelled_files(self._h, chain, self.ds._h, directory.encode()))
+
+
+class _BorrowedRun(Run):
+    """a ser_run owned by a Multi (never destroyed from Python)"""
+
+    def __init__(self, handle, ds, n_chains, manycd):
+        self._h, self.ds, self.N, self.M, self.n_chains, self.manycd = handle, ds, ds.N, ds.M, n_chains, manycd
+
+    def close(self):
+        self._h = None
+
+    __del__ = close
+
+
+class Comm:
+    """NCCL communicator of one rank (one process per GPU).  ``Comm.unique_id()`` on rank 0, broadcast the 128
+    bytes with whatever launched the ranks (torch.distributed, MPI, a file), then ``Comm(id, n_ranks, rank, device)``."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        _check(lib().ser_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, uid: bytes, n_ranks: int, rank: int, device: int = 0):
+        assert len(uid) == COMM_ID_BYTES
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(uid)
+        h = _vp()
+        _check(lib().ser_comm_create(buf, n_ranks, rank, device, C.byref(h)))
+        self._h, self.n_ranks, self.rank = h, n_ranks, rank
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ser_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Multi:
+    """All chains of one call sharded over the GPUs of one box by ONE process (run_all_chains' Pool, script.py:48-67)."""
+
+    def __init__(self, ds: Dataset, n_chains: int, n_gpus: int, *, seed=0, chain_offset=0, sweeps_per_call=10, store=STORE_PI,
+                 max_samples=0, manycd=False, devices=None):
+        self.ds, self.N, self.M, self.n_chains, self.n_gpus, self.first = ds, ds.N, ds.M, n_chains, n_gpus, chain_offset
+        self.manycd = bool(manycd)
+        cfg = RunConfig(C.sizeof(RunConfig), n_chains, chain_offset, sweeps_per_call, MODE_FREE, seed, store, max_samples, 0, int(self.manycd))
+        dev = np.ascontiguousarray(devices, dtype=np.int32) if devices is not None else None
+        h = _vp()
+        _check(lib().ser_multi_create(ds._h, C.byref(cfg), n_gpus, _p(dev, C.c_int32), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ser_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def init(self):
+        _check(lib().ser_multi_init(self._h))
+        return self
+
+    def advance(self, burn_calls: int, sample_calls: int):
+        _check(lib().ser_multi_advance(self._h, burn_calls, sample_calls))
+        return self
+
+    def sync(self):
+        _check(lib().ser_multi_sync(self._h))
+        return self
+
+    def elapsed_ms(self, reset=False) -> float:
+        ms = C.c_double()
+        _check(lib().ser_multi_elapsed_ms(self._h, C.byref(ms), int(reset)))
+        return ms.value
+
+    def layout(self) -> dict:
+        n, per, peer = C.c_int32(), np.zeros(8, np.int32), C.c_int32()
+        _check(lib().ser_multi_layout(self._h, C.byref(n), _p(per, C.c_int32), C.byref(peer)))
+        return dict(n_gpus=n.value, chains_per_gpu=per[:n.value].tolist(), peer_stores=bool(peer.value))
+
+    def locate(self, global_chain: int):
+        """(Run view, local chain index) of a global chain id"""
+        h, loc = _vp(), C.c_int32()
+        _check(lib().ser_multi_locate(self._h, global_chain, C.byref(h), C.byref(loc)))
+        return _BorrowedRun(h, self.ds, self.n_chains, self.manycd), loc.value
+
+    def check(self) -> int:
+        bad = C.c_int32()
+        rc = lib().ser_multi_check(self._h, C.byref(bad))
+        if rc not in (0, -7):
+            _check(rc)
+        return bad.value
+
+    def chain_stats(self):
+        e, c, d = (np.empty(self.n_chains) for _ in range(3))
+        n = C.c_int32()
+        _check(lib().ser_multi_chain_stats(self._h, _p(e, C.c_double), _p(c, C.c_double), _p(d, C.c_double), C.byref(n)))
+        return dict(e_negloglik=e, e_c=c, e_d=d, n_samples=n.value)
+
+    def cross_chain(self, k: int, with_counts: bool = True):
+        chosen, n = np.empty(k, np.int32), C.c_int32()
+        mn, sd = C.c_double(), C.c_double()
+        counts = np.empty((k, self.N, self.N), np.int32) if with_counts else None
+        _check(lib().ser_multi_cross_chain(self._h, k, _p(chosen, C.c_int32), C.byref(n), C.byref(mn), C.byref(sd), _p(counts, C.c_int32)))
+        return dict(chosen=chosen[:n.value].copy(), min=mn.value, sigma=sd.value, counts=counts)
 
 
 def select_chains(e_negloglik, k: int):
@@ -389,12 +549,15 @@ def compute_pair_order_matrix(batch: ChainBatch, chains, chains_selected: int, s
     return po_finalize(counts, chains_selected, faithful)
 
 
-def compute_exp_cd(batch: ChainBatch, chains, chains_selected: int):
-    """script.py:102-126: mean over the chosen chains of the per-chain means of exp(c), exp(d)
-    (divided by ``chains_selected``, as the reference does)."""
+def compute_exp_cd(batch: ChainBatch, chains, chains_selected: int, faithful: bool = True):
+    """script.py:102-126: per chosen chain the sum over its samples of exp(c), exp(d) divided by the LITERAL 1000
+    (:119-120; like compute_exp_ages / _pi / _a and exp_data.csv -- equal to the mean only for the reference's
+    1000 samples), summed over the chains and divided by ``chains_selected``.  ``faithful=False`` divides by the
+    number of samples actually taken."""
     st = batch.stats()
-    return (float(np.sum(st["e_c"][list(chains)]) / chains_selected),
-            float(np.sum(st["e_d"][list(chains)]) / chains_selected))
+    scale = st["n_samples"] / 1000 if faithful else 1.0
+    return (float(np.sum(st["e_c"][list(chains)]) * scale / chains_selected),
+            float(np.sum(st["e_d"][list(chains)]) * scale / chains_selected))
 
 
 def pearson_from_corr_num(corr_num, n_samples: int, n_sites: int):
@@ -485,39 +648,3 @@ def new_data_matrix(batch: ChainBatch, chains, chains_selected: int, dataset=Non
     ds = batch.run.ds if dataset is None else (dataset if isinstance(dataset, Dataset) else Dataset.read_txt(str(dataset)))
     return _reorder_like_script(ds.arrays()[0].astype(np.float64), compute_exp_pi(batch, chains, None, chains_selected, faithful),
                                 compute_exp_a(batch, chains, chains_selected, None, faithful))
-
-
-# ------------------------------------------------------------------------------------------------
-# multi-rank cross-chain step (host buffers; any torch.distributed backend)
-def cross_chain_distributed(e_local, k: int, po_counts_fn, n_sites: int, chains_selected: int | None = None,
-                            faithful: bool = True):
-    """Selection + pair-order matrix when the chains are sharded over ranks.
-
-    ``e_local``: this rank's E[-logL] (global chain id = rank * len(e_local) + i);
-    ``po_counts_fn(chosen_global_ids) -> int32 [k][N][N]`` fills the slabs of the chains this rank
-    owns and leaves the others zero (Run.po_counts does exactly that).
-    The exchange is what the path needs and nothing more: one all-gather of 8 bytes per chain, one
-    all-reduce(sum) of the count slabs.  Without an initialised process group it degrades to the
-    single-rank case.  Returns (chosen global ids, po matrix)."""
-    import torch
-    import torch.distributed as dist
-    e_local = np.ascontiguousarray(e_local, dtype=np.float64)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        world = dist.get_world_size()
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        mine = torch.from_numpy(e_local).to(dev)
-        allv = torch.empty(world * e_local.size, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allv, mine)
-        e_all = allv.cpu().numpy()
-    else:
-        dev, e_all = "cpu", e_local
-    chosen, _, _ = select_chains(e_all, k)
-    padded = np.full(k, -1, np.int32)
-    padded[:len(chosen)] = chosen
-    counts = np.ascontiguousarray(po_counts_fn(padded), dtype=np.int32)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        t = torch.from_numpy(counts).to(dev)
-        dist.all_reduce(t)
-        counts = t.cpu().numpy()
-    po = po_finalize(counts[:max(1, len(chosen))], chains_selected or k, faithful) if len(chosen) else np.zeros((n_sites, n_sites))
-    return [int(c) for c in chosen], po

@@ -83,15 +83,27 @@ __global__ void ser_check_kernel(KParams p, int *bad_count)
     if (t0a != sc.t0a || f0a != sc.f0a || t1a != sc.t1a || f1a != sc.f1a || fabs(ll - sc.loglik) > 1e-8 + 1e-12 * fabs(ll)) s_flags |= 16;
     const int fl = s_flags | (sc.flags & 1);
     if (fl) atomicAdd(bad_count, 1);
-    p.scal[chain].flags = (sc.flags & 1) | fl;
+    p.scal[chain].flags = (sc.flags & (1 | SER_FLAG_COLUMNS)) | fl;
   }
 }
 
 /* ------------------------------------------------------------------ cross-chain kernels */
-__global__ void ser_stats_kernel(const ChainScalars *scal, int n, double *out)
+/* Destinations of a cross-chain kernel: the same buffer on this device and, for the single-process multi-GPU
+ * path (ser_multi.cuh), on every peer device -- the kernel's stores ARE the all-gather (NVLink peer stores). */
+#define SER_MAX_PEERS 8
+struct PeerPtrs {
+  void *p[SER_MAX_PEERS];
+  int n;
+};
+
+/* E[-logL] of every local chain (compute_exp_data / print_exp_data, mcmc.c:53-67, divided by the samples taken),
+ * written at dst[offset + chain] of every destination */
+__global__ void ser_stats_kernel(const ChainScalars *scal, int n, PeerPtrs dst, int offset)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = scal[i].n_samples > 0 ? scal[i].sum_negll / (double)scal[i].n_samples : 0.0;
+  if (i >= n) return;
+  const double v = scal[i].n_samples > 0 ? scal[i].sum_negll / (double)scal[i].n_samples : 0.0;
+  for (int q = 0; q < dst.n; q++) ((double *)dst.p[q])[offset + i] = v;
 }
 
 __device__ double block_reduce_d(double v, double *sh, int op) /* 0 sum, 1 min */
@@ -169,27 +181,64 @@ __global__ void ser_select_kernel(const double *e, int n, int k, int *chosen, do
   }
 }
 
-/* pair-order counts (script.py:178-189) for one chosen chain per blockIdx.z */
-__global__ void ser_po_kernel(const uint16_t *samp_pi, int N, int max_samples, int n_samples, const int *chosen,
-                              int chain_offset, int n_local, int *counts)
+/* samples of a chain that the store holds */
+__device__ __forceinline__ int stored_samples(const ChainScalars *scal, int local, int max_samples)
+{
+  const int n = scal[local].n_samples;
+  return n < max_samples ? n : max_samples;
+}
+
+/* pair-order counts (script.py:178-189) for one chosen chain per blockIdx.z: a 32 x 32 tile of (i, j) per
+ * block, the positions of the tile's 64 sites staged through shared memory 32 samples at a time (coalesced
+ * rows of the sample store).  T = the CHOSEN chain's own sample count.  Only the owner of a chosen chain
+ * writes its slab -- to every destination (peer stores: the slabs are disjoint, so no reduction is needed). */
+#define SER_PO_TS 32
+__global__ void __launch_bounds__(256) ser_po_kernel(const uint16_t *samp_pi, const ChainScalars *scal, int N, int max_samples,
+                                                      const int *chosen, int chain_offset, int n_local, PeerPtrs dst)
 {
   const int g = chosen[blockIdx.z];
   if (g < chain_offset || g >= chain_offset + n_local) return;
-  const int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N || j >= N) return;
+  const int T = stored_samples(scal, g - chain_offset, max_samples);
+  __shared__ uint16_t si[SER_PO_TS][32], sj[SER_PO_TS][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; /* 32 x 8 threads; thread (tx, ty) owns j = j0+tx, i = i0+ty+8r */
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const uint16_t *pi = samp_pi + (size_t)(g - chain_offset) * max_samples * N;
-  int c = 0;
-  for (int t = 0; t < n_samples; t++) c += pi[(size_t)t * N + i] < pi[(size_t)t * N + j];
-  counts[((size_t)blockIdx.z * N + i) * N + j] = (i == j) ? -n_samples : c;
+  int c[4] = {0, 0, 0, 0};
+  for (int t0 = 0; t0 < T; t0 += SER_PO_TS) {
+    const int nt = min(SER_PO_TS, T - t0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < nt * 32; q += 256) {
+      const int t = q >> 5, x = q & 31;
+      si[t][x] = i0 + x < N ? pi[(size_t)(t0 + t) * N + i0 + x] : (uint16_t)0;
+      sj[t][x] = j0 + x < N ? pi[(size_t)(t0 + t) * N + j0 + x] : (uint16_t)0;
+    }
+    __syncthreads();
+    for (int t = 0; t < nt; t++) {
+      const int pj = sj[t][tx];
+#pragma unroll
+      for (int r = 0; r < 4; r++) c[r] += (int)si[t][ty + 8 * r] < pj;
+    }
+  }
+  const int j = j0 + tx;
+  if (j >= N) return;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int i = i0 + ty + 8 * r;
+    if (i >= N) continue;
+    const int v = (i == j) ? -T : c[r];
+    for (int q = 0; q < dst.n; q++) ((int *)dst.p[q])[((size_t)blockIdx.z * N + i) * N + j] = v;
+  }
 }
 
 /* posterior sums over the stored samples of one chosen chain per block (script.py:129-152, :230-276) */
-__global__ void ser_posterior_kernel(const uint16_t *samp_pi, const uint16_t *samp_a, const uint16_t *samp_b, int N, int M,
-                                     int max_samples, int n_samples, const int *chosen, int chain_offset, int n_local,
-                                     long long *corr_num, int *pi_sum, int *a_sum, int *b_sum)
+__global__ void ser_posterior_kernel(const uint16_t *samp_pi, const uint16_t *samp_a, const uint16_t *samp_b, const ChainScalars *scal,
+                                     int N, int M, int max_samples, const int *chosen, int chain_offset, int n_local,
+                                     long long *corr_num, int *pi_sum, int *a_sum, int *b_sum, int *n_out)
 {
   const int g = chosen[blockIdx.x];
   if (g < chain_offset || g >= chain_offset + n_local) return;
+  const int n_samples = stored_samples(scal, g - chain_offset, max_samples);
+  if (threadIdx.x == 0 && n_out) n_out[blockIdx.x] = n_samples;
   const size_t base = (size_t)(g - chain_offset) * max_samples;
   long long s = 0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -211,11 +260,13 @@ __global__ void ser_posterior_kernel(const uint16_t *samp_pi, const uint16_t *sa
 /* alive[c][j][m] = #{t : a_t(m) <= j <= b_t(m)} over the stored samples of chosen chain c
  * (script.py:321-329; closed at b, as the reference tests it).  One thread per taxon: +1 / -1
  * marks at a and b+1 in its own column of the slab, then a running sum down the positions. */
-__global__ void ser_alive_kernel(const uint16_t *samp_a, const uint16_t *samp_b, int N, int M, int max_samples, int n_samples,
-                                 const int *chosen, int chain_offset, int n_local, int *alive)
+__global__ void ser_alive_kernel(const uint16_t *samp_a, const uint16_t *samp_b, const ChainScalars *scal, int N, int M, int max_samples,
+                                 const int *chosen, int chain_offset, int n_local, int *alive, int *n_out)
 {
   const int g = chosen[blockIdx.x];
   if (g < chain_offset || g >= chain_offset + n_local) return;
+  const int n_samples = stored_samples(scal, g - chain_offset, max_samples);
+  if (blockIdx.y == 0 && threadIdx.x == 0 && n_out) n_out[blockIdx.x] = n_samples;
   const int m = blockIdx.y * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const size_t base = (size_t)(g - chain_offset) * max_samples;

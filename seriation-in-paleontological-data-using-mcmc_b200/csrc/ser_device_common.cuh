@@ -2,7 +2,7 @@
  * Part of the single translation unit ser_kernels.cu (included there, in this order). */
 
 /* ------------------------------------------------------------------ per-chain global state */
-struct ChainScalars {
+struct __align__(16) ChainScalars { /* a multiple of 16 bytes: loaded / stored as int4 words */
   double c, cc, d, dd; /* log P(false 1), log(1-e^c), log P(false 0), log(1-e^d) */
   double loglik;
   double sum_negll, sum_ec, sum_ed; /* compute_exp_data, mcmc.c:53-58 */
@@ -11,9 +11,12 @@ struct ChainScalars {
   int t0a, f0a, t1a, f1a;
   unsigned int sweep; /* free-running: sweep index = Philox counter word */
   int n_samples;
-  int flags; /* bit0 tape exhausted, bit1.. consistency failures */
+  int flags; /* bit0 tape exhausted, bits 1-4 consistency failures (ser_check_kernel), bit5 bit columns stored in gVc */
   int pad;
+  long long pad2;
 };
+static_assert(sizeof(ChainScalars) % 16 == 0, "ChainScalars is moved as int4 words");
+#define SER_FLAG_COLUMNS 32
 
 struct KParams {
   int N, M, W, C, nh, Mw, Npad, Mpad;
@@ -38,7 +41,14 @@ struct KParams {
   unsigned int seed;
   const double *tape;
   const unsigned long long *tape_off;
-  int n_calls, sweeps_per_call, sampling;
+  int n_calls, sweeps_per_call;
+  int burn_calls;           /* calls [0, burn_calls) of a launch are burn-in, the rest emit a thinned sample each */
+  /* persistent work-queue grid (ser_sweep_kernel): items = chunks of chunk_calls calls of one chain */
+  unsigned int n_items, chunk_base; /* items of this launch; done[chain] before the launch */
+  int chunk_calls;
+  uint32_t *gVc;            /* [chain][W][C] bit columns carried between work items */
+  unsigned int *queue;      /* next item */
+  unsigned int *done;       /* [chain] items completed since init */
   int store, max_samples;
   uint16_t *samp_a, *samp_b, *samp_pi;
   double *samp_cdl;

@@ -377,10 +377,12 @@ int ser_write_chain_files(ser_run *run, int32_t chain, const char *dir)
   const int many = ser_run_is_manycd(run);
   double *call = NULL, *dall = NULL, *fc = NULL, *fd = NULL;
   FILE *f = NULL;
+  if (!a || !b || !pi || !c || !d || !ll || !fa || !fb || !fpi) { ser_set_error("ser_write_chain_files: out of memory"); rc = SER_E_ARG; goto done; }
   rc = ser_run_fetch_samples(run, chain, a, b, pi, c, d, ll, &ns);
   if (!rc && many) {
     call = (double *)malloc((size_t)(ns ? ns : 1) * M * 8); dall = (double *)malloc((size_t)(ns ? ns : 1) * M * 8);
     fc = (double *)malloc((size_t)M * 8); fd = (double *)malloc((size_t)M * 8);
+    if (!call || !dall || !fc || !fd) { ser_set_error("ser_write_chain_files: out of memory"); rc = SER_E_ARG; goto done; }
     rc = ser_run_fetch_cd_samples(run, chain, call, dall, NULL);
     if (!rc) rc = ser_run_get_cd(run, chain, fc, fd);
   }
@@ -450,6 +452,7 @@ int ser_write_labelled_files(ser_run *run, int32_t chain, const ser_dataset *ds,
   if (ds->N != N || ds->M != M) { ser_set_error("ser_write_labelled_files: dataset does not match the run"); return SER_E_ARG; }
   if (!ds->taxon_names || !ds->site_names) { ser_set_error("ser_write_labelled_files: no labels loaded (ser_dataset_read_names)"); return SER_E_STATE; }
   int32_t *a = (int32_t *)malloc((size_t)M * 4), *b = (int32_t *)malloc((size_t)M * 4), *pi = (int32_t *)malloc((size_t)N * 4);
+  if (!a || !b || !pi) { free(a); free(b); free(pi); ser_set_error("ser_write_labelled_files: out of memory"); return SER_E_ARG; }
   int rc = ser_run_get_state(run, chain, a, b, pi, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
   if (!rc) {
     snprintf(path, sizeof(path), "%s/taxa_named.csv", dir);
@@ -471,5 +474,59 @@ int ser_write_labelled_files(ser_run *run, int32_t chain, const ser_dataset *ds,
     }
   }
   free(a); free(b); free(pi);
+  return rc;
+}
+
+/* ------------------------------------------------------------------ CORR_MN against the .sites ages
+ * Docs/Report.pdf Table 1 reports the correlation of the sampled site order with the MN chronology; the
+ * reference's compute_exp_ages (script.py:129-152) uses the FILE order as a stand-in for it (the files list the
+ * sites oldest first).  Here the .sites columns are used: the mean over the stored samples of
+ * pearsonr(pi_t, x) for x = MN unit and x = -age.  pi_t is a permutation of 0..N-1 (mean (N-1)/2, variance
+ * (N^2-1)/12), so the mean over samples follows exactly from sum_t pi_t(i), which the posterior kernel reduces
+ * on the device:  mean_t r_t = sum_i (x_i - xbar) (pi_sum_i / T - (N-1)/2) / (N sd_pi sd_x). */
+int ser_run_site_age_corr(ser_run *run, const ser_dataset *ds, const int32_t *chosen, int32_t k, double *corr_age, double *corr_mn,
+                          int32_t *n_sites_used)
+{
+  int32_t N, M, nh, nc, T = 0, first;
+  if (!run || !ds || !chosen || k < 1) { ser_set_error("ser_run_site_age_corr: bad argument"); return SER_E_ARG; }
+  ser_run_dims(run, &N, &M, &nh, &nc);
+  first = ser_run_chain_offset(run);
+  if (ds->N != N) { ser_set_error("ser_run_site_age_corr: dataset does not match the run"); return SER_E_ARG; }
+  if (!ds->site_age || !ds->site_mn) { ser_set_error("ser_run_site_age_corr: no site ages loaded (ser_dataset_read_names with a .sites file)"); return SER_E_STATE; }
+  for (int32_t n = 0; n < N; n++)
+    if (!(ds->site_age[n] > 0.0)) { ser_set_error("ser_run_site_age_corr: site %d has no age", n); return SER_E_STATE; }
+  int64_t *corr = (int64_t *)calloc((size_t)k, sizeof(int64_t));
+  int32_t *pis = (int32_t *)calloc((size_t)k * N, sizeof(int32_t));
+  if (!corr || !pis) { free(corr); free(pis); ser_set_error("ser_run_site_age_corr: out of memory"); return SER_E_ARG; }
+  int rc = ser_run_posterior_sums(run, chosen, k, corr, pis, NULL, NULL, &T);
+  if (!rc && T < 1) { ser_set_error("ser_run_site_age_corr: no stored samples"); rc = SER_E_STATE; }
+  if (!rc) {
+    double mean_age = 0.0, mean_mn = 0.0, var_age = 0.0, var_mn = 0.0, sum_age = 0.0, sum_mn = 0.0;
+    const double mean_pi = ((double)N - 1.0) / 2.0, sd_pi = sqrt(((double)N * N - 1.0) / 12.0);
+    int owned = 0;
+    for (int32_t n = 0; n < N; n++) { mean_age += ds->site_age[n]; mean_mn += ds->site_mn[n]; }
+    mean_age /= N; mean_mn /= N;
+    for (int32_t n = 0; n < N; n++) {
+      var_age += (ds->site_age[n] - mean_age) * (ds->site_age[n] - mean_age);
+      var_mn += (ds->site_mn[n] - mean_mn) * (ds->site_mn[n] - mean_mn);
+    }
+    var_age /= N; var_mn /= N;
+    for (int32_t c = 0; c < k; c++) {
+      if (chosen[c] < first || chosen[c] >= first + nc) continue; /* owned by another rank, or -1 */
+      owned++;
+      for (int32_t n = 0; n < N; n++) {
+        const double dp = (double)pis[(size_t)c * N + n] / T - mean_pi;
+        sum_age += (ds->site_age[n] - mean_age) * dp;
+        sum_mn += (ds->site_mn[n] - mean_mn) * dp;
+      }
+    }
+    if (!owned) { ser_set_error("ser_run_site_age_corr: none of the chosen chains lives on this run"); rc = SER_E_ARG; }
+    else {
+      if (corr_age) *corr_age = var_age > 0.0 ? -sum_age / owned / (N * sd_pi * sqrt(var_age)) : 0.0; /* older = earlier */
+      if (corr_mn) *corr_mn = var_mn > 0.0 ? sum_mn / owned / (N * sd_pi * sqrt(var_mn)) : 0.0;
+      if (n_sites_used) *n_sites_used = N;
+    }
+  }
+  free(corr); free(pis);
   return rc;
 }

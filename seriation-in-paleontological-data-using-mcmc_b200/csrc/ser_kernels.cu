@@ -77,25 +77,60 @@ struct ser_run {
   uint16_t *d_gpre;
   int *d_bgrp;
   int initialized, have_tapes;
+  /* persistent work-queue grid of ser_sweep_kernel: (chain, chunk of calls) items, see ser_run_advance_both */
+  uint32_t *d_V;            /* [chain][W][C] bit columns carried between work items */
+  unsigned int *d_queue;    /* next work item of the running launch */
+  unsigned int *d_done;     /* [chain] work items completed since init (monotonic) */
+  unsigned int chunks_done; /* host mirror: items every chain has completed before the next launch */
+  int sweep_slots;          /* resident CTAs of the chosen sweep instantiation on the whole device */
+  /* cross-chain step on the run's stream (ser_run_cross_chain_async) */
+  double *d_e_all, *d_info;
+  int *d_chosen, *d_counts;
+  int cc_k, cc_total, cc_ranks, cc_rank, cc_valid;
 };
 
+/* multi-GPU pieces (ser_multi.cuh): NCCL entry points resolved at run time */
+struct ser_comm;
+static int comm_all_gather_e(ser_comm *comm, double *d_e_all, int n_local, cudaStream_t stream);
+static int comm_all_reduce_counts(ser_comm *comm, int *d_counts, size_t n, cudaStream_t stream);
+static int comm_ranks(const ser_comm *comm, int *n_ranks, int *rank);
+
 /* Stream-ordered pool allocation: cudaMalloc/cudaFree are synchronous driver calls with erratic
- * latency (tens to hundreds of ms on shared hosts); the default memory pool with an unlimited
- * release threshold keeps freed blocks cached, so creating / destroying runs and the temporary
- * buffers of the cross-chain steps cost microseconds after the first use. */
+ * latency (tens to hundreds of ms on shared hosts).  The library allocates from its OWN memory pool per
+ * device (not the process-wide default pool other allocators share), with a bounded release threshold:
+ * up to SER_POOL_KEEP_MB (default 1024) of freed blocks stay cached, so creating / destroying runs and
+ * the temporary buffers of the cross-chain steps cost microseconds after the first use, while a
+ * multi-GB sample store goes back to the driver when its run is destroyed. */
+#include <mutex>
 static cudaError_t pool_alloc(void **ptr, size_t bytes, cudaStream_t stream)
 {
-  static bool configured[64] = {false};
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {nullptr};
   int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  cudaMemPool_t pool = nullptr;
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if (cudaMemPoolCreate(&pools[dev], &props) == cudaSuccess) {
+        unsigned long long keep = 1024ull << 20;
+        if (const char *v = getenv("SER_POOL_KEEP_MB")) keep = (unsigned long long)atoll(v) << 20;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+      } else {
+        pools[dev] = nullptr;
+        cudaGetLastError();
+      }
     }
-    configured[dev] = true;
+    pool = pools[dev];
   }
+  if (pool) return cudaMallocFromPoolAsync(ptr, bytes ? bytes : 1, pool, stream);
   return cudaMallocAsync(ptr, bytes ? bytes : 1, stream);
 }
 #define POOL_ALLOC(ptr, bytes) pool_alloc((void **)(ptr), (bytes), run->stream)
@@ -167,21 +202,10 @@ static int choose_groups(KParams &kp, const std::vector<int> &off, int M, int N,
   return SER_OK;
 }
 
-extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, ser_run **out)
+/* builds `run` in place; on any failure the caller (ser_run_create) releases whatever exists so far */
+static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser_run *run)
 {
-  if (!ds || !cfg || !out) { ser_set_error("ser_run_create: null argument"); return SER_E_ARG; }
   const int N = ds->N, M = ds->M;
-  if (N < 2 || N > SER_MAX_SITES) { ser_set_error("ser_run_create: N=%d outside [2,%d]", N, SER_MAX_SITES); return SER_E_ARG; }
-  if (M < 1 || M > SER_MAX_TAXA) { ser_set_error("ser_run_create: M=%d outside [1,%d]", M, SER_MAX_TAXA); return SER_E_ARG; }
-  if (cfg->n_chains < 1 || cfg->sweeps_per_call < 1) { ser_set_error("ser_run_create: n_chains and sweeps_per_call must be >= 1"); return SER_E_ARG; }
-  if (cfg->mode != SER_MODE_FREE && cfg->mode != SER_MODE_REPLAY) { ser_set_error("ser_run_create: bad mode"); return SER_E_ARG; }
-  if (cfg->manycd != 0 && cfg->manycd != 1) { ser_set_error("ser_run_create: manycd must be 0 or 1"); return SER_E_ARG; }
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    ser_set_error("ser_run_create: no CUDA device (this library has no CPU path)");
-    return SER_E_CUDA;
-  }
-  ser_run *run = (ser_run *)calloc(1, sizeof(ser_run));
   run->cfg = *cfg;
   run->N = N; run->M = M; run->nh = ds->nh;
   run->W = N / 32 + 1;
@@ -241,6 +265,7 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     for (int e = off[c]; e < off[c + 1]; e++) item_col[e] = ((uint32_t)c << 16) | (uint32_t)(e - off[c]);
   kp.ones_total = ones_total;
   run->h_hard = (uint8_t *)malloc(N);
+  if (!run->h_hard) { ser_set_error("ser_run_create: out of memory"); return SER_E_ARG; }
   memcpy(run->h_hard, ds->hard, N);
 
   const size_t nc = (size_t)cfg->n_chains;
@@ -366,6 +391,57 @@ extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, 
     kp.gV = run->d_gV; kp.gpre = run->d_gpre;
   }
   kp.n_chains = cfg->n_chains;
+  if (!run->big) { /* persistent work-queue grid: bit columns carried between work items, queue head, per-chain progress */
+    int per_sm = 1, n_sm = 1;
+    const size_t smem = cfg->manycd ? run->smem_many : run->smem_sweep;
+    if (cfg->manycd && run->variant_many) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel<384, 2, true>, run->C, smem));
+    else if (cfg->manycd) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel<1024, 1, true>, run->C, smem));
+    else if (run->variant == 1) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel<384, 2, false>, run->C, smem));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel<1024, 1, false>, run->C, smem));
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    run->sweep_slots = std::max(1, per_sm * n_sm);
+    if (const char *v = getenv("SER_SWEEP_SLOTS")) run->sweep_slots = std::max(1, atoi(v));
+    CUDA_TRY(POOL_ALLOC(&run->d_V, nc * (size_t)run->W * run->C * sizeof(uint32_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_queue, sizeof(unsigned int)));
+    CUDA_TRY(POOL_ALLOC(&run->d_done, nc * sizeof(unsigned int)));
+    kp.gVc = run->d_V; kp.queue = run->d_queue; kp.done = run->d_done;
+  }
+  return SER_OK;
+}
+
+extern "C" int ser_run_create(const ser_dataset *ds, const ser_run_config *cfg, ser_run **out)
+{
+  if (!ds || !cfg || !out) { ser_set_error("ser_run_create: null argument"); return SER_E_ARG; }
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(ser_run_config)) {
+    ser_set_error("ser_run_create: cfg->struct_size is %u, this library's ser_run_config has %zu bytes (set struct_size = sizeof(ser_run_config); "
+                  "the caller was built against another header)", cfg->struct_size, sizeof(ser_run_config));
+    return SER_E_ARG;
+  }
+  const int N = ds->N, M = ds->M;
+  if (N < 2 || N > SER_MAX_SITES) { ser_set_error("ser_run_create: N=%d outside [2,%d]", N, SER_MAX_SITES); return SER_E_ARG; }
+  if (M < 1 || M > SER_MAX_TAXA) { ser_set_error("ser_run_create: M=%d outside [1,%d]", M, SER_MAX_TAXA); return SER_E_ARG; }
+  if (cfg->n_chains < 1 || cfg->sweeps_per_call < 1) { ser_set_error("ser_run_create: n_chains and sweeps_per_call must be >= 1"); return SER_E_ARG; }
+  if (cfg->mode != SER_MODE_FREE && cfg->mode != SER_MODE_REPLAY) { ser_set_error("ser_run_create: bad mode"); return SER_E_ARG; }
+  if (cfg->manycd != 0 && cfg->manycd != 1) { ser_set_error("ser_run_create: manycd must be 0 or 1"); return SER_E_ARG; }
+  if (cfg->store < SER_STORE_NONE || cfg->store > SER_STORE_FULL || cfg->max_samples < 0) { ser_set_error("ser_run_create: bad store / max_samples"); return SER_E_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    ser_set_error("ser_run_create: no CUDA device (this library has no CPU path)");
+    return SER_E_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { ser_set_error("ser_run_create: device %d of %d", cfg->device, ndev); return SER_E_ARG; }
+  ser_run *run = (ser_run *)calloc(1, sizeof(ser_run));
+  if (!run) { ser_set_error("ser_run_create: out of memory"); return SER_E_ARG; }
+  const int rc = run_create_impl(ds, cfg, run);
+  if (rc != SER_OK) { /* single exit for every failure: release the stream, events and buffers made so far */
+    char keep[512];
+    snprintf(keep, sizeof(keep), "%s", ser_last_error());
+    ser_run_destroy(run);
+    cudaGetLastError();
+    ser_set_error("%s", keep);
+    return rc;
+  }
   *out = run;
   return SER_OK;
 }
@@ -376,11 +452,13 @@ extern "C" void ser_run_destroy(ser_run *run)
   cudaSetDevice(run->cfg.device);
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
-                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp};
+                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp,
+                  run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
-  cudaStreamSynchronize(run->stream);
-  cudaEventDestroy(run->ev_start); cudaEventDestroy(run->ev_stop);
-  cudaStreamDestroy(run->stream);
+  if (run->stream) cudaStreamSynchronize(run->stream);
+  if (run->ev_start) cudaEventDestroy(run->ev_start);
+  if (run->ev_stop) cudaEventDestroy(run->ev_stop);
+  if (run->stream) cudaStreamDestroy(run->stream);
   free(run->h_hard);
   free(run);
 }
@@ -396,6 +474,7 @@ extern "C" int ser_run_dims(const ser_run *run, int32_t *N, int32_t *M, int32_t 
 }
 extern "C" const uint8_t *ser_run_hard_flags(const ser_run *run) { return run ? run->h_hard : nullptr; }
 extern "C" int ser_run_is_manycd(const ser_run *run) { return run ? run->cfg.manycd : 0; }
+extern "C" int ser_run_chain_offset(const ser_run *run) { return run ? run->cfg.chain_offset : 0; }
 
 extern "C" int ser_run_set_tapes(ser_run *run, const double *flat, const uint64_t *offsets)
 {
@@ -421,6 +500,8 @@ extern "C" int ser_run_init(ser_run *run)
   if (!run) return SER_E_ARG;
   if (run->cfg.mode == SER_MODE_REPLAY && !run->have_tapes) { ser_set_error("ser_run_init: replay mode needs ser_run_set_tapes first"); return SER_E_TAPE; }
   if (set_device(run)) return SER_E_CUDA;
+  if (run->d_done) CUDA_TRY(cudaMemsetAsync(run->d_done, 0, (size_t)run->cfg.n_chains * sizeof(unsigned int), run->stream));
+  run->chunks_done = 0;
   mark_launch(run);
   ser_init_kernel<<<run->cfg.n_chains, run->Caux, run->smem_init, run->stream>>>(run->kp);
   CUDA_TRY(cudaGetLastError());
@@ -428,22 +509,49 @@ extern "C" int ser_run_init(ser_run *run)
   return SER_OK;
 }
 
-extern "C" int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling)
+/* One launch = burn_calls burn-in calls, then sample_calls sampling calls, on every chain.
+ * One-thread-per-column kernels: a persistent grid (as many CTAs as the device holds) pulls
+ * (chain, chunk of calls) work items from a queue, so the last wave of a launch is never longer than
+ * one item whatever the number of chains; chunks are as long as the balance allows (>= 32 items per
+ * resident CTA when the launch has that much work), because an item boundary costs one state
+ * round trip through HBM. */
+extern "C" int ser_run_advance_both(ser_run *run, int32_t burn_calls, int32_t sample_calls)
 {
   if (!run) return SER_E_ARG;
   if (!run->initialized) { ser_set_error("ser_run_advance: call ser_run_init first"); return SER_E_STATE; }
+  if (burn_calls < 0 || sample_calls < 0) { ser_set_error("ser_run_advance: negative call count"); return SER_E_ARG; }
+  const int n_calls = burn_calls + sample_calls;
   if (n_calls <= 0) return SER_OK;
   if (set_device(run)) return SER_E_CUDA;
   KParams kp = run->kp;
-  kp.n_calls = n_calls; kp.sampling = sampling;
+  kp.n_calls = n_calls; kp.burn_calls = burn_calls;
   mark_launch(run);
-  if (run->cfg.manycd && run->variant_many) ser_sweep_kernel<384, 2, true><<<run->cfg.n_chains, run->C, run->smem_many, run->stream>>>(kp);
-  else if (run->cfg.manycd) ser_sweep_kernel<1024, 1, true><<<run->cfg.n_chains, run->C, run->smem_many, run->stream>>>(kp);
-  else if (run->big) ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
-  else if (run->variant == 1) ser_sweep_kernel<384, 2, false><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
-  else ser_sweep_kernel<1024, 1, false><<<run->cfg.n_chains, run->C, run->smem_sweep, run->stream>>>(kp);
+  if (run->big) {
+    ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+    CUDA_TRY(cudaGetLastError());
+    return SER_OK;
+  }
+  const long long work = (long long)run->cfg.n_chains * n_calls;
+  int chunk = (int)std::min<long long>(n_calls, std::max<long long>(1, work / (32ll * run->sweep_slots)));
+  if (const char *v = getenv("SER_CHUNK_CALLS")) chunk = std::max(1, std::min(n_calls, atoi(v)));
+  const int per_chain = (n_calls + chunk - 1) / chunk;
+  kp.chunk_calls = chunk;
+  kp.n_items = (unsigned int)run->cfg.n_chains * (unsigned int)per_chain;
+  kp.chunk_base = run->chunks_done;
+  run->chunks_done += (unsigned int)per_chain;
+  const int grid = (int)std::min<long long>((long long)kp.n_items, run->sweep_slots);
+  CUDA_TRY(cudaMemsetAsync(run->d_queue, 0, sizeof(unsigned int), run->stream));
+  if (run->cfg.manycd && run->variant_many) ser_sweep_kernel<384, 2, true><<<grid, run->C, run->smem_many, run->stream>>>(kp);
+  else if (run->cfg.manycd) ser_sweep_kernel<1024, 1, true><<<grid, run->C, run->smem_many, run->stream>>>(kp);
+  else if (run->variant == 1) ser_sweep_kernel<384, 2, false><<<grid, run->C, run->smem_sweep, run->stream>>>(kp);
+  else ser_sweep_kernel<1024, 1, false><<<grid, run->C, run->smem_sweep, run->stream>>>(kp);
   CUDA_TRY(cudaGetLastError());
   return SER_OK;
+}
+
+extern "C" int ser_run_advance(ser_run *run, int32_t n_calls, int32_t sampling)
+{
+  return sampling ? ser_run_advance_both(run, 0, n_calls) : ser_run_advance_both(run, n_calls, 0);
 }
 
 extern "C" int ser_run_sync(ser_run *run)
@@ -537,7 +645,7 @@ extern "C" int ser_run_get_flags(ser_run *run, int32_t chain, int32_t *flags)
   ChainScalars sc;
   CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal + chain, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
   CUDA_TRY(cudaStreamSynchronize(run->stream));
-  *flags = sc.flags;
+  *flags = sc.flags & 31; /* bit 5 is internal (bit columns stored) */
   return SER_OK;
 }
 
@@ -588,15 +696,41 @@ extern "C" int ser_run_chain_stats(ser_run *run, double *e_negloglik, double *e_
   return SER_OK;
 }
 
+static PeerPtrs one_dest(void *ptr)
+{
+  PeerPtrs d;
+  memset(&d, 0, sizeof(d));
+  d.p[0] = ptr; d.n = 1;
+  return d;
+}
+
+/* E[-logL] of the local chains at dst[offset + chain] of every destination, on the run's stream */
+static int run_stats_to(ser_run *run, const PeerPtrs &dst, int offset)
+{
+  const int nc = run->cfg.n_chains;
+  mark_launch(run);
+  ser_stats_kernel<<<(nc + 255) / 256, 256, 0, run->stream>>>(run->d_scal, nc, dst, offset);
+  CUDA_TRY(cudaGetLastError());
+  return SER_OK;
+}
+
+/* pair-order slabs of the chosen chains this run owns, into every destination, on the run's stream */
+/* id_base = the id local chain 0 has in the numbering `d_chosen` uses */
+static int run_po_to(ser_run *run, const int32_t *d_chosen, int k, const PeerPtrs &dst, int id_base)
+{
+  dim3 grd((run->N + 31) / 32, (run->N + 31) / 32, k);
+  mark_launch(run);
+  ser_po_kernel<<<grd, 256, 0, run->stream>>>(run->d_samp_pi, run->d_scal, run->N, run->cfg.max_samples, d_chosen, id_base,
+                                              run->cfg.n_chains, dst);
+  CUDA_TRY(cudaGetLastError());
+  return SER_OK;
+}
+
 extern "C" int ser_run_chain_stats_device(ser_run *run, double *d_e_negloglik)
 {
   if (!run || !d_e_negloglik) return SER_E_ARG;
   if (set_device(run)) return SER_E_CUDA;
-  const int nc = run->cfg.n_chains;
-  mark_launch(run);
-  ser_stats_kernel<<<(nc + 255) / 256, 256, 0, run->stream>>>(run->d_scal, nc, d_e_negloglik);
-  CUDA_TRY(cudaGetLastError());
-  return SER_OK;
+  return run_stats_to(run, one_dest(d_e_negloglik), 0);
 }
 
 extern "C" int ser_run_fetch_samples(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32_t *pi, double *c, double *d,
@@ -698,16 +832,7 @@ extern "C" int ser_run_po_counts_device(ser_run *run, const int32_t *d_chosen, i
   if (!run || !d_chosen || !d_counts || k < 1) return SER_E_ARG;
   if (run->cfg.store < SER_STORE_PI) { ser_set_error("ser_run_po_counts: run has no pi sample store"); return SER_E_STATE; }
   if (set_device(run)) return SER_E_CUDA;
-  ChainScalars sc;
-  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
-  CUDA_TRY(cudaStreamSynchronize(run->stream));
-  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples;
-  dim3 blk(32, 8), grd((run->N + 31) / 32, (run->N + 7) / 8, k);
-  mark_launch(run);
-  ser_po_kernel<<<grd, blk, 0, run->stream>>>(run->d_samp_pi, run->N, run->cfg.max_samples, ns, d_chosen, run->cfg.chain_offset,
-                                              run->cfg.n_chains, d_counts);
-  CUDA_TRY(cudaGetLastError());
-  return SER_OK;
+  return run_po_to(run, d_chosen, k, one_dest(d_counts), run->cfg.chain_offset); /* T is read per chosen chain on the device: no host round trip */
 }
 
 extern "C" int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *counts)
@@ -729,6 +854,19 @@ extern "C" int ser_run_po_counts(ser_run *run, const int32_t *chosen, int32_t k,
   return rc;
 }
 
+/* common sample count of the chosen chains this run owns (n_out[c] < 0: not owned) */
+static int common_samples(const std::vector<int> &n_out, int32_t *n_samples, const char *who)
+{
+  int ns = -1;
+  for (int v : n_out) {
+    if (v < 0) continue;
+    if (ns >= 0 && v != ns) { ser_set_error("%s: the chosen chains hold different numbers of samples (%d vs %d)", who, ns, v); return SER_E_STATE; }
+    ns = v;
+  }
+  if (n_samples) *n_samples = ns < 0 ? 0 : ns;
+  return SER_OK;
+}
+
 extern "C" int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32_t k, int64_t *corr_num, int32_t *pi_sum,
                                       int32_t *a_sum, int32_t *b_sum, int32_t *n_samples)
 {
@@ -736,39 +874,44 @@ extern "C" int ser_run_posterior_sums(ser_run *run, const int32_t *chosen, int32
   if (run->cfg.store < SER_STORE_PI) { ser_set_error("ser_run_posterior_sums: run has no pi sample store"); return SER_E_STATE; }
   if ((a_sum || b_sum) && run->cfg.store < SER_STORE_FULL) { ser_set_error("ser_run_posterior_sums: a/b sums need SER_STORE_FULL"); return SER_E_STATE; }
   if (set_device(run)) return SER_E_CUDA;
-  ChainScalars sc;
-  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
-  CUDA_TRY(cudaStreamSynchronize(run->stream));
-  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples, N = run->N, M = run->M;
-  int *d_ch = nullptr, *d_pi = nullptr, *d_a = nullptr, *d_b = nullptr;
+  const int N = run->N, M = run->M;
+  int *d_ch = nullptr, *d_pi = nullptr, *d_a = nullptr, *d_b = nullptr, *d_n = nullptr;
   long long *d_corr = nullptr;
-  CUDA_TRY(POOL_ALLOC(&d_ch, k * sizeof(int)));
-  CUDA_TRY(POOL_ALLOC(&d_corr, k * sizeof(long long)));
-  CUDA_TRY(POOL_ALLOC(&d_pi, (size_t)k * N * sizeof(int)));
-  if (a_sum) { CUDA_TRY(POOL_ALLOC(&d_a, (size_t)k * M * sizeof(int))); CUDA_TRY(POOL_ALLOC(&d_b, (size_t)k * M * sizeof(int))); }
-  CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
-  CUDA_TRY(cudaMemcpyAsync(d_corr, corr_num, k * sizeof(long long), cudaMemcpyHostToDevice, run->stream));
-  CUDA_TRY(cudaMemcpyAsync(d_pi, pi_sum, (size_t)k * N * sizeof(int), cudaMemcpyHostToDevice, run->stream));
-  if (a_sum) {
-    CUDA_TRY(cudaMemcpyAsync(d_a, a_sum, (size_t)k * M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
-    if (b_sum) CUDA_TRY(cudaMemcpyAsync(d_b, b_sum, (size_t)k * M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
-  }
-  mark_launch(run);
-  ser_posterior_kernel<<<k, 256, 0, run->stream>>>(run->d_samp_pi, run->d_samp_a, run->d_samp_b, N, M, run->cfg.max_samples, ns, d_ch,
-                                                   run->cfg.chain_offset, run->cfg.n_chains, d_corr, d_pi, d_a, b_sum ? d_b : nullptr);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(corr_num, d_corr, k * sizeof(long long), cudaMemcpyDeviceToHost, run->stream));
-  CUDA_TRY(cudaMemcpyAsync(pi_sum, d_pi, (size_t)k * N * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
-  if (a_sum) {
-    CUDA_TRY(cudaMemcpyAsync(a_sum, d_a, (size_t)k * M * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
-    if (b_sum) CUDA_TRY(cudaMemcpyAsync(b_sum, d_b, (size_t)k * M * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
-  }
-  CUDA_TRY(cudaStreamSynchronize(run->stream));
-  cudaFreeAsync(d_ch, run->stream); cudaFreeAsync(d_corr, run->stream); cudaFreeAsync(d_pi, run->stream);
-  if (d_a) cudaFreeAsync(d_a, run->stream);
-  if (d_b) cudaFreeAsync(d_b, run->stream);
-  if (n_samples) *n_samples = ns;
-  return SER_OK;
+  std::vector<int> n_out(k, -1);
+  int rc = SER_OK;
+  auto body = [&]() -> int {
+    CUDA_TRY(POOL_ALLOC(&d_ch, k * sizeof(int)));
+    CUDA_TRY(POOL_ALLOC(&d_n, k * sizeof(int)));
+    CUDA_TRY(POOL_ALLOC(&d_corr, k * sizeof(long long)));
+    CUDA_TRY(POOL_ALLOC(&d_pi, (size_t)k * N * sizeof(int)));
+    if (a_sum) { CUDA_TRY(POOL_ALLOC(&d_a, (size_t)k * M * sizeof(int))); CUDA_TRY(POOL_ALLOC(&d_b, (size_t)k * M * sizeof(int))); }
+    CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+    CUDA_TRY(cudaMemsetAsync(d_n, 0xff, k * sizeof(int), run->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_corr, corr_num, k * sizeof(long long), cudaMemcpyHostToDevice, run->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_pi, pi_sum, (size_t)k * N * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+    if (a_sum) {
+      CUDA_TRY(cudaMemcpyAsync(d_a, a_sum, (size_t)k * M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+      if (b_sum) CUDA_TRY(cudaMemcpyAsync(d_b, b_sum, (size_t)k * M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+    }
+    mark_launch(run);
+    ser_posterior_kernel<<<k, 256, 0, run->stream>>>(run->d_samp_pi, run->d_samp_a, run->d_samp_b, run->d_scal, N, M, run->cfg.max_samples, d_ch,
+                                                     run->cfg.chain_offset, run->cfg.n_chains, d_corr, d_pi, d_a, b_sum ? d_b : nullptr, d_n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(corr_num, d_corr, k * sizeof(long long), cudaMemcpyDeviceToHost, run->stream));
+    CUDA_TRY(cudaMemcpyAsync(pi_sum, d_pi, (size_t)k * N * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+    CUDA_TRY(cudaMemcpyAsync(n_out.data(), d_n, k * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+    if (a_sum) {
+      CUDA_TRY(cudaMemcpyAsync(a_sum, d_a, (size_t)k * M * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+      if (b_sum) CUDA_TRY(cudaMemcpyAsync(b_sum, d_b, (size_t)k * M * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(run->stream));
+    return SER_OK;
+  };
+  rc = body();
+  void *tmp[] = {d_ch, d_n, d_corr, d_pi, d_a, d_b};
+  for (void *t : tmp) if (t) cudaFreeAsync(t, run->stream);
+  if (rc != SER_OK) return rc;
+  return common_samples(n_out, n_samples, "ser_run_posterior_sums");
 }
 
 extern "C" int ser_run_alive_counts(ser_run *run, const int32_t *chosen, int32_t k, int32_t *alive, int32_t *n_samples)
@@ -776,24 +919,102 @@ extern "C" int ser_run_alive_counts(ser_run *run, const int32_t *chosen, int32_t
   if (!run || !chosen || !alive || k < 1) { ser_set_error("ser_run_alive_counts: bad argument"); return SER_E_ARG; }
   if (run->cfg.store < SER_STORE_FULL) { ser_set_error("ser_run_alive_counts: needs SER_STORE_FULL (a, b samples)"); return SER_E_STATE; }
   if (set_device(run)) return SER_E_CUDA;
-  ChainScalars sc;
-  CUDA_TRY(cudaMemcpyAsync(&sc, run->d_scal, sizeof(sc), cudaMemcpyDeviceToHost, run->stream));
-  CUDA_TRY(cudaStreamSynchronize(run->stream));
-  const int ns = sc.n_samples < run->cfg.max_samples ? sc.n_samples : run->cfg.max_samples, N = run->N, M = run->M;
+  const int N = run->N, M = run->M;
   const size_t cells = (size_t)k * N * M;
-  int *d_ch = nullptr, *d_alive = nullptr;
-  CUDA_TRY(POOL_ALLOC(&d_ch, k * sizeof(int)));
-  CUDA_TRY(POOL_ALLOC(&d_alive, cells * sizeof(int)));
-  CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
-  CUDA_TRY(cudaMemcpyAsync(d_alive, alive, cells * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+  int *d_ch = nullptr, *d_alive = nullptr, *d_n = nullptr;
+  std::vector<int> n_out(k, -1);
+  auto body = [&]() -> int {
+    CUDA_TRY(POOL_ALLOC(&d_ch, k * sizeof(int)));
+    CUDA_TRY(POOL_ALLOC(&d_n, k * sizeof(int)));
+    CUDA_TRY(POOL_ALLOC(&d_alive, cells * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(d_ch, chosen, k * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+    CUDA_TRY(cudaMemsetAsync(d_n, 0xff, k * sizeof(int), run->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_alive, alive, cells * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+    mark_launch(run);
+    ser_alive_kernel<<<dim3(k, (M + 127) / 128), 128, 0, run->stream>>>(run->d_samp_a, run->d_samp_b, run->d_scal, N, M, run->cfg.max_samples, d_ch,
+                                                                       run->cfg.chain_offset, run->cfg.n_chains, d_alive, d_n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(alive, d_alive, cells * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+    CUDA_TRY(cudaMemcpyAsync(n_out.data(), d_n, k * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+    CUDA_TRY(cudaStreamSynchronize(run->stream));
+    return SER_OK;
+  };
+  const int rc = body();
+  void *tmp[] = {d_ch, d_n, d_alive};
+  for (void *t : tmp) if (t) cudaFreeAsync(t, run->stream);
+  if (rc != SER_OK) return rc;
+  return common_samples(n_out, n_samples, "ser_run_alive_counts");
+}
+
+/* ------------------------------------------------------------------ the cross-chain step on one stream
+ * stats -> (all-gather) -> selection -> zero counts -> pair-order slabs -> (all-reduce): six enqueues, no host
+ * synchronisation (script.py:70-99 + :155-189 over run_all_chains' chains, :48-67). */
+extern "C" int ser_run_cross_chain_async(ser_run *run, ser_comm *comm, int32_t k)
+{
+  if (!run || k < 1) { ser_set_error("ser_run_cross_chain: bad argument"); return SER_E_ARG; }
+  if (run->cfg.store < SER_STORE_PI) { ser_set_error("ser_run_cross_chain: run has no pi sample store"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  int ranks = 1, rank = 0;
+  if (comm && comm_ranks(comm, &ranks, &rank)) return SER_E_ARG;
+  const int nl = run->cfg.n_chains, total = nl * ranks, N = run->N;
+  if (run->cfg.chain_offset < rank * nl) {
+    ser_set_error("ser_run_cross_chain: rank %d holds chain_offset %d; ranks hold consecutive blocks of %d chains", rank, run->cfg.chain_offset, nl);
+    return SER_E_ARG;
+  }
+  if (run->cc_k != k || run->cc_total != total) { /* (re)size the step's device buffers */
+    void *old[] = {run->d_e_all, run->d_info, run->d_chosen, run->d_counts};
+    for (void *b : old) if (b) cudaFreeAsync(b, run->stream);
+    run->d_e_all = nullptr; run->d_info = nullptr; run->d_chosen = nullptr; run->d_counts = nullptr;
+    run->cc_k = 0;
+    CUDA_TRY(POOL_ALLOC(&run->d_e_all, (size_t)total * sizeof(double)));
+    CUDA_TRY(POOL_ALLOC(&run->d_info, 3 * sizeof(double)));
+    CUDA_TRY(POOL_ALLOC(&run->d_chosen, (size_t)k * sizeof(int)));
+    CUDA_TRY(POOL_ALLOC(&run->d_counts, (size_t)k * N * N * sizeof(int)));
+    run->cc_k = k; run->cc_total = total;
+  }
+  run->cc_ranks = ranks; run->cc_rank = rank; run->cc_valid = 0;
+  int rc = run_stats_to(run, one_dest(run->d_e_all), rank * nl); /* straight into this rank's slot of the gather buffer */
+  if (rc) return rc;
+  if (comm && (rc = comm_all_gather_e(comm, run->d_e_all, nl, run->stream))) return rc;
   mark_launch(run);
-  ser_alive_kernel<<<dim3(k, (M + 127) / 128), 128, 0, run->stream>>>(run->d_samp_a, run->d_samp_b, N, M, run->cfg.max_samples, ns, d_ch,
-                                                                     run->cfg.chain_offset, run->cfg.n_chains, d_alive);
+  ser_select_kernel<<<1, 1024, 0, run->stream>>>(run->d_e_all, total, k, run->d_chosen, run->d_info);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(alive, d_alive, cells * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaMemsetAsync(run->d_counts, 0, (size_t)k * N * N * sizeof(int), run->stream));
+  /* the selection numbers the chains by their index in the gathered array: this rank's chain 0 is rank * nl there */
+  if ((rc = run_po_to(run, run->d_chosen, k, one_dest(run->d_counts), rank * nl))) return rc;
+  if (comm && (rc = comm_all_reduce_counts(comm, run->d_counts, (size_t)k * N * N, run->stream))) return rc;
+  run->cc_valid = 1;
+  return SER_OK;
+}
+
+extern "C" int ser_run_cross_chain_result(ser_run *run, int32_t *chosen, int32_t *n_chosen, double *min_out, double *sigma_out,
+                                          int32_t *counts)
+{
+  if (!run) return SER_E_ARG;
+  if (!run->cc_valid) { ser_set_error("ser_run_cross_chain_result: call ser_run_cross_chain_async first"); return SER_E_STATE; }
+  if (set_device(run)) return SER_E_CUDA;
+  const int k = run->cc_k, N = run->N;
+  double info[3] = {0, 0, 0};
+  std::vector<int> ch(k, -1);
+  CUDA_TRY(cudaMemcpyAsync(info, run->d_info, sizeof(info), cudaMemcpyDeviceToHost, run->stream));
+  CUDA_TRY(cudaMemcpyAsync(ch.data(), run->d_chosen, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
+  if (counts) CUDA_TRY(cudaMemcpyAsync(counts, run->d_counts, (size_t)k * N * N * sizeof(int), cudaMemcpyDeviceToHost, run->stream));
   CUDA_TRY(cudaStreamSynchronize(run->stream));
-  cudaFreeAsync(d_ch, run->stream); cudaFreeAsync(d_alive, run->stream);
-  if (n_samples) *n_samples = ns;
+  const int base = run->cfg.chain_offset - run->cc_rank * run->cfg.n_chains; /* index in the gathered array -> GLOBAL id */
+  if (chosen) for (int i = 0; i < k; i++) chosen[i] = ch[i] < 0 ? -1 : ch[i] + base;
+  if (n_chosen) *n_chosen = (int)info[0];
+  if (min_out) *min_out = info[1];
+  if (sigma_out) *sigma_out = info[2];
+  return SER_OK;
+}
+
+extern "C" int ser_run_cross_chain_buffers(ser_run *run, double **d_e_all, int32_t **d_chosen, double **d_info, int32_t **d_counts)
+{
+  if (!run || !run->cc_valid) { ser_set_error("ser_run_cross_chain_buffers: no cross-chain step enqueued"); return SER_E_STATE; }
+  if (d_e_all) *d_e_all = run->d_e_all;
+  if (d_chosen) *d_chosen = run->d_chosen;
+  if (d_info) *d_info = run->d_info;
+  if (d_counts) *d_counts = run->d_counts;
   return SER_OK;
 }
 
@@ -834,3 +1055,5 @@ extern "C" int ser_microbench(int32_t device, double out[3])
   cudaFree(buf);
   return SER_OK;
 }
+
+#include "ser_multi.cuh"

@@ -102,31 +102,70 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
   Smem sm;
   smem_layout(&sm, smem_raw, p.N, p.W, p.C, p.I, MANY ? 1 : 0, p.Ival);
 
-  const int chain = blockIdx.x, tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
-  const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+  const int tid = threadIdx.x, N = p.N, M = p.M, C = p.C, W = p.W;
   uint32_t *col = sm.V + tid;
   uint16_t *pre = sm.pre + tid;
   const bool is_taxon = tid < M, is_col = tid <= M;
+  __shared__ unsigned int s_item;
 
-  /* ---- load chain state */
-  ChainScalars sc = p.scal[chain];
-  for (int n = tid; n < N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
-  int a = 0, b = 0, taxon = 0, off_c = 0, ones_c = 0;
-  double c = p.c0, cc = p.cc0, d = p.d0, dd = p.dd0; /* MANY: this taxon's c, log(1-e^c), d, log(1-e^d) */
+  /* static per column (the same for every chain this CTA serves) */
+  int taxon = 0, off_c = 0, ones_c = 0;
   if (is_taxon) {
-    a = p.ab[(size_t)chain * 2 * p.Mpad + tid];
-    b = p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid];
     taxon = p.order[tid]; /* the taxon this column holds: indexes the tape, the samples, terms[] */
     off_c = p.off[tid];
     ones_c = p.ones[tid];
     sm.ones16[tid] = (uint16_t)ones_c;
+  }
+
+  /* ---- persistent grid: the CTAs pull (chain, chunk of calls) work items from a queue until it is empty.
+   * Items are numbered chunk-major, so a chain's chunks are claimed in order; a chunk waits until the chain's
+   * previous chunk has published its state (done[chain], release / acquire).  The holder of an earlier item is
+   * always a running CTA, so the wait cannot deadlock, whatever the grid size. */
+  for (;;) {
+  __syncthreads(); /* the previous item is done with shared memory (and with s_item) */
+  if (tid == 0) s_item = atomicAdd(p.queue, 1u);
+  __syncthreads();
+  const unsigned int item = s_item;
+  if (item >= p.n_items) break;
+  const int chunk = (int)(item / (unsigned int)p.n_chains), chain = (int)(item - (unsigned int)chunk * (unsigned int)p.n_chains);
+  const int call_lo = chunk * p.chunk_calls, call_hi = min(p.n_calls, call_lo + p.chunk_calls);
+  if (chunk > 0) {
+    if (tid == 0) {
+      const volatile unsigned int *dn = p.done + chain;
+      while ((int)(*dn - (p.chunk_base + (unsigned int)chunk)) < 0) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+
+  /* ---- load chain state (L1-bypassing loads: another SM may have written it a moment ago) */
+  ChainScalars sc;
+  {
+    const int4 *src = reinterpret_cast<const int4 *>(p.scal + chain);
+    int4 *dst = reinterpret_cast<int4 *>(&sc);
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(ChainScalars) / 16); q++) dst[q] = __ldcg(src + q);
+  }
+  for (int n = tid; n < N; n += C) sm.rpi[n] = __ldcg(p.rpi + (size_t)chain * p.Npad + n);
+  int a = 0, b = 0;
+  double c = p.c0, cc = p.cc0, d = p.d0, dd = p.dd0; /* MANY: this taxon's c, log(1-e^c), d, log(1-e^d) */
+  if (is_taxon) {
+    a = __ldcg(p.ab + (size_t)chain * 2 * p.Mpad + tid);
+    b = __ldcg(p.ab + (size_t)chain * 2 * p.Mpad + p.Mpad + tid);
     if constexpr (MANY) {
       const double *cd = p.cd4 + (size_t)chain * 4 * p.Mpad + tid;
-      c = cd[0]; cc = cd[p.Mpad]; d = cd[2 * p.Mpad]; dd = cd[3 * p.Mpad];
+      c = __ldcg(cd); cc = __ldcg(cd + p.Mpad); d = __ldcg(cd + 2 * p.Mpad); dd = __ldcg(cd + 3 * p.Mpad);
     }
   }
   __syncthreads();
-  build_columns(p, sm);
+  if (sc.flags & SER_FLAG_COLUMNS) { /* the bit columns travel with the chain between work items */
+    const uint32_t *gv = p.gVc + (size_t)chain * W * C + tid;
+    for (int w = 0; w < W; w++) sm.V[w * C + tid] = __ldcg(gv + (size_t)w * C);
+    ser_col_build_pre(sm.V + tid, sm.pre + tid, C, W);
+  } else {
+    build_columns(p, sm);
+  }
   __syncthreads();
   if (tid == M) rebuild_hard(p, sm);
   __syncthreads();
@@ -152,7 +191,8 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
   PropState ps;
   ps.k = 0; ps.buf = 0;
 
-  for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
+  for (int call = call_lo; call < call_hi && !(sc.flags & 1); call++) {
+    const bool sampling = call >= p.burn_calls; /* burn-in calls first, then sampling calls (mcmc.c:140-143, :180-185) */
     for (int s = 0; s < p.sweeps_per_call; s++) {
       __syncthreads(); /* every thread is done reading the previous sweep's staged draws */
       double ua = 0.0, ub = 0.0;
@@ -317,7 +357,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
       }
       /* the log-likelihood is only ever observed after the last sweep of a sampling call
        * (mcmc_save_chain); there it is formed with the reference's own sequential sums */
-      const bool exact = p.sampling && s == p.sweeps_per_call - 1;
+      const bool exact = sampling && s == p.sweeps_per_call - 1;
       if constexpr (MANY) {
         {
           int t1 = 0, len = 0, T1, LEN, CH;
@@ -452,7 +492,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
 
     /* ================= thinned sample (mcmc_save_chain + compute_exp_data) ================= */
     if constexpr (MANY) {
-      if (p.sampling) {
+      if (sampling) {
         const int sidx = sc.n_samples;
         const double c_first = sm.draws_cd[0], d_first = sm.draws_cd[1]; /* taxon 0's c, d (compute_exp_data, mcmc.c:56-57) */
         if (sidx < p.max_samples) {
@@ -474,7 +514,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
         sc.n_samples++;
       }
     } else {
-      if (p.sampling) {
+      if (sampling) {
         const int sidx = sc.n_samples;
         if (sidx < p.max_samples) {
           const size_t row = (size_t)chain * p.max_samples + sidx;
@@ -493,31 +533,35 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
     }
   }
 
-  /* ---- save chain state */
+  /* ---- save chain state (incl. the bit columns) and publish the item */
+  __syncthreads();
+  sc.flags |= SER_FLAG_COLUMNS;
+  {
+    uint32_t *gv = p.gVc + (size_t)chain * W * C + tid;
+    for (int w = 0; w < W; w++) gv[(size_t)w * C] = sm.V[w * C + tid];
+  }
+  if (is_taxon) {
+    p.ab[(size_t)chain * 2 * p.Mpad + tid] = (uint16_t)a;
+    p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid] = (uint16_t)b;
+  }
+  for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
   if constexpr (MANY) {
-    __syncthreads();
     if (is_taxon) {
-      p.ab[(size_t)chain * 2 * p.Mpad + tid] = (uint16_t)a;
-      p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid] = (uint16_t)b;
       double *cd = p.cd4 + (size_t)chain * 4 * p.Mpad + tid;
       cd[0] = c; cd[p.Mpad] = cc; cd[2 * p.Mpad] = d; cd[3 * p.Mpad] = dd;
       if (taxon == 0) { sm.draws_cd[0] = c; sm.draws_cd[1] = cc; sm.draws_cd[2] = d; sm.draws_cd[3] = dd; }
     }
-    for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
     __syncthreads();
-    if (tid == 0) { /* the scalar slots carry taxon 0's c, d */
-      sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3];
-      p.scal[chain] = sc;
-    }
-  } else {
-    __syncthreads();
-    if (is_taxon) {
-      p.ab[(size_t)chain * 2 * p.Mpad + tid] = (uint16_t)a;
-      p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + tid] = (uint16_t)b;
-    }
-    for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
-    if (tid == 0) p.scal[chain] = sc;
+    if (tid == 0) { sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3]; } /* the scalar slots carry taxon 0's c, d */
   }
+  if (tid == 0) p.scal[chain] = sc;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    *(volatile unsigned int *)(p.done + chain) = p.chunk_base + (unsigned int)chunk + 1u;
+  }
+  } /* work items */
 }
 
 /* phase timing of the large-shape kernel (debug builds: NVCC_EXTRA=-DSER_PHASE_TIMING): thread 0 of every

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
     ps.k = 0; ps.buf = 0;
 
     for (int call = 0; call < p.n_calls && !(sc.flags & 1); call++) {
+      const bool sampling = call >= p.burn_calls; /* burn-in calls first, then sampling calls */
       for (int s = 0; s < p.sweeps_per_call; s++) {
         /* ================= stage this sweep's draws ================= */
         __syncthreads();
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           }
         }
         __syncthreads();
-        const bool exact = p.sampling && s == p.sweeps_per_call - 1;
+        const bool exact = sampling && s == p.sweeps_per_call - 1;
         {
           int t1 = 0, len = 0, T1, LEN, CH;
           for (int c = tid; c < M; c += C) {
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
       }
       if (sc.flags & 1) break;
 
-      if (p.sampling) {
+      if (sampling) {
         const int sidx = sc.n_samples;
         if (sidx < p.max_samples) {
           const size_t row = (size_t)chain * p.max_samples + sidx;

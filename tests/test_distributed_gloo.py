@@ -44,7 +44,8 @@ def _worker(rank, world, port, q):
     e, pis, N, T, k = _make_inputs()
     per = len(e) // world
     owned = set(range(rank * per, (rank + 1) * per))
-    chosen, po = S.cross_chain_distributed(e[rank * per:(rank + 1) * per], k, lambda ch: _counts_for(pis, owned, ch), N)
+    from tools.dist_helpers import cross_chain_distributed
+    chosen, po = cross_chain_distributed(S, e[rank * per:(rank + 1) * per], k, lambda ch: _counts_for(pis, owned, ch), N)
     q.put((rank, chosen, po))
     dist.barrier()
     dist.destroy_process_group()
@@ -57,7 +58,8 @@ def test_sharded_selection_and_pair_order_equal_single_process():
     e, pis, N, T, k = _make_inputs()
     want_chosen = O.choose_chains(e, k)
     want_po = O.pair_order_matrix([O.pair_order_counts(pis[g]) for g in want_chosen], k)
-    single_chosen, single_po = S.cross_chain_distributed(e, k, lambda ch: _counts_for(pis, set(range(len(e))), ch), N)
+    from tools.dist_helpers import cross_chain_distributed
+    single_chosen, single_po = cross_chain_distributed(S, e, k, lambda ch: _counts_for(pis, set(range(len(e))), ch), N)
     assert single_chosen == want_chosen and np.allclose(single_po, want_po, atol=1e-15)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
