@@ -115,6 +115,10 @@ int ser_run_sync(ser_run *run);
 /* CUDA-event time of all kernels launched by this run since creation / last reset, in ms */
 int ser_run_elapsed_ms(ser_run *run, double *ms, int32_t reset);
 int ser_run_kernel_launches(const ser_run *run, int64_t *n);
+/* CUDA-event time of the SWEEP launches alone since the last reset, and how many there were.  The events are
+ * recorded around every launch and only read here, so measuring the dominant kernel puts no host
+ * synchronisation between the launches of a timed region. */
+int ser_run_sweep_time(ser_run *run, double *ms, int32_t *n_launches, int32_t reset);
 
 /* full model state of one local chain (any pointer may be NULL) */
 int ser_run_get_state(ser_run *run, int32_t chain, int32_t *a, int32_t *b, int32_t *pi, int32_t *rpi,
@@ -256,6 +260,9 @@ int ser_write_labelled_files(ser_run *run, int32_t chain, const ser_dataset *ds,
 /* micro-benchmarks of the SM-local ceilings the sweep is bound by (DESIGN.md "roofline"):
  * out[0] = fp64 FMA TFLOP/s, out[1] = shared-memory load GB/s, out[2] = popc Gop/s */
 int ser_microbench(int32_t device, double out[3]);
+/* the same plus out[3..5] = the kernel times (ms) behind the three rates, so the peaks can be re-derived:
+ * work = 2 x SMs x 1024 threads x 20 000 iterations x {8 FMA = 16 flop, (1/4 of the iterations) 8 x 16 B, 8 popc} */
+int ser_microbench_ex(int32_t device, double out[6]);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,8 @@ SYMBOLS = [
     ("ser_write_chain_files", C.c_int, [_vp, C.c_int32, C.c_char_p]),
     ("ser_write_labelled_files", C.c_int, [_vp, C.c_int32, _vp, C.c_char_p]),
     ("ser_microbench", C.c_int, [C.c_int32, _dp]),
+    ("ser_microbench_ex", C.c_int, [C.c_int32, _dp]),
+    ("ser_run_sweep_time", C.c_int, [_vp, _dp, _i32p, C.c_int32]),
     ("ser_run_site_age_corr", C.c_int, [_vp, _vp, _i32p, C.c_int32, _dp, _dp, _i32p]),
     ("ser_run_cross_chain_async", C.c_int, [_vp, _vp, C.c_int32]),
     ("ser_run_cross_chain_result", C.c_int, [_vp, _i32p, _i32p, _dp, _dp, _i32p]),
@@ -239,6 +241,12 @@ class Run:
         ms = C.c_double()
         _check(lib().ser_run_elapsed_ms(self._h, C.byref(ms), int(reset)))
         return ms.value
+
+    def sweep_time(self, reset=False):
+        """(ms, launches): CUDA-event time of the sweep launches alone since the last reset"""
+        ms, n = C.c_double(), C.c_int32()
+        _check(lib().ser_run_sweep_time(self._h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
 
     def kernel_launches(self) -> int:
         n = C.c_int64()
@@ -496,9 +504,9 @@ def po_finalize(counts: np.ndarray, chains_selected: int, faithful=True) -> np.n
 
 
 def microbench(device=0) -> dict:
-    out = np.empty(3)
-    _check(lib().ser_microbench(device, _p(out, C.c_double)))
-    return dict(fp64_tflops=out[0], lds_gbs=out[1], popc_gops=out[2])
+    out = np.empty(6)
+    _check(lib().ser_microbench_ex(device, _p(out, C.c_double)))
+    return dict(fp64_tflops=out[0], lds_gbs=out[1], popc_gops=out[2], fp64_kernel_ms=out[3], lds_kernel_ms=out[4], popc_kernel_ms=out[5])
 
 
 # ------------------------------------------------------------------------------------------------

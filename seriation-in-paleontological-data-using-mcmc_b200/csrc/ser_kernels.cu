@@ -87,6 +87,10 @@ struct ser_run {
   double *d_e_all, *d_info;
   int *d_chosen, *d_counts;
   int cc_k, cc_total, cc_ranks, cc_rank, cc_valid;
+  /* CUDA-event pairs around every sweep launch since the last reset (ser_run_sweep_time): read after the fact, so
+   * timing the dominant kernel does not put a host synchronisation into the timed region */
+  std::vector<cudaEvent_t> *sweep_ev;
+  size_t sweep_ev_used;
 };
 
 /* multi-GPU pieces (ser_multi.cuh): NCCL entry points resolved at run time */
@@ -456,6 +460,10 @@ extern "C" void ser_run_destroy(ser_run *run)
                   run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   if (run->stream) cudaStreamSynchronize(run->stream);
+  if (run->sweep_ev) {
+    for (cudaEvent_t e : *run->sweep_ev) cudaEventDestroy(e);
+    delete run->sweep_ev;
+  }
   if (run->ev_start) cudaEventDestroy(run->ev_start);
   if (run->ev_stop) cudaEventDestroy(run->ev_stop);
   if (run->stream) cudaStreamDestroy(run->stream);
@@ -526,9 +534,24 @@ extern "C" int ser_run_advance_both(ser_run *run, int32_t burn_calls, int32_t sa
   KParams kp = run->kp;
   kp.n_calls = n_calls; kp.burn_calls = burn_calls;
   mark_launch(run);
+  /* event pair of this sweep launch */
+  if (!run->sweep_ev) run->sweep_ev = new std::vector<cudaEvent_t>();
+  const bool rec = run->sweep_ev_used < 2 * 256; /* at most 256 launches between two reads; later ones are not timed */
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (rec) {
+    if (run->sweep_ev_used + 2 > run->sweep_ev->size()) {
+      cudaEvent_t a, b;
+      CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+      run->sweep_ev->push_back(a); run->sweep_ev->push_back(b);
+    }
+    ev0 = (*run->sweep_ev)[run->sweep_ev_used]; ev1 = (*run->sweep_ev)[run->sweep_ev_used + 1];
+    run->sweep_ev_used += 2;
+  }
   if (run->big) {
+    if (rec) CUDA_TRY(cudaEventRecord(ev0, run->stream));
     ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
     CUDA_TRY(cudaGetLastError());
+    if (rec) CUDA_TRY(cudaEventRecord(ev1, run->stream));
     return SER_OK;
   }
   const long long work = (long long)run->cfg.n_chains * n_calls;
@@ -541,11 +564,31 @@ extern "C" int ser_run_advance_both(ser_run *run, int32_t burn_calls, int32_t sa
   run->chunks_done += (unsigned int)per_chain;
   const int grid = (int)std::min<long long>((long long)kp.n_items, run->sweep_slots);
   CUDA_TRY(cudaMemsetAsync(run->d_queue, 0, sizeof(unsigned int), run->stream));
+  if (rec) CUDA_TRY(cudaEventRecord(ev0, run->stream));
   if (run->cfg.manycd && run->variant_many) ser_sweep_kernel<384, 2, true><<<grid, run->C, run->smem_many, run->stream>>>(kp);
   else if (run->cfg.manycd) ser_sweep_kernel<1024, 1, true><<<grid, run->C, run->smem_many, run->stream>>>(kp);
   else if (run->variant == 1) ser_sweep_kernel<384, 2, false><<<grid, run->C, run->smem_sweep, run->stream>>>(kp);
   else ser_sweep_kernel<1024, 1, false><<<grid, run->C, run->smem_sweep, run->stream>>>(kp);
   CUDA_TRY(cudaGetLastError());
+  if (rec) CUDA_TRY(cudaEventRecord(ev1, run->stream));
+  return SER_OK;
+}
+
+/* total CUDA-event time of the sweep launches since the last reset and their number (waits for the last one) */
+extern "C" int ser_run_sweep_time(ser_run *run, double *ms, int32_t *n_launches, int32_t reset)
+{
+  if (!run || !ms) return SER_E_ARG;
+  if (set_device(run)) return SER_E_CUDA;
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < run->sweep_ev_used; i += 2) {
+    float t = 0.f;
+    CUDA_TRY(cudaEventSynchronize((*run->sweep_ev)[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&t, (*run->sweep_ev)[i], (*run->sweep_ev)[i + 1]));
+    total += t;
+  }
+  *ms = total;
+  if (n_launches) *n_launches = (int32_t)(run->sweep_ev_used / 2);
+  if (reset) run->sweep_ev_used = 0;
   return SER_OK;
 }
 
@@ -1018,7 +1061,9 @@ extern "C" int ser_run_cross_chain_buffers(ser_run *run, double **d_e_all, int32
   return SER_OK;
 }
 
-extern "C" int ser_microbench(int32_t device, double out[3])
+/* out[0..2] = fp64 FMA TFLOP/s, shared-memory load GB/s, popc Gop/s; out[3..5] (ser_microbench_ex) = the kernel
+ * times in ms they were derived from; work = blocks x threads x iters x {8 FMA x 2 flop, 8 x 16 B, 8 popc} */
+extern "C" int ser_microbench_ex(int32_t device, double out[6])
 {
   if (!out) return SER_E_ARG;
   CUDA_TRY(cudaSetDevice(device));
@@ -1036,23 +1081,33 @@ extern "C" int ser_microbench(int32_t device, double out[3])
     CUDA_TRY(cudaEventRecord(e1)); CUDA_TRY(cudaEventSynchronize(e1));
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   }
-  out[0] = (double)blocks * threads * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+  out[0] = (double)blocks * threads * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12; out[3] = ms;
   for (int rep = 0; rep < 2; rep++) {
     CUDA_TRY(cudaEventRecord(e0));
     mb_lds_kernel<<<blocks, threads>>>((unsigned *)buf, iters / 4);
     CUDA_TRY(cudaEventRecord(e1)); CUDA_TRY(cudaEventSynchronize(e1));
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   }
-  out[1] = (double)blocks * threads * (iters / 4) * 8.0 * 16.0 / (ms * 1e-3) / 1e9;
+  out[1] = (double)blocks * threads * (iters / 4) * 8.0 * 16.0 / (ms * 1e-3) / 1e9; out[4] = ms;
   for (int rep = 0; rep < 2; rep++) {
     CUDA_TRY(cudaEventRecord(e0));
     mb_popc_kernel<<<blocks, threads>>>((unsigned *)buf, iters);
     CUDA_TRY(cudaEventRecord(e1)); CUDA_TRY(cudaEventSynchronize(e1));
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   }
-  out[2] = (double)blocks * threads * iters * 8.0 / (ms * 1e-3) / 1e9;
+  out[2] = (double)blocks * threads * iters * 8.0 / (ms * 1e-3) / 1e9; out[5] = ms;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(buf);
+  return SER_OK;
+}
+
+extern "C" int ser_microbench(int32_t device, double out[3])
+{
+  double all[6];
+  if (!out) return SER_E_ARG;
+  const int rc = ser_microbench_ex(device, all);
+  if (rc) return rc;
+  out[0] = all[0]; out[1] = all[1]; out[2] = all[2];
   return SER_OK;
 }
 

@@ -373,4 +373,26 @@ void emul_get_cd(void *p, double *c, double *d) {
   for (int m = 0; m < ch.M; m++) { c[m] = ch.WT(m).c; d[m] = ch.WT(m).d; }
 }
 
+
+/* ---- the product's bit-reproducible math / samplers (csrc/ser_detmath.h, ser_chain_core.h), exported so that
+ * tests can validate them INDEPENDENTLY of the oracle, which includes the same header (tests/test_detmath.py) */
+void emul_detmath_log(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = ser_log(x[i]); }
+void emul_detmath_exp(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = ser_exp(x[i]); }
+void emul_exp_weight(const double *x, int n, double *out) { for (int i = 0; i < n; i++) out[i] = ser_exp_weight(x[i]); }
+/* n Gamma(shape, 1) variates: the draw of chain `chain0 + i`, sweep 0, block 0 of the structured stream */
+void emul_gamma(double shape, uint32_t seed, uint32_t chain0, int n, double *out)
+{
+  for (int i = 0; i < n; i++) out[i] = ser_gamma_ge1(shape, seed, chain0 + (uint32_t)i, 0u, 0u);
+}
+/* n Beta(a, b) variates exactly as the sweep forms them: two Gammas from blocks 0 and 1 */
+void emul_beta(double a, double b, uint32_t seed, uint32_t chain0, int n, double *out)
+{
+  for (int i = 0; i < n; i++)
+    out[i] = ser_beta_from_gammas(ser_gamma_ge1(a, seed, chain0 + (uint32_t)i, 0u, 0u), ser_gamma_ge1(b, seed, chain0 + (uint32_t)i, 0u, 1u));
+}
+void emul_uniform(uint32_t seed, uint32_t chain, uint32_t sweep, uint32_t block, int n, double *out)
+{
+  for (int i = 0; i < n; i++) out[i] = ser_stream_uniform(seed, chain, sweep, block, (uint32_t)i);
+}
+
 } // extern "C"

@@ -184,3 +184,51 @@ def test_probability_map_finalisers_match_script_semantics(S, oracle_mod):
     assert np.allclose(S.false_ones_probability_matrix(batch, chains, k), oracle_mod.false_ones_matrix(a_s, b_s, pis, k, X), rtol=0, atol=1e-13)
     Y = S.new_data_matrix(batch, chains, k)
     assert Y.shape == (N, M) and Y.sum() == X.sum()
+
+
+# ----------------------------------------------------------------------------- the ABI struct and INTEGRATION.md
+def _integration_snippet():
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    level2 = text[text.index("## Level 2"):]
+    return level2[level2.index("```python\n") + len("```python\n"):level2.index("\n```\n")]
+
+
+def test_integration_snippet_matches_the_abi(S):
+    """INTEGRATION.md's ctypes RunConfig, api.RunConfig and the header's ser_run_config list the same fields in
+    the same order with the same widths (round 1 shipped a doc struct one field short)."""
+    header = open(os.path.join(ROOT, "include", "seriation_b200.h")).read()
+    body = header[header.index("typedef struct ser_run_config {"):header.index("} ser_run_config;")]
+    h_fields = re.findall(r"^\s*(u?int32_t)\s+([a-z_]+);", body, re.M)
+    ctype = {"int32_t": C.c_int32, "uint32_t": C.c_uint32}
+    want = [(name, ctype[t]) for t, name in h_fields]
+    assert len(want) == 10 and want[0][0] == "struct_size"
+    assert [(n, t) for n, t in S.RunConfig._fields_] == want
+    ns = {}
+    snippet = _integration_snippet()
+    exec(snippet[snippet.index("class RunConfig"):snippet.index("n_chains, burn, samples, k =")], {"C": C}, ns)
+    assert [(n, t) for n, t in ns["RunConfig"]._fields_] == want
+    assert C.sizeof(ns["RunConfig"]) == C.sizeof(S.RunConfig) == 4 * len(want)
+
+
+def test_run_create_refuses_a_struct_of_another_size(S):
+    """a caller built against another layout is refused before anything is read past its struct"""
+    ds = S.Dataset.from_bits(np.eye(4, 3, dtype=np.uint8))
+    cfg = S.RunConfig(C.sizeof(S.RunConfig) - 4, 1, 0, 10, 0, 0, 0, 0, 0, 0)
+    h = C.c_void_p()
+    assert S.lib().ser_run_create(ds._h, C.byref(cfg), C.byref(h)) == -1 and not h.value
+    assert b"struct_size" in S.lib().ser_last_error()
+    assert S.lib().ser_multi_create(ds._h, C.byref(cfg), 1, None, C.byref(h)) == -1 and not h.value
+
+
+def test_compute_entry_points_fail_loudly_without_a_device(S):
+    """no CPU fallback: on a box without a GPU every compute entry point says so"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    ds = S.Dataset.from_bits(np.eye(4, 3, dtype=np.uint8))
+    with pytest.raises(S.SeriationError) as e:
+        S.Run(ds, 2)
+    assert "no CUDA device" in str(e.value) and "no CPU path" in str(e.value)
+    with pytest.raises(S.SeriationError) as e:
+        S.Multi(ds, 4, 2)
+    assert "no CUDA device" in str(e.value)

@@ -740,3 +740,293 @@ def test_live_runs_of_different_shapes_interleave(S):
         r.sync()
         assert r.check() == 0
         r.close()
+
+
+# ----------------------------------------------------------------------------- round 2: longer replays, config 5 vs the reference
+def _oracle_chains_parallel(O, X, hard, seeds, burn, samp):
+    """the oracle's chains on all host cores (ctypes releases the GIL inside orc_run)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        return list(ex.map(lambda s: _oracle_chain(O, X, hard, s, burn, samp), seeds))
+
+
+def _replay_case_parallel(S, O, X, hard, seeds, burn, samp):
+    chains = _oracle_chains_parallel(O, X, hard, seeds, burn, samp)
+    run = S.Run(S.Dataset.from_bits(X, hard), len(seeds), mode=S.MODE_REPLAY, store=S.STORE_FULL, max_samples=samp)
+    run.set_tapes([c[4] for c in chains]).init().advance_both(burn, samp).sync()
+    assert run.check() == 0
+    stats = run.chain_stats()
+    for i, (o, init, res, final, tape) in enumerate(chains):
+        _cmp_state(run.state(i), final, ("final", i))
+        assert run.state(i)["slots"] == tape.size and run.state(i)["loglik"] == final.loglik
+        _cmp_samples(run.fetch_samples(i), res, ("samples", i))
+        assert stats["e_negloglik"][i] == res["sums"][0] / samp
+        # every float decision of this tape stayed away from its boundary (see test_oracle_golden.py).  With ~1e7 picks x
+        # ~500 CDF steps per chain set the closest approach is expected around 1e-11; the GPU's CDF is good to ~1e-14
+        m = o.margins()
+        assert m["min_pick"] > 1e-12 and m["min_accept"] > 1e-10, (i, m)
+    run.close()
+
+
+@pytest.mark.parametrize("name", NOW)
+def test_replay_2000_sweeps_16_chains_now_subsets(S, oracle_mod, name):
+    """16 chains x (1000 burn-in + 1000 sampling) sweeps on every NOW subset: all 100 thinned samples per chain
+    (a, b, pi, c, d and the bits of the saved log-likelihood), final state, cursor, exp_data sums."""
+    X, hard = load_hex_dataset(name)
+    _replay_case_parallel(S, oracle_mod, X, hard, list(range(200, 216)), 100, 100)
+
+
+def test_replay_config2_100_chains_1000_sweeps(S, oracle_mod):
+    """BASELINE.json config 2 (g10s2, 100 chains, seeds 0..99) at 1000 sweeps per chain"""
+    X, hard = load_hex_dataset("g10s2")
+    _replay_case_parallel(S, oracle_mod, X, hard, list(range(100)), 50, 50)
+
+
+def test_config5_replay_vs_unmodified_reference_golden(S, oracle_mod):
+    """BASELINE.json config 5's matrix against the UNMODIFIED reference: tests/golden/ref_synthetic_1024x4096.npz holds
+    the states oracle/_ref/ref_mcmc_big (mcmc.c with MAXS raised, nothing else) went through for 8 seeds x 10
+    mcmc_sample() calls = 100 sweeps.  The tapes (53 MB) are regenerated from the seeds by the oracle's MT19937 --
+    length and CRC must equal the reference's recorded tapes -- and replayed through the large-shape kernel:
+    a, b, pi, c, d and the saved log-likelihood bits of every call, totals and cursor at the end."""
+    import zlib
+    g = np.load(os.path.join(GOLDEN, "ref_synthetic_1024x4096.npz"))
+    X, hard = S.Dataset.synthetic(1024, 4096, 16).arrays()
+    assert [zlib.crc32(X.tobytes()), zlib.crc32(hard.tobytes())] == g["x_crc"].tolist()
+    seeds, calls = [int(s) for s in g["seeds"]], g["a"].shape[1] - 1
+    chains = _oracle_chains_parallel(oracle_mod, X, hard, seeds, 0, calls)
+    for i, c in enumerate(chains):
+        assert c[4].size == int(g["tape_len"][i]) and zlib.crc32(c[4].tobytes()) == int(g["tape_crc"][i]), i
+    run = S.Run(S.Dataset.from_bits(X, hard), len(seeds), mode=S.MODE_REPLAY, store=S.STORE_FULL, max_samples=calls)
+    run.set_tapes([c[4] for c in chains]).init().sync()
+    for i in range(len(seeds)):
+        st = run.state(i)
+        for k in ("a", "b", "pi"):
+            assert np.array_equal(st[k], g[k][i][0].astype(np.int32)), ("init", i, k)
+    run.advance(calls, True).sync()
+    assert run.check() == 0
+    for i in range(len(seeds)):
+        got, st = run.fetch_samples(i), run.state(i)
+        for k in ("a", "b", "pi"):
+            assert np.array_equal(got[k], g[k][i][1:].astype(np.int32)), (i, k)
+        assert np.array_equal(got["c"], g["cdl"][i][1:, 0]) and np.array_equal(got["d"], g["cdl"][i][1:, 1]), i
+        assert np.array_equal(got["loglik"], g["cdl"][i][1:, 2]), (i, np.max(np.abs(got["loglik"] - g["cdl"][i][1:, 2])))
+        assert np.array_equal(st["tot"], g["tot"][i][-1]) and st["slots"] == int(g["slots"][i][-1]), i
+    run.close()
+
+
+def test_fuzz_replay_40_cases_all_variants(S):
+    """tools/fuzz_replay.py as a driver-visible test: 40 random shapes / densities / hard-site counts, each through the
+    one-thread-per-column kernel, the per-taxon c/d instantiation, the large-shape kernel (random block size and
+    group budget), a random column-group count, and three free-running variants -- 7 variants per case, bit-exact
+    against the oracle.  The differential evidence that the hand-placed barriers of the sweep kernels hold."""
+    from tools.fuzz_replay import run_fuzz
+    out = run_fuzz(40, seed=2026)
+    assert out["passed"], out["failures"][:3]
+    assert len(out["refused"]) < 40   # most variants actually ran
+
+
+def _batch_fingerprint(S, ds, n, seed, burn, samp, **kw):
+    run = S.Run(ds, n, seed=seed, store=S.STORE_PI, max_samples=samp, **kw).init().advance_both(burn, samp).sync()
+    assert run.check() == 0
+    st = run.chain_stats()
+    states = [run.state(i) for i in (0, 1, n // 2, n - 1)]
+    po = run.po_counts(np.array([0, n // 3, n - 1], np.int32))
+    cnt = np.stack([run.counters(i) for i in (0, n - 1)])
+    run.close()
+    return st, states, po, cnt
+
+
+def _same_fingerprint(x, y):
+    for k in ("e_negloglik", "e_c", "e_d"):
+        assert x[0][k].tobytes() == y[0][k].tobytes(), k
+    for sa, sb in zip(x[1], y[1]):
+        for k in ("a", "b", "pi", "rpi", "t0", "f0", "t1", "f1", "tot"):
+            assert np.array_equal(sa[k], sb[k]), k
+        assert (sa["c"], sa["d"], sa["loglik"]) == (sb["c"], sb["d"], sb["loglik"])
+    assert np.array_equal(x[2], y[2]) and np.array_equal(x[3], y[3])
+
+
+def test_determinism_across_runs_and_schedules(S, monkeypatch):
+    """race evidence without a race detector: the same 4096-chain free-running batch gives identical bits when run
+    twice, with other column-group counts, with one-call work items, with an odd number of persistent CTAs (other
+    chain -> SM interleavings) and through the large-shape kernel."""
+    X, hard = load_hex_dataset("g5s5")
+    ds = S.Dataset.from_bits(X, hard)
+    base = _batch_fingerprint(S, ds, 4096, 99, 3, 3)
+    _same_fingerprint(base, _batch_fingerprint(S, ds, 4096, 99, 3, 3))
+    for env in ({"SER_SWEEP_GROUPS": "1"}, {"SER_SWEEP_GROUPS": "4"}, {"SER_CHUNK_CALLS": "1"}, {"SER_SWEEP_SLOTS": "37"},
+                {"SER_CHUNK_CALLS": "2", "SER_SWEEP_SLOTS": "1000"}, {"SER_FORCE_BIG": "256"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _same_fingerprint(base, _batch_fingerprint(S, ds, 4096, 99, 3, 3))
+        for k in env:
+            monkeypatch.delenv(k)
+
+
+def test_work_items_of_one_call_with_few_chains(S, oracle_mod, monkeypatch):
+    """fewer chains than persistent CTAs and one-call work items: a chain's items run on different SMs back to back,
+    each waiting for the previous one's published state (bit columns included) -- still bit-exact vs the oracle"""
+    monkeypatch.setenv("SER_CHUNK_CALLS", "1")
+    X, hard = load_hex_dataset("g10s10")
+    _replay_case(S, oracle_mod, X, hard, [3, 4, 5], 12, 12)
+    _manycd_replay_case(S, oracle_mod, X, hard, [6], 4, 4)
+
+
+def test_advance_both_equals_two_launches(S):
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    one = S.Run(ds, 300, seed=8, store=S.STORE_PI, max_samples=4).init().advance_both(5, 4).sync()
+    two = S.Run(ds, 300, seed=8, store=S.STORE_PI, max_samples=4).init().advance(5, False).advance(4, True).sync()
+    assert one.chain_stats()["e_negloglik"].tobytes() == two.chain_stats()["e_negloglik"].tobytes()
+    for i in (0, 150, 299):
+        assert np.array_equal(one.fetch_samples(i, full=False)["pi"], two.fetch_samples(i, full=False)["pi"])
+        assert one.state(i)["loglik"] == two.state(i)["loglik"]
+    assert one.kernel_launches() < two.kernel_launches()
+
+
+# ----------------------------------------------------------------------------- round 2: the boundary
+def test_integration_snippet_runs(S, tmp_path, monkeypatch):
+    """INTEGRATION.md's Level-2 ctypes snippet, executed as printed (only the run length is shortened)"""
+    from tools.datasets import write_txt
+    text = open(os.path.join(os.path.dirname(GOLDEN), "..", "INTEGRATION.md")).read()
+    level2 = text[text.index("## Level 2"):]
+    snippet = level2[level2.index("```python\n") + len("```python\n"):level2.index("\n```\n")]
+    line = "n_chains, burn, samples, k = 4096, 1000, 1000, 2"
+    assert line in snippet
+    snippet = snippet.replace(line, "n_chains, burn, samples, k = 256, 20, 20, 2")
+    (tmp_path / "Dataset").mkdir()
+    write_txt(str(tmp_path / "Dataset" / "g10s10.txt"), *load_hex_dataset("g10s10"))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("SERIATION_B200_LIB", S.LIB_PATH)
+    ns = {}
+    exec(snippet, ns)
+    po = np.array(ns["po"][:]).reshape(124, 124)
+    assert ns["nk"].value == 2 and np.all(np.diag(po) < 0) and 0 <= ns["chosen"][0] < ns["chosen"][1] < 256
+    # the same numbers through the shipped wrapper
+    run = S.Run(S.Dataset.from_bits(*load_hex_dataset("g10s10")), 256, seed=20060206, store=S.STORE_PI, max_samples=20)
+    res = run.init().advance_both(20, 20).cross_chain(2)
+    assert list(res["chosen"]) == list(ns["chosen"][:]) and np.array_equal(S.po_finalize(res["counts"], 2), po)
+
+
+def test_cross_chain_one_call_equals_the_separate_steps(S, oracle_mod):
+    X, hard = load_hex_dataset("g10s10")
+    n, samp, k = 500, 10, 4
+    run = S.Run(S.Dataset.from_bits(X, hard), n, seed=7, chain_offset=1000, store=S.STORE_PI, max_samples=samp)
+    run.init().advance_both(15, samp)
+    res = run.cross_chain(k)
+    e = run.chain_stats()["e_negloglik"]
+    want = oracle_mod.choose_chains(e, k)
+    assert [c - 1000 for c in res["chosen"]] == want             # GLOBAL ids out
+    assert res["min"] == e.min() and abs(res["sigma"] - np.std(e)) < 1e-9
+    assert np.array_equal(res["counts"], run.po_counts(np.array(want, np.int32) + 1000))
+    for c, ch in enumerate(want):
+        assert np.array_equal(res["counts"][c], oracle_mod.pair_order_counts(run.fetch_samples(ch, full=False)["pi"]))
+    # a one-rank NCCL communicator goes through the collective code path and changes nothing
+    comm = S.Comm(S.Comm.unique_id(), 1, 0, 0)
+    run0 = S.Run(S.Dataset.from_bits(X, hard), n, seed=7, chain_offset=1000, store=S.STORE_PI, max_samples=samp).init().advance_both(15, samp)
+    res0 = run0.cross_chain(k, comm=comm)
+    assert [c - 1000 for c in res0["chosen"]] == want and np.array_equal(res0["counts"], res["counts"])
+    comm.close()
+
+
+def test_pair_order_uses_each_chains_own_sample_count(S, oracle_mod):
+    """a chain whose tape ran out early holds fewer samples than chain 0: its slab counts ITS samples (round 1 took T
+    from chain 0 for every chain)"""
+    X, hard = load_hex_dataset("g10s10")
+    full = _oracle_chain(oracle_mod, X, hard, 5, 0, 6)
+    short = _oracle_chain(oracle_mod, X, hard, 6, 0, 3)
+    run = S.Run(S.Dataset.from_bits(X, hard), 2, mode=S.MODE_REPLAY, store=S.STORE_PI, max_samples=6)
+    run.set_tapes([full[4], short[4]]).init().advance(6, True).sync()
+    counts = run.po_counts(np.array([0, 1], np.int32))
+    assert counts[0][0, 0] == -6 and counts[1][0, 0] == -3
+    assert np.array_equal(counts[1], oracle_mod.pair_order_counts(short[2]["pi"]))
+    with pytest.raises(S.SeriationError):
+        run.posterior_sums([0, 1])          # the mirrors assume one T: chains that disagree are refused, not mis-scaled
+
+
+def test_site_age_correlation_against_numpy(S, tmp_path):
+    """CORR_MN (Report Table 1) with the .sites chronology in place of the file order"""
+    X, hard = load_hex_dataset("g10s10")
+    N, M = X.shape
+    rng = np.random.default_rng(5)
+    mn = np.sort(rng.integers(2, 14, N))
+    age = np.round(22.0 - 1.1 * mn + rng.random(N) * 0.5, 2)
+    (tmp_path / "t.genus").write_text("".join("G%d \n" % m for m in range(M)))
+    (tmp_path / "t.sites").write_text("".join("S%d [%d,%s]%s\n" % (n, mn[n], repr(float(age[n])), " *" if hard[n] else "") for n in range(N)))
+    ds = S.Dataset.from_bits(X, hard).read_names(str(tmp_path / "t.genus"), str(tmp_path / "t.sites"))
+    run = S.Run(ds, 40, seed=3, store=S.STORE_PI, max_samples=30).init().advance_both(100, 30).sync()
+    chosen = S.select_chains(run.chain_stats()["e_negloglik"], 3)[0]
+    ca, cm = run.site_age_corr(chosen)
+    pis = [run.fetch_samples(int(c), full=False)["pi"] for c in chosen]
+    want_mn = np.mean([np.mean([np.corrcoef(p, mn)[0, 1] for p in ps]) for ps in pis])
+    want_age = np.mean([np.mean([np.corrcoef(p, -age)[0, 1] for p in ps]) for ps in pis])
+    assert abs(cm - want_mn) < 1e-12 and abs(ca - want_age) < 1e-12
+    assert abs(cm) > 0.5                     # the sampler recovers the chronology (either direction of time)
+
+
+# ----------------------------------------------------------------------------- round 2: multi-GPU behind the C ABI
+def test_multi_on_one_device_equals_a_plain_run(S, oracle_mod):
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    n, k = 700, 3
+    m = S.Multi(ds, n, 1, seed=11, chain_offset=50, store=S.STORE_PI, max_samples=5).init().advance(6, 5).sync()
+    assert m.check() == 0 and m.layout() == dict(n_gpus=1, chains_per_gpu=[n], peer_stores=True)
+    run = S.Run(ds, n, seed=11, chain_offset=50, store=S.STORE_PI, max_samples=5).init().advance_both(6, 5).sync()
+    assert m.chain_stats()["e_negloglik"].tobytes() == run.chain_stats()["e_negloglik"].tobytes()
+    a, b = m.cross_chain(k), run.cross_chain(k)
+    assert list(a["chosen"]) == list(b["chosen"]) and np.array_equal(a["counts"], b["counts"])
+    r, loc = m.locate(50 + 123)
+    assert loc == 123 and np.array_equal(r.state(loc)["pi"], run.state(123)["pi"])
+    m.close()
+
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("nccl", [False, True])
+def test_multi_gpu_sharding_is_invisible(S, monkeypatch, nccl):
+    """the chains of one call over all GPUs of the box (ser_multi_*): same chosen chains, same pair-order counts, same
+    per-chain statistics as one GPU, through the kernels' own peer stores and through NCCL"""
+    G = _device_count()
+    if G < 2:
+        pytest.skip("one GPU on this box")
+    if nccl:
+        monkeypatch.setenv("SER_MULTI_NCCL", "1")
+    X, hard = load_hex_dataset("g10s10")
+    ds = S.Dataset.from_bits(X, hard)
+    n, k = 64 * G if nccl else 64 * G + 3, 4       # uneven blocks are fine with peer stores
+    m = S.Multi(ds, n, G, seed=21, store=S.STORE_PI, max_samples=6).init().advance(8, 6).sync()
+    assert m.check() == 0 and m.layout()["peer_stores"] == (not nccl)
+    run = S.Run(ds, n, seed=21, store=S.STORE_PI, max_samples=6).init().advance_both(8, 6).sync()
+    assert m.chain_stats()["e_negloglik"].tobytes() == run.chain_stats()["e_negloglik"].tobytes()
+    for _ in range(2):                               # twice: the second call reuses the peer buffers
+        a, b = m.cross_chain(k), run.cross_chain(k)
+        assert list(a["chosen"]) == list(b["chosen"]) and a["min"] == b["min"] and a["sigma"] == b["sigma"]
+        assert np.array_equal(a["counts"], b["counts"])
+    m.close()
+
+
+def test_cli_multi_gpu_and_index_check(S, tmp_path):
+    import subprocess
+    from tools.datasets import write_txt
+    X, hard = load_hex_dataset("g10s10")
+    ds = tmp_path / "g10s10.txt"
+    write_txt(str(ds), X, hard)
+    exe = os.path.join(S.PKG_DIR, "mcmc")
+    with open(ds) as f:   # an index without a Chains/chain_XX directory is refused up front (it used to run and write nothing)
+        r = subprocess.run([exe, "100"], stdin=f, cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "0..99" in r.stderr
+    G = min(_device_count(), 8)
+    outs = []
+    for g in sorted({1, G}):
+        out = subprocess.run([exe, "--chains", "640", "--gpus", str(g), "--burn", "10", "--samples", "8", "--seed", "4", "--dataset", str(ds),
+                              "--select", "3", "--po", str(tmp_path / ("po%d.csv" % g))], check=True, capture_output=True, text=True)
+        assert "gpus %d" % g in out.stdout and "no chain files" not in out.stderr
+        outs.append([ln for ln in out.stdout.split("\n") if ln.startswith(("selection", "E[c]"))])
+        po = np.loadtxt(tmp_path / ("po%d.csv" % g), delimiter=",")
+        assert po.shape == (124, 124)
+    assert all(o == outs[0] for o in outs)
+    if G > 1:
+        assert (tmp_path / "po1.csv").read_bytes() == (tmp_path / ("po%d.csv" % G)).read_bytes()

@@ -143,3 +143,47 @@ def test_reference_pipeline_golden_reproduces_report_table1(oracle_mod):
     po = g["po"].astype(np.float64)
     off = ~np.eye(124, dtype=bool)
     assert np.allclose((po + po.T)[off], 1.0, atol=2e-3)   # 8 chains x 1000 samples / 1000 / 8 (+ the carry-over quirk's 1e-3)
+
+
+@pytest.mark.parametrize("name", ["ref_g10s10", "ref_g10s2", "ref_g5s5", "ref_g2s2", "ref_g10s10_philox", "ref_g10s10_manycd"])
+def test_golden_tapes_keep_every_float_decision_far_from_its_boundary(oracle_mod, name):
+    """SURVEY section 7 "decisions must match; floats need not": the GPU evaluates the Gibbs weights in another order
+    (closed-form runs) and with its own exp, so its picks equal the reference's only while no draw lands within
+    rounding distance of a CDF step or of an accept threshold.  Audit the committed tapes: the smallest distance
+    of a uniform from the neighbouring CDF steps (mcmc_randompick, mcmc.c:910-913; probabilities sum to 1) and
+    the smallest |delta - log u| of the MH tails (mcmc.c:1261/:1441/:1636) stay many orders above 1e-12."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    X, hard = load_hex_dataset("g10s10" if "g10s10" in name else name[4:])
+    o = oracle_mod.Oracle(X, hard)
+    if name.endswith("manycd"):
+        o.manycd()
+    o.source_tape(g["tape"])
+    o.randomize()
+    for _ in range(1, len(g["kind"])):
+        o.sample()
+    assert o.slots == g["tape"].size and o.tape_mismatches == 0
+    m = o.margins()
+    assert m["n_proposals"] >= 16 * 10 * (len(g["kind"]) - 1) - 5 * 10 * (len(g["kind"]) - 1)   # hard-site refusals skip the tail
+    assert m["min_pick"] > 1e-9, m
+    assert m["min_accept"] > 1e-9, m
+
+
+def test_restatement_matches_reference_on_the_config5_matrix(oracle_mod):
+    """tests/golden/ref_synthetic_1024x4096.npz (tools/make_golden_big.py): the UNMODIFIED reference (MAXS raised so
+    it can read 8 192-character rows) on the 1024 x 4096 synthetic matrix of BASELINE.json config 5.  CPU suite:
+    chain 0 through its first two calls (20 sweeps); the GPU suite replays all 8 chains x 100 sweeps."""
+    import zlib
+    import seriation_b200 as S
+    g = np.load(os.path.join(GOLDEN, "ref_synthetic_1024x4096.npz"))
+    X, hard = S.Dataset.synthetic(1024, 4096, 16).arrays()
+    assert [zlib.crc32(X.tobytes()), zlib.crc32(hard.tobytes())] == g["x_crc"].tolist()   # the generator is frozen
+    o = oracle_mod.Oracle(X, hard).source_mt(int(g["seeds"][0])).record(True)
+    o.randomize()
+    for r in range(3):
+        if r:
+            o.sample()
+        st = o.state()
+        for k in ("a", "b", "pi"):
+            assert np.array_equal(getattr(st, k), g[k][0][r].astype(np.int32)), (k, r)
+        assert np.array_equal(st.tot, g["tot"][0][r]) and st.slots == int(g["slots"][0][r])
+        assert (st.c, st.d, st.loglik) == tuple(g["cdl"][0][r]), r

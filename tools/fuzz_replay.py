@@ -52,9 +52,9 @@ def compare(run, states, burn, samp, manycd):
     return bad
 
 
-def main():
-    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+def run_fuzz(cases=60, seed=1):
+    """-> dict(cases, variants_per_case, failures, refused, passed); also used by tests/test_gpu_parity.py"""
+    rng = np.random.default_rng(seed)
     failures, log = [], []
     for case in range(cases):
         N = int(rng.integers(2, 300)) if rng.random() < 0.8 else int(rng.integers(300, 700))
@@ -125,7 +125,13 @@ def main():
                     os.environ.pop(k, None)
             if bad:
                 failures.append(dict(case=case, variant=name, N=N, M=M, density=dens, nh=nh, bad=[str(b_) for b_ in bad[:6]]))
-    out = dict(cases=cases, variants_per_case=7, failures=failures, refused=log, passed=not failures)
+    return dict(cases=cases, variants_per_case=7, failures=failures, refused=log, passed=not failures)
+
+
+def main():
+    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    out = run_fuzz(cases, int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    failures, log = out["failures"], out["refused"]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "fuzz_replay.json"), "w") as f:
         json.dump(out, f, indent=1)
