@@ -239,6 +239,11 @@ def main():
     import torch.distributed as dist
     import seriation_b200 as S
 
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) write to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -370,7 +375,7 @@ def main():
             v, kind = cpu_reference_run(args.dataset, ccalls, procs)
             cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": kind, "sample": cpu_sample_text(procs, ccalls, args.dataset)}
         h2d, d2h = job.bytes_per_step()
-        print(json.dumps({
+        line = json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": ("synthetic 1024 x 4096 occurrence matrix (ser_dataset_synthetic), Philox free-running chains" if big else
@@ -384,7 +389,9 @@ def main():
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                    "ms_per_step": dt_e2e / args.steps * 1e3},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "also": also or None,
-        }))
+        })
+        sys.stdout.flush()
+        os.write(json_fd, (line + "\n").encode())
     if comm is not None:
         comm.close()
     if world > 1:
