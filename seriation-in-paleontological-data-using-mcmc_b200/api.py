@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libseriation_b200.so")
+LIB_PATH = os.environ.get("SERIATION_B200_LIB") or os.path.join(HERE, "libseriation_b200.so")  # the override: instrumented builds
 
 MODE_FREE, MODE_REPLAY = 0, 1
 STORE_NONE, STORE_PI, STORE_FULL = 0, 1, 2

@@ -1,6 +1,23 @@
 /* ser_device_common.cuh -- kernel parameters, the shared-memory carve-up, block helpers and the init kernel.
  * Part of the single translation unit ser_kernels.cu (included there, in this order). */
 
+/* phase timing of the sweep kernels (debug builds: NVCC_EXTRA=-DSER_PHASE_TIMING): thread 0 of every
+ * CTA adds the cycles between marks; ser_debug_phase_cycles() reads and clears the totals */
+#ifdef SER_PHASE_TIMING
+__device__ unsigned long long ser_phase_cycles[24];
+#define PHASE_T0() long long ph_t = clock64()
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long ph_n = clock64(); atomicAdd(&ser_phase_cycles[i], (unsigned long long)(ph_n - ph_t)); ph_t = ph_n; } } while (0)
+extern "C" int ser_debug_phase_cycles(unsigned long long out[24])
+{
+  unsigned long long zero[24] = {0};
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out, ser_phase_cycles, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(ser_phase_cycles, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define PHASE_T0() do { } while (0)
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 /* ------------------------------------------------------------------ per-chain global state */
 struct __align__(16) ChainScalars { /* a multiple of 16 bytes: loaded / stored as int4 words */
   double c, cc, d, dd; /* log P(false 1), log(1-e^c), log P(false 0), log(1-e^d) */

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
     const bool sampling = call >= p.burn_calls; /* burn-in calls first, then sampling calls (mcmc.c:140-143, :180-185) */
     for (int s = 0; s < p.sweeps_per_call; s++) {
       __syncthreads(); /* every thread is done reading the previous sweep's staged draws */
+      PHASE_T0();
       double ua = 0.0, ub = 0.0;
       if constexpr (MANY) {
         /* ================= draws: M Betas for c, M for d, 2M uniforms, then the pi draws ================= */
@@ -309,7 +310,9 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
        * item formulation (ser_chain_core.h): postings of the column, then for the a-step and
        * the b-step: per-column maximum (own thread), item weights (dense over the CTA),
        * per-column scan + inverse CDF (own thread). */
+      PHASE_MARK(8);
       if (is_taxon) ser_expand_ones(col, C, W, sm.pos + off_c);
+      PHASE_MARK(9);
       int changed = 0;
 #pragma unroll 1
       for (int step = 0; step < 2; step++) {
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           sm.st4[4 * tid + 2] = (uint16_t)st.ocur; sm.st4[4 * tid + 3] = (uint16_t)st.kb;
         }
         __syncthreads();
+        PHASE_MARK(10);
 #pragma unroll 1
         for (int g = 0; g < p.n_groups; g++) { /* columns grp_c[g]..grp_c[g+1] = items grp_e[g]..grp_e[g+1] */
           const int e0 = p.grp_e[g], e1 = p.grp_e[g + 1];
@@ -348,11 +352,13 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             }
           }
           __syncthreads();
+          PHASE_MARK(11);
           if (is_taxon && tid >= p.grp_c[g] && tid < p.grp_c[g + 1]) {
             const int pick = ser_step_pick<MANY ? 0 : 1>(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
             if (step == 0) { changed += pick != a; a = pick; }
             else { changed += (N - pick) != b; b = N - pick; }
           }
+          PHASE_MARK(12);
         }
       }
       /* the log-likelihood is only ever observed after the last sweep of a sampling call
@@ -400,7 +406,9 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
 
       /* ================= 16 proposals for pi (mcmc.c:237-243) ================= */
       ps.k = 0;
+      PHASE_MARK(13);
       for (int prop = 0; prop < 16; prop++) {
+        PHASE_MARK(14 + (prop <= 1 ? 3 : ((prop + 1) % 3))); /* charged to the PREVIOUS proposal's kind: 14 pi1, 15 pi2, 16 pi3, 17 swap */
         /* order: pi2(swap), then 5 x (pi1, pi2(0), pi3) */
         const int kind = prop == 0 ? 3 : ((prop - 1) % 3); /* 0 pi1, 1 pi2(0), 2 pi3, 3 pi2(swap) */
         int dt0 = 0, dt1 = 0, D0, D1;
@@ -484,6 +492,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
         __syncthreads(); /* columns / hard mask / rpi visible before the next proposal */
       }
 
+      PHASE_MARK(16);
       if (p.mode == SER_MODE_REPLAY) sc.cursor += (MANY ? 8 * (long long)M : 6 + 2 * (long long)M) + ps.k;
       else sc.sweep++;
       sc.counters[7]++;
@@ -564,19 +573,3 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
   } /* work items */
 }
 
-/* phase timing of the large-shape kernel (debug builds: NVCC_EXTRA=-DSER_PHASE_TIMING): thread 0 of every
- * CTA adds the cycles between marks; ser_debug_phase_cycles() reads and clears the totals */
-#ifdef SER_PHASE_TIMING
-__device__ unsigned long long ser_phase_cycles[8];
-#define PHASE_T0() long long ph_t = clock64()
-#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long ph_n = clock64(); atomicAdd(&ser_phase_cycles[i], (unsigned long long)(ph_n - ph_t)); ph_t = ph_n; } } while (0)
-extern "C" int ser_debug_phase_cycles(unsigned long long out[8])
-{
-  unsigned long long zero[8] = {0};
-  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(out, ser_phase_cycles, sizeof(zero)) != cudaSuccess) return -1;
-  return cudaMemcpyToSymbol(ser_phase_cycles, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
-}
-#else
-#define PHASE_T0() do { } while (0)
-#define PHASE_MARK(i) do { } while (0)
-#endif

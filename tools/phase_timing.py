@@ -6,7 +6,7 @@ import seriation_b200 as S
 ds = S.Dataset.synthetic(1024, 4096, 16)
 run = S.Run(ds, 296, seed=1, store=S.STORE_PI, max_samples=4)
 run.init().advance(1, False).sync()
-out = (C.c_ulonglong * 8)()
+out = (C.c_ulonglong * 24)()
 S.lib().ser_debug_phase_cycles(out)
 run.advance(2, True).sync(); ms = run.elapsed_ms(reset=True)
 S.lib().ser_debug_phase_cycles(out)
