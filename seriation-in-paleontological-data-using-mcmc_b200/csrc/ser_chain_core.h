@@ -194,6 +194,9 @@ struct SerHard {
   const uint16_t *hpre; /* hpre[w * C] = #hard positions in words < w, w = 0..W */
   const uint16_t *hp;   /* the nh hard positions, ascending */
   int C, W, N, nh;
+  /* optional lookup tables (the one-thread-per-column kernel keeps them in shared memory; rebuilt whenever a hard
+   * site moves): rank_tab[p] = hard positions < p, p = 0..N; nonhard_tab[r] = position of the r-th non-hard site */
+  const uint16_t *rank_tab, *nonhard_tab;
 };
 
 /* rebuild the sorted list of hard positions from the mask (owner thread, after a move) */
@@ -207,7 +210,7 @@ SER_HD void ser_hard_list(const uint32_t *hcol, int C, int W, uint16_t *hp)
 }
 
 /* number of hard positions < p, p in [0, N] */
-SER_HD int ser_hard_rank(const SerHard &h, int p) { return ser_rank1(h.hcol, h.hpre, h.C, p); }
+SER_HD int ser_hard_rank(const SerHard &h, int p) { return h.rank_tab ? (int)h.rank_tab[p] : ser_rank1(h.hcol, h.hpre, h.C, p); }
 SER_HD int ser_is_hard(const SerHard &h, int p) { return (h.hcol[(p >> 5) * h.C] >> (p & 31)) & 1u; }
 /* number of hard positions in [lo, hi] */
 SER_HD int ser_hard_count(const SerHard &h, int lo, int hi) { return ser_hard_rank(h, hi + 1) - ser_hard_rank(h, lo); }
@@ -216,6 +219,7 @@ SER_HD int ser_hard_count(const SerHard &h, int lo, int hi) { return ser_hard_ra
  * an upper-bound search over the sorted hard list. */
 SER_HD int ser_select_nonhard(const SerHard &h, int r)
 {
+  if (h.nonhard_tab) return (int)h.nonhard_tab[r];
   int lo = 0, hi = h.nh; /* first k with hp[k] - k > r */
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;

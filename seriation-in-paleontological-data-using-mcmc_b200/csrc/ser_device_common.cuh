@@ -79,6 +79,10 @@ struct KParams {
    * Ival doubles: a smaller buffer = more resident chains per SM */
   int n_groups, Ival;
   int grp_c[SER_MAX_GROUPS + 1], grp_e[SER_MAX_GROUPS + 1];
+  /* units of the Gibbs phase: heavy columns are served by 2 / 4 / 8 adjacent lanes (ser_sweep_kernel.cuh) */
+  const uint2 *unit_tab; /* [n_units] = {column | sub << 16 | lsh << 24, first item of the column} */
+  int n_units;
+  int grp_u[SER_MAX_GROUPS + 1]; /* units of column group g = [grp_u[g], grp_u[g+1]) */
 };
 
 /* ------------------------------------------------------------------ shared-memory carve-up */
@@ -100,6 +104,7 @@ struct Smem {
   double *wcol;     /* manycd only: 4*C per-column weights A, g, 1/g, 1/(1-e^-g) for the dense item phase */
   double *redd;     /* manycd only: 2*32 doubles of reduction scratch */
   uint16_t *rpi, *tmp16, *perm16; /* N each */
+  uint16_t *hrank, *nhpos; /* N+2 each: hard positions before p; position of the r-th non-hard site (SerHard's tables) */
 };
 
 __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int N, int W, int C, int I, int manycd = 0, int Ival = -1)
@@ -115,7 +120,9 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
   size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
+  size_t o_hr = take(sizeof(uint16_t) * (N + 2)), o_nh = take(sizeof(uint16_t) * (N + 2));
   if (s) {
+    s->hrank = (uint16_t *)(base + o_hr); s->nhpos = (uint16_t *)(base + o_nh);
     s->logdraw = (double *)(base + o_ld);
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
     s->H = (double *)(base + o_H);
@@ -169,8 +176,22 @@ __device__ void build_columns(const KParams &p, const Smem &sm)
   ser_col_build_pre(sm.V + tid, sm.pre + tid, C, p.W);
 }
 
-/* sorted hard positions from the hard-mask column (its owner thread, tid == M) */
-__device__ void rebuild_hard(const KParams &p, const Smem &sm) { ser_hard_list(sm.V + p.M, p.C, p.W, sm.hp); }
+/* The hard-site tables from the hard-mask column, by all threads of the CTA (the column must be complete: barrier
+ * before; the tables are complete after the next barrier): hrank[q] = hard positions < q, hp[k] = position of the
+ * k-th hard site, nhpos[r] = position of the r-th non-hard site. */
+__device__ __forceinline__ void rebuild_hard(const KParams &p, const Smem &sm)
+{
+  const uint32_t *hcol = sm.V + p.M;
+  const uint16_t *hpre = sm.pre + p.M;
+  for (int q = threadIdx.x; q <= p.N; q += blockDim.x) {
+    const int r = ser_rank1(hcol, hpre, p.C, q);
+    sm.hrank[q] = (uint16_t)r;
+    if (q < p.N) {
+      if ((hcol[(q >> 5) * p.C] >> (q & 31)) & 1u) sm.hp[r] = (uint16_t)q;
+      else sm.nhpos[q - r] = (uint16_t)q;
+    }
+  }
+}
 
 __device__ __forceinline__ void set_weights(SerWeights &wt, double c, double cc, double d, double dd)
 {

@@ -57,6 +57,7 @@ struct ser_run {
   int *d_ones, *d_off;
   uint16_t *d_order;
   uint32_t *d_item_col;
+  uint2 *d_unit_tab;
   uint16_t *d_ab, *d_rpi;
   ChainScalars *d_scal;
   double *d_tape;
@@ -395,6 +396,45 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     kp.gV = run->d_gV; kp.gpre = run->d_gpre;
   }
   kp.n_chains = cfg->n_chains;
+  if (!run->big) {
+    /* Units of the Gibbs phase: a column with many items is served by 2, 4 or 8 adjacent lanes.  Columns are sorted by
+     * occurrence count, so the lane counts are non-increasing along the table and every lane group is aligned inside
+     * its warp.  T = items per lane aimed at: the value that minimises the summed critical path of the rounds
+     * (a round = C units); SER_UNIT_ITEMS forces it. */
+    int bestT = 1 << 30;
+    long long best_cost = -1;
+    auto lsh_of = [](int items, int T) { int l = 0; while (l < 3 && ((items + (1 << l) - 1) >> l) > T) l++; return l; };
+    for (int T = 4; T <= 1024; T++) {
+      std::vector<int> chunk;
+      for (int c = 0; c < M; c++) {
+        const int items = ones[c] + 1, l = lsh_of(items, T);
+        for (int q = 0; q < (1 << l); q++) chunk.push_back((items + (1 << l) - 1) >> l);
+      }
+      long long cost = 0;
+      for (size_t u0 = 0; u0 < chunk.size(); u0 += run->C) {
+        int mx = 0;
+        for (size_t u = u0; u < std::min(chunk.size(), u0 + run->C); u++) mx = std::max(mx, chunk[u]);
+        cost += mx + 6; /* + the fixed cost of a round */
+      }
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; bestT = T; }
+      if (T >= ones[0] + 1) break; /* one lane per column from here on */
+    }
+    if (const char *v = getenv("SER_UNIT_ITEMS")) bestT = std::max(1, atoi(v));
+    std::vector<uint2> units;
+    int g = 0;
+    kp.grp_u[0] = 0;
+    for (int c = 0; c < M; c++) {
+      while (g < kp.n_groups && c == kp.grp_c[g + 1]) kp.grp_u[++g] = (int)units.size();
+      const int l = lsh_of(ones[c] + 1, bestT);
+      for (int q = 0; q < (1 << l); q++) units.push_back(make_uint2((uint32_t)c | ((uint32_t)q << 16) | ((uint32_t)l << 24), (uint32_t)off[c]));
+    }
+    while (g < kp.n_groups) kp.grp_u[++g] = (int)units.size();
+    kp.n_units = (int)units.size();
+    CUDA_TRY(POOL_ALLOC(&run->d_unit_tab, units.size() * sizeof(uint2)));
+    CUDA_TRY(cudaMemcpyAsync(run->d_unit_tab, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice, run->stream));
+    CUDA_TRY(cudaStreamSynchronize(run->stream));
+    kp.unit_tab = run->d_unit_tab;
+  }
   if (!run->big) { /* persistent work-queue grid: bit columns carried between work items, queue head, per-chain progress */
     int per_sm = 1, n_sm = 1;
     const size_t smem = cfg->manycd ? run->smem_many : run->smem_sweep;
@@ -457,7 +497,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
                   run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp,
-                  run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts};
+                  run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts, run->d_unit_tab};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   if (run->stream) cudaStreamSynchronize(run->stream);
   if (run->sweep_ev) {

@@ -90,6 +90,31 @@ __device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, cons
   return accept;
 }
 
+/* A unit of the Gibbs phase: `lpc` = 1 << lsh adjacent lanes serve column c, this lane is number `sub` of them;
+ * off = first item of the column (KParams::unit_tab, built by ser_run_create) */
+struct Unit {
+  int c, sub, lsh, lpc, off;
+  bool live;
+};
+__device__ __forceinline__ Unit unit_load(const KParams &p, int u, int n_units)
+{
+  Unit un;
+  un.live = u < n_units;
+  const uint2 t = un.live ? __ldg(p.unit_tab + u) : make_uint2(0u, 0u);
+  un.c = (int)(t.x & 0xffffu); un.sub = (int)((t.x >> 16) & 0xffu); un.lsh = (int)(t.x >> 24); un.lpc = 1 << un.lsh;
+  un.off = (int)t.y;
+  return un;
+}
+/* the step geometry the column's owner published */
+__device__ __forceinline__ SerStep unit_step(const Smem &sm, int c, int N, int step)
+{
+  const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c); /* cur, bound | ocur, kb */
+  SerStep it;
+  it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
+  it.nones = sm.ones16[c]; it.N = N; it.rev = step;
+  return it;
+}
+
 /* MAXT = largest block the instantiation is launched with: the small-block instantiation may use
  * more registers per thread (shared memory, not registers, limits residency there).
  * MANY = per-taxon c, d (manycd = 1, mcmc.c:777-785, :807-815): same choreography; the Beta draws, weights
@@ -167,7 +192,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
     build_columns(p, sm);
   }
   __syncthreads();
-  if (tid == M) rebuild_hard(p, sm);
+  rebuild_hard(p, sm);
   __syncthreads();
 
   const double *tape = nullptr;
@@ -187,7 +212,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
   }
   wt.eps = p.eps;
   SerHard hd;
-  hd.hcol = sm.V + M; hd.hpre = sm.pre + M; hd.hp = sm.hp; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh;
+  hd.hcol = sm.V + M; hd.hpre = sm.pre + M; hd.hp = sm.hp; hd.C = C; hd.W = W; hd.N = N; hd.nh = p.nh; hd.rank_tab = sm.hrank; hd.nonhard_tab = sm.nhpos;
   PropState ps;
   ps.k = 0; ps.buf = 0;
 
@@ -311,24 +336,58 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
        * the b-step: per-column maximum (own thread), item weights (dense over the CTA),
        * per-column scan + inverse CDF (own thread). */
       PHASE_MARK(8);
-      if (is_taxon) ser_expand_ones(col, C, W, sm.pos + off_c);
+      /* The per-column loops of this phase -- postings, maximum, cumulative weights -- are served by UNITS: a column
+       * with many ones gets 2, 4 or 8 adjacent lanes (static table, built from the column's item count), so the
+       * longest serial loop of a pass is ~1/6 of the heaviest column (g2s2: 95 items -> 12-16 per lane).  With one
+       * thread per column the warp that owns the 32 heaviest columns was the critical path of every pass while the
+       * other nine waited at the barrier (30 % of the sweep's cycles). */
+      for (int ub = 0; ub < p.n_units; ub += C) { /* postings: lane `sub` expands its share of the column's words */
+        const Unit un = unit_load(p, ub + tid, p.n_units);
+        if (un.live) {
+          const int wq = (W + un.lpc - 1) >> un.lsh, w0 = un.sub * wq, w1 = min(W, w0 + wq);
+          if (w0 < w1) {
+            uint16_t *out = sm.pos + un.off + sm.pre[w0 * C + un.c]; /* the prefix table gives the first slot */
+            for (int w = w0; w < w1; w++) {
+              uint32_t v = sm.V[w * C + un.c];
+              while (v) { *out++ = (uint16_t)(32 * w + SER_FFS(v) - 1); v &= v - 1u; }
+            }
+          }
+        }
+      }
       PHASE_MARK(9);
       int changed = 0;
 #pragma unroll 1
       for (int step = 0; step < 2; step++) {
-        SerStep st;
-        double lmax = 0.0;
-        if (is_taxon) {
-          st = step == 0 ? ser_step_a(col, pre, C, W, N, a, b) : ser_step_b(col, pre, C, W, N, a, b);
-          lmax = ser_step_lmax(wt, st, sm.pos + off_c);
-          sm.lmax[tid] = lmax;
-          sm.st4[4 * tid + 0] = (uint16_t)st.cur; sm.st4[4 * tid + 1] = (uint16_t)st.bound;
-          sm.st4[4 * tid + 2] = (uint16_t)st.ocur; sm.st4[4 * tid + 3] = (uint16_t)st.kb;
+        if (is_taxon) { /* step geometry of the own column, published for the units */
+          const SerStep st = step == 0 ? ser_step_a(col, pre, C, W, N, a, b) : ser_step_b(col, pre, C, W, N, a, b);
+          *reinterpret_cast<uint2 *>(sm.st4 + 4 * tid) =
+              make_uint2((uint32_t)st.cur | ((uint32_t)st.bound << 16), (uint32_t)st.ocur | ((uint32_t)st.kb << 16));
+        }
+        __syncthreads(); /* also: the postings are complete */
+        for (int ub = 0; ub < p.n_units; ub += C) { /* maximum log-weight per column (the reference's z, mcmc.c:727-730) */
+          const Unit un = unit_load(p, ub + tid, p.n_units);
+          double lm = -1.0e300;
+          if (un.live) {
+            const SerStep it = unit_step(sm, un.c, N, step);
+            const uint16_t *pos = sm.pos + un.off;
+            SerWeights w = wt;
+            if constexpr (MANY) { w.A = sm.wcol[4 * un.c + 0]; w.g = sm.wcol[4 * un.c + 1]; }
+            for (int kk = un.sub; kk <= it.kb; kk += un.lpc) {
+              int q, n;
+              lm = ser_fmax(lm, ser_item_eval(w, it, pos, kk, &q, &n));
+            }
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, lm, o);
+            if (o < un.lpc) lm = ser_fmax(lm, t);
+          }
+          if (un.live && un.sub == 0) sm.lmax[un.c] = lm;
         }
         __syncthreads();
         PHASE_MARK(10);
 #pragma unroll 1
-        for (int g = 0; g < p.n_groups; g++) { /* columns grp_c[g]..grp_c[g+1] = items grp_e[g]..grp_e[g+1] */
+        for (int g = 0; g < p.n_groups; g++) { /* columns grp_c[g]..grp_c[g+1] = items grp_e[g]..grp_e[g+1] = units grp_u[g]..grp_u[g+1] */
           const int e0 = p.grp_e[g], e1 = p.grp_e[g + 1];
           if (g) __syncthreads(); /* the previous group's scans are done with val */
           uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u; /* item -> column map, fetched one iteration ahead */
@@ -353,8 +412,32 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           }
           __syncthreads();
           PHASE_MARK(11);
+          /* cumulative weights (mcmc_randompick's running sum, mcmc.c:901-915).  Lane `sub` owns the contiguous chunk
+           * [k0, k1) of the column's items: serial sums inside the chunk, an exclusive scan of the chunk totals over the
+           * column's lanes, then the lane's base is added to its chunk, so val[] ends up holding the cumulative
+           * weights of the whole column. */
+          const int ug1 = p.grp_u[g + 1];
+          for (int ub = p.grp_u[g]; ub < ug1; ub += C) { /* warp-uniform trip count: the shuffles need every lane */
+            const Unit un = unit_load(p, ub + tid, ug1);
+            const int kb = un.live ? (int)sm.st4[4 * un.c + 3] : 0;
+            double *val = sm.val + (un.off - e0);
+            const int chunk = (kb + un.lpc) >> un.lsh, k0 = min(kb + 1, un.sub * chunk), k1 = min(kb + 1, k0 + chunk);
+            double tot = 0.0;
+            if (un.live) for (int kk = k0; kk < k1; kk++) { tot = SER_ADD(tot, val[kk]); val[kk] = tot; }
+            double incl = tot; /* inclusive scan of the chunk totals over the column's lanes */
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              const double t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (o < un.lpc && un.sub >= o) incl = SER_ADD(incl, t);
+            }
+            const double base = SER_SUB(incl, tot);
+            if (un.live && un.sub) for (int kk = k0; kk < k1; kk++) val[kk] = SER_ADD(base, val[kk]);
+          }
+          __syncthreads();
+          /* inverse CDF by the column's owner: binary search over the cumulative weights, closed-form pick inside the run */
           if (is_taxon && tid >= p.grp_c[g] && tid < p.grp_c[g + 1]) {
-            const int pick = ser_step_pick<MANY ? 0 : 1>(wt, st, sm.pos + off_c, sm.val + (off_c - e0), lmax, step == 0 ? ua : ub);
+            const SerStep st = unit_step(sm, tid, N, step);
+            const int pick = ser_step_pick_scanned<MANY ? 0 : 1>(wt, st, sm.pos + off_c, sm.val + (off_c - e0), sm.lmax[tid], step == 0 ? ua : ub);
             if (step == 0) { changed += pick != a; a = pick; }
             else { changed += (N - pick) != b; b = N - pick; }
           }
@@ -429,7 +512,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
           __syncthreads();
           for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
-          if (tid == M && nhw) rebuild_hard(p, sm); /* the hard column only changed if the window holds a hard site */
+          if (nhw) { __syncthreads(); rebuild_hard(p, sm); } /* the hard column only changed if the window holds a hard site */
           sc.counters[3]++;
         } else if (kind == 1 || kind == 3) { /* ---------------- mcmc_samplepi2, mcmc.c:1311-1486 */
           int i, j;
@@ -459,7 +542,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             const uint16_t t = sm.rpi[n];
             sm.rpi[n] = sm.rpi[i + j - n]; sm.rpi[i + j - n] = t;
           }
-          if (tid == M && nhw) rebuild_hard(p, sm);
+          if (nhw) { __syncthreads(); rebuild_hard(p, sm); }
           sc.counters[kind == 1 ? 4 : 5]++;
         } else { /* ---------------- mcmc_samplepi3, mcmc.c:1489-1682 */
           const int nfree = N - p.nh;

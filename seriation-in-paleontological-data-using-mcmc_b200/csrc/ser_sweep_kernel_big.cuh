@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
     wt.eps = p.eps; wt.H = sm.H; wt.hmax = 0;
     set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
     SerHard hd;
-    hd.hcol = V + M; hd.hpre = PRE + M; hd.hp = sm.hp; hd.C = Cs; hd.W = W; hd.N = N; hd.nh = p.nh;
+    hd.hcol = V + M; hd.hpre = PRE + M; hd.hp = sm.hp; hd.C = Cs; hd.W = W; hd.N = N; hd.nh = p.nh; hd.rank_tab = nullptr; hd.nonhard_tab = nullptr;
     PropState ps;
     ps.k = 0; ps.buf = 0;
 
