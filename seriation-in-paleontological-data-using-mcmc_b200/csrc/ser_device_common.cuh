@@ -104,6 +104,7 @@ struct Smem {
   double *wcol;     /* manycd only: 4*C per-column weights A, g, 1/g, 1/(1-e^-g) for the dense item phase */
   double *redd;     /* manycd only: 2*32 doubles of reduction scratch */
   uint16_t *rpi, *tmp16, *perm16; /* N each */
+  uint16_t *pick16; /* C: the item the column's uniform fell into (Gibbs step) */
   uint16_t *hrank, *nhpos; /* N+2 each: hard positions before p; position of the r-th non-hard site (SerHard's tables) */
 };
 
@@ -120,8 +121,9 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
   size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
-  size_t o_hr = take(sizeof(uint16_t) * (N + 2)), o_nh = take(sizeof(uint16_t) * (N + 2));
+  size_t o_hr = take(sizeof(uint16_t) * (N + 2)), o_nh = take(sizeof(uint16_t) * (N + 2)), o_pk = take(sizeof(uint16_t) * C);
   if (s) {
+    s->pick16 = (uint16_t *)(base + o_pk);
     s->hrank = (uint16_t *)(base + o_hr); s->nhpos = (uint16_t *)(base + o_nh);
     s->logdraw = (double *)(base + o_ld);
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);

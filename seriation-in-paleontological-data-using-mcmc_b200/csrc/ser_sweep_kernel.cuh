@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
       int changed = 0;
 #pragma unroll 1
       for (int step = 0; step < 2; step++) {
-        if (is_taxon) { /* step geometry of the own column, published for the units */
+        if (is_taxon) { /* step geometry of the own column and its uniform, published for the units */
+          sm.terms[tid] = step == 0 ? ua : ub; /* terms[] is idle during the Gibbs phase */
           const SerStep st = step == 0 ? ser_step_a(col, pre, C, W, N, a, b) : ser_step_b(col, pre, C, W, N, a, b);
           *reinterpret_cast<uint2 *>(sm.st4 + 4 * tid) =
               make_uint2((uint32_t)st.cur | ((uint32_t)st.bound << 16), (uint32_t)st.ocur | ((uint32_t)st.kb << 16));
@@ -412,14 +413,15 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           }
           __syncthreads();
           PHASE_MARK(11);
-          /* cumulative weights (mcmc_randompick's running sum, mcmc.c:901-915).  Lane `sub` owns the contiguous chunk
-           * [k0, k1) of the column's items: serial sums inside the chunk, an exclusive scan of the chunk totals over the
-           * column's lanes, then the lane's base is added to its chunk, so val[] ends up holding the cumulative
-           * weights of the whole column. */
+          /* cumulative weights and the item the uniform falls into (mcmc_randompick, mcmc.c:901-915).  Lane `sub` owns
+           * the contiguous chunk [k0, k1) of the column's items: serial sums inside the chunk (chunk-relative), a scan of
+           * the chunk totals over the column's lanes; the lane whose chunk is the first to reach target = U x total
+           * finds the item inside its chunk and leaves (item, target - weight before the item) for the owner. */
           const int ug1 = p.grp_u[g + 1];
           for (int ub = p.grp_u[g]; ub < ug1; ub += C) { /* warp-uniform trip count: the shuffles need every lane */
             const Unit un = unit_load(p, ub + tid, ug1);
             const int kb = un.live ? (int)sm.st4[4 * un.c + 3] : 0;
+            const double u01 = un.live ? sm.terms[un.c] : 0.0;
             double *val = sm.val + (un.off - e0);
             const int chunk = (kb + un.lpc) >> un.lsh, k0 = min(kb + 1, un.sub * chunk), k1 = min(kb + 1, k0 + chunk);
             double tot = 0.0;
@@ -430,19 +432,32 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
               const double t = __shfl_up_sync(0xffffffffu, incl, o);
               if (o < un.lpc && un.sub >= o) incl = SER_ADD(incl, t);
             }
-            const double base = SER_SUB(incl, tot);
-            if (un.live && un.sub) for (int kk = k0; kk < k1; kk++) val[kk] = SER_ADD(base, val[kk]);
-          }
-          __syncthreads();
-          /* inverse CDF by the column's owner: binary search over the cumulative weights, closed-form pick inside the run */
-          if (is_taxon && tid >= p.grp_c[g] && tid < p.grp_c[g + 1]) {
-            const SerStep st = unit_step(sm, tid, N, step);
-            const int pick = ser_step_pick_scanned<MANY ? 0 : 1>(wt, st, sm.pos + off_c, sm.val + (off_c - e0), sm.lmax[tid], step == 0 ? ua : ub);
-            if (step == 0) { changed += pick != a; a = pick; }
-            else { changed += (N - pick) != b; b = N - pick; }
+            const int lane = tid & 31;
+            const double total = __shfl_sync(0xffffffffu, incl, (lane | (un.lpc - 1)));
+            const double before = __shfl_up_sync(0xffffffffu, incl, 1);
+            const double base = un.sub ? before : 0.0, target = SER_MUL(u01, total);
+            if (un.live && k0 < k1 && incl >= target && (un.sub == 0 || base < target)) {
+              int lo = k0, hi = k1 - 1; /* first item of the chunk whose cumulative weight reaches the target */
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
+              }
+              sm.pick16[un.c] = (uint16_t)lo;
+              sm.terms[un.c] = SER_SUB(target, lo > k0 ? SER_ADD(base, val[lo - 1]) : base);
+            }
           }
           PHASE_MARK(12);
         }
+        __syncthreads();
+        if (is_taxon) { /* the owner: closed-form pick inside the item's run */
+          const SerStep st = unit_step(sm, tid, N, step);
+          int q, n;
+          const double le = SER_SUB(ser_item_eval(wt, st, sm.pos + off_c, (int)sm.pick16[tid], &q, &n), sm.lmax[tid]);
+          const int pick = q - n + 1 + ser_run_pick<MANY ? 0 : 1>(wt, n, le, 0.0, sm.terms[tid]);
+          if (step == 0) { changed += pick != a; a = pick; }
+          else { changed += (N - pick) != b; b = N - pick; }
+        }
+        PHASE_MARK(18);
       }
       /* the log-likelihood is only ever observed after the last sweep of a sampling call
        * (mcmc_save_chain); there it is formed with the reference's own sequential sums */
