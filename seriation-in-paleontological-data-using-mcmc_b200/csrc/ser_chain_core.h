@@ -140,30 +140,37 @@ SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j, uint16_t 
   }
 }
 
-/* in-place: move bit i to position j, shifting the bits in between by one (pi1) */
+/* in-place: move bit i to position j, shifting the bits in between by one (pi1).  No copy of the column: a word
+ * only needs its old neighbour on the side the bits come from, and the words are rewritten in the order that
+ * leaves that neighbour untouched (upwards for i < j, downwards for i > j). */
 SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j, uint16_t *pre = 0)
 {
-  uint32_t old[SER_MAXW];
   const int lo = i < j ? i : j, hi = i < j ? j : i;
   const int w0 = lo >> 5, w1 = hi >> 5;
-  for (int w = w0; w <= w1; w++) old[w] = col[w * C];
-  const uint32_t moved = (old[i >> 5] >> (i & 31)) & 1u;
-  int acc = pre ? (int)pre[w0 * C] : 0;
-  for (int wn = w0; wn <= w1; wn++) {
-    uint32_t bits, m;
-    const uint32_t cur = old[wn];
-    const uint32_t up = (wn + 1 <= w1) ? old[wn + 1] : 0u, dn = (wn - 1 >= w0) ? old[wn - 1] : 0u;
-    if (i < j) { /* new[p] = old[p+1] for p in [i, j-1] */
-      bits = (cur >> 1) | (up << 31);
-      m = ser_range_mask(wn, i, j);
-    } else { /* new[p] = old[p-1] for p in [j+1, i] */
-      bits = (cur << 1) | (dn >> 31);
-      m = ser_range_mask(wn, j + 1, i + 1);
+  const uint32_t moved = (col[(i >> 5) * C] >> (i & 31)) & 1u;
+  if (i < j) { /* new[p] = old[p+1] for p in [i, j-1] */
+    int acc = pre ? (int)pre[w0 * C] : 0;
+    uint32_t cur = col[w0 * C];
+    for (int wn = w0; wn <= w1; wn++) {
+      const uint32_t up = (wn + 1 <= w1) ? col[(wn + 1) * C] : 0u;
+      const uint32_t m = ser_range_mask(wn, i, j);
+      uint32_t nw = (cur & ~m) | (((cur >> 1) | (up << 31)) & m);
+      if (wn == w1) nw = (nw & ~(1u << (j & 31))) | (moved << (j & 31));
+      col[wn * C] = nw;
+      if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
+      cur = up;
     }
-    uint32_t nw = (cur & ~m) | (bits & m);
-    if (wn == (j >> 5)) nw = (nw & ~(1u << (j & 31))) | (moved << (j & 31));
-    col[wn * C] = nw;
-    if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
+  } else { /* new[p] = old[p-1] for p in [j+1, i] */
+    uint32_t cur = col[w1 * C];
+    for (int wn = w1; wn >= w0; wn--) {
+      const uint32_t dn = (wn - 1 >= w0) ? col[(wn - 1) * C] : 0u;
+      const uint32_t m = ser_range_mask(wn, j + 1, i + 1);
+      uint32_t nw = (cur & ~m) | (((cur << 1) | (dn >> 31)) & m);
+      if (wn == w0) nw = (nw & ~(1u << (j & 31))) | (moved << (j & 31));
+      col[wn * C] = nw;
+      cur = dn;
+    }
+    if (pre) ser_col_fix_pre(col, pre, C, w0, w1);
   }
 }
 
@@ -603,8 +610,12 @@ SER_HD int ser_pi3_perm(const SerHard &h, const SerPi3 &g, int n)
 }
 
 /* pi3: only the non-hard sites of [i, j] are reversed; a/b mirror as in pi2 */
+/* HB: the column's ones at the hard sites come from `hbits` (bit k = the column has a one at the k-th hard site;
+ * hard sites keep their relative order, mcmc.c:1049-1072, so this is a constant of the column; needs nh <= 32)
+ * instead of a walk over the hard positions inside the two ranges */
+template <bool HB = false>
 SER_HD void ser_pi3_delta(const uint32_t *col, const uint16_t *pre, int C, const SerHard &h, const SerPi3 &g, int a,
-                          int b, int inc1, int inc2, int *dt0, int *dt1)
+                          int b, int inc1, int inc2, int *dt0, int *dt1, uint32_t hbits = 0u)
 {
   const int i = g.i, j = g.j;
   const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
@@ -628,8 +639,13 @@ SER_HD void ser_pi3_delta(const uint32_t *col, const uint16_t *pre, int C, const
   /* B = (hard in [nac,nbc)) + (non-hard in [lo2,hi2)) */
   const int nB = (hr_nb - hr_na) + ((hi2 > lo2 ? hi2 - lo2 : 0) - (hr_hi2 - hr_lo2));
   int oB = ser_col_popc(col, pre, C, lo2, hi2);
-  for (int k = hr_lo2; k < hr_hi2; k++) oB -= ser_col_bit(col, C, h.hp[k]); /* hard ones inside [lo2,hi2) do not count */
-  for (int k = hr_na; k < hr_nb; k++) oB += ser_col_bit(col, C, h.hp[k]);   /* hard ones in [nac,nbc) do */
+  if (HB) { /* hard ranks in [x, y) -> bits x..y-1 of hbits */
+    oB -= SER_POPC(hbits & ser_mask_lt(hr_hi2) & ~ser_mask_lt(hr_lo2));
+    oB += SER_POPC(hbits & ser_mask_lt(hr_nb) & ~ser_mask_lt(hr_na));
+  } else {
+    for (int k = hr_lo2; k < hr_hi2; k++) oB -= ser_col_bit(col, C, h.hp[k]); /* hard ones inside [lo2,hi2) do not count */
+    for (int k = hr_na; k < hr_nb; k++) oB += ser_col_bit(col, C, h.hp[k]);   /* hard ones in [nac,nbc) do */
+  }
   *dt1 = oB - oA;
   *dt0 = (nA - oA) - (nB - oB); /* true zeros = dead zeros: gain what the alive zeros lose */
 }

@@ -43,6 +43,7 @@ struct KParams {
   const uint16_t *order;    /* [M] column -> taxon (columns are sorted by ones, descending) */
   const int *off;           /* [M+1] first item of each column; a column has ones+1 items */
   const uint32_t *item_col; /* [I] item -> (column << 16) | index of the item inside its column */
+  const uint32_t *hbits;    /* [M] bit k = the column has a one at the k-th hard site in file order (first 32 hard sites) */
   int I;                    /* ones_total + M */
   /* large-shape path (ser_sweep_kernel_big): per-CTA-slot scratch in global memory */
   int Cs;                   /* column stride of the scratch bit matrix (>= M+1) */

@@ -135,11 +135,13 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
 
   /* static per column (the same for every chain this CTA serves) */
   int taxon = 0, off_c = 0, ones_c = 0;
+  uint32_t hbits_c = 0u; /* bit k: this column has a one at the k-th hard site (static; nh <= 32) */
   if (is_taxon) {
     taxon = p.order[tid]; /* the taxon this column holds: indexes the tape, the samples, terms[] */
     off_c = p.off[tid];
     ones_c = p.ones[tid];
     sm.ones16[tid] = (uint16_t)ones_c;
+    hbits_c = p.hbits[tid];
   }
 
   /* ---- persistent grid: the CTAs pull (chain, chunk of calls) work items from a queue until it is empty.
@@ -409,6 +411,10 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
               } else {
                 sm.val[e - e0] = ser_item_weight<1>(wt, it, sm.pos + (e - kk), kk, sm.lmax[c]);
               }
+#if defined(SER_PHASE_TIMING) && defined(SER_COUNT_ITEMS) /* how many items are evaluated / lie above the LOGEPSILON floor */
+              { int q_, n_; const bool unfl = SER_SUB(ser_item_eval(wt, it, sm.pos + (e - kk), kk, &q_, &n_), sm.lmax[c]) >= SER_LOGEPSILON;
+                atomicAdd(&ser_phase_cycles[20], 1ull); if (unfl) atomicAdd(&ser_phase_cycles[21], 1ull); }
+#endif
             }
           }
           __syncthreads();
@@ -569,7 +575,10 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           const SerPi3 g = ser_pi3_window(hd, ir, jr);
           const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
           ps.k += 2;
-          if (is_taxon) ser_pi3_delta(col, pre, C, hd, g, a, b, inc1, inc2, &dt0, &dt1);
+          if (is_taxon) {
+            if (p.nh <= 32) ser_pi3_delta<true>(col, pre, C, hd, g, a, b, inc1, inc2, &dt0, &dt1, hbits_c);
+            else ser_pi3_delta<false>(col, pre, C, hd, g, a, b, inc1, inc2, &dt0, &dt1);
+          }
           if (!mh_decide<MANY>(p, sm, wt, ps, taxon, is_taxon, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
           __syncthreads();
