@@ -35,6 +35,7 @@
 #include "ser_device_common.cuh"
 #include "ser_sweep_kernel.cuh"
 #include "ser_sweep_kernel_big.cuh"
+#include "ser_sweep_kernel_cluster.cuh"
 #include "ser_aux_kernels.cuh"
 
 /* ================================================================== host side: the run object */
@@ -78,6 +79,11 @@ struct ser_run {
   uint32_t *d_gV;
   uint16_t *d_gpre;
   int *d_bgrp;
+  /* cluster path of the large shapes */
+  int cl_mode, cl_R, cl_clusters;
+  size_t smem_cl;
+  int *d_cl_off, *d_cl_grp;
+  uint32_t *d_cl_item;
   int initialized, have_tapes;
   /* persistent work-queue grid of ser_sweep_kernel: (chain, chunk of calls) items, see ser_run_advance_both */
   uint32_t *d_V;            /* [chain][W][C] bit columns carried between work items */
@@ -169,6 +175,7 @@ static cudaError_t allow_max_dynamic_smem(void)
   allow((const void *)ser_sweep_kernel<1024, 1, true>);
   allow((const void *)ser_sweep_kernel<384, 2, true>);
   allow((const void *)ser_sweep_kernel_big);
+  allow((const void *)ser_sweep_kernel_cl);
   return e;
 }
 
@@ -366,7 +373,83 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
       if (const char *v = getenv("SER_SWEEP_VARIANT")) run->variant = (atoi(v) == 1 && run->C <= 384) ? 1 : 0;
     }
   }
-  if (run->big) {
+  if (run->big && getenv("SER_BIG_MODE") && !strcmp(getenv("SER_BIG_MODE"), "cluster")) {
+    /* Cluster path (opt-in, SER_BIG_MODE=cluster): the chain's bit columns sharded over the shared memory of R CTAs
+     * (ser_sweep_kernel_cluster.cuh).  It removes the HBM re-streaming of the slot path, but on the 1024 x 4096 matrix it
+     * needs R = 8, and the per-proposal latency chain, replicated in 8 CTAs, costs more than the DRAM round trips it saves
+     * (measured 93 k vs 160 k sweeps/s, profiles/r02): the slot path stays the default.
+     * R = the smallest cluster whose CTAs hold their share of the columns + prefix tables and an item buffer of at least
+     * max(M, N + 1, 4096) items (M: the per-taxon terms of the exact sums are gathered there); SER_CLUSTER_R forces it. */
+    int force_r = 0;
+    if (const char *v = getenv("SER_CLUSTER_R")) force_r = atoi(v);
+    for (int R = 1; R <= SER_CL_MAXR && !run->cl_mode; R <<= 1) {
+      if (force_r && R != force_r) continue;
+      if (R > 1 && M < 2 * R) continue;
+      const int Mc = (M + R - 1) / R, gcap = std::min(Mc, 256);
+      const size_t fixed = cl_layout(nullptr, nullptr, N, run->W, Mc, 0, gcap);
+      const long long want = std::max(std::max(M, N + 1), 4096);
+      long long icap = ((long long)SER_SMEM_DYN_MAX - (long long)fixed - 64) / 10 / 32 * 32; /* val 8 + pos 2 bytes per item */
+      if (icap < want) continue;
+      /* per-rank item numbering, item tables and column groups */
+      std::vector<int> cl_off(M, 0), grp_all;
+      std::vector<uint32_t> item_all;
+      long long max_items = 0;
+      for (int r = 0; r < R; r++) {
+        kp.cl_item_base[r] = (int)item_all.size();
+        kp.cl_grp_base[r] = (int)grp_all.size() / 2;
+        const int nloc = (M - r + R - 1) / R;
+        std::vector<int> loff(nloc + 1, 0);
+        for (int lc = 0; lc < nloc; lc++) {
+          const int gc = lc * R + r;
+          cl_off[gc] = loff[lc];
+          loff[lc + 1] = loff[lc] + ones[gc] + 1;
+          for (int kk = 0; kk <= ones[gc]; kk++) item_all.push_back(((uint32_t)lc << 16) | (uint32_t)kk);
+        }
+        max_items = std::max<long long>(max_items, loff[nloc]);
+        const long long cap = std::min<long long>(icap, ((long long)loff[nloc] + 31) / 32 * 32);
+        int c0 = 0;
+        while (c0 < nloc) {
+          int c1 = c0;
+          while (c1 < nloc && c1 - c0 < gcap && loff[c1 + 1] - loff[c0] <= cap) c1++;
+          if (c1 == c0) { c1 = c0 + 1; } /* cannot happen: icap >= N + 1 >= one column */
+          grp_all.push_back(c0); grp_all.push_back(loff[c0]);
+          c0 = c1;
+        }
+        grp_all.push_back(nloc); grp_all.push_back(loff[nloc]);
+      }
+      kp.cl_item_base[R] = (int)item_all.size();
+      kp.cl_grp_base[R] = (int)grp_all.size() / 2;
+      icap = std::min<long long>(icap, std::max<long long>(want, (max_items + 31) / 32 * 32));
+      kp.cl_R = R; kp.cl_Mc = Mc; kp.cl_icap = (int)icap; kp.cl_gcap = gcap;
+      run->smem_cl = cl_layout(nullptr, nullptr, N, run->W, Mc, (int)icap, gcap);
+      /* how many clusters the device holds at once */
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.gridDim = dim3(R * 64, 1, 1); lc.blockDim = dim3(run->big_threads, 1, 1); lc.dynamicSmemBytes = run->smem_cl;
+      lc.attrs = at; lc.numAttrs = 1;
+      int n_cl = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_cl, ser_sweep_kernel_cl, &lc) != cudaSuccess || n_cl < 1) { cudaGetLastError(); continue; }
+      if (const char *v = getenv("SER_CLUSTERS")) n_cl = std::max(1, std::min(n_cl, atoi(v)));
+      run->cl_clusters = std::max(1, std::min(cfg->n_chains, n_cl));
+      CUDA_TRY(POOL_ALLOC(&run->d_cl_off, (size_t)M * sizeof(int)));
+      CUDA_TRY(POOL_ALLOC(&run->d_cl_item, item_all.size() * sizeof(uint32_t)));
+      CUDA_TRY(POOL_ALLOC(&run->d_cl_grp, grp_all.size() * sizeof(int)));
+      CUDA_TRY(cudaMemcpyAsync(run->d_cl_off, cl_off.data(), (size_t)M * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+      CUDA_TRY(cudaMemcpyAsync(run->d_cl_item, item_all.data(), item_all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, run->stream));
+      CUDA_TRY(cudaMemcpyAsync(run->d_cl_grp, grp_all.data(), grp_all.size() * sizeof(int), cudaMemcpyHostToDevice, run->stream));
+      CUDA_TRY(cudaStreamSynchronize(run->stream));
+      kp.cl_off = run->d_cl_off; kp.cl_item = run->d_cl_item; kp.cl_grp = run->d_cl_grp;
+      run->cl_mode = 1; run->cl_R = R;
+    }
+    if (!run->cl_mode && getenv("SER_BIG_MODE") && !strcmp(getenv("SER_BIG_MODE"), "cluster")) {
+      ser_set_error("ser_run_create: the shape does not fit the shared memory of a cluster of up to %d CTAs", SER_CL_MAXR);
+      return SER_E_ARG;
+    }
+  }
+  if (run->big && !run->cl_mode) {
     /* column groups of the Gibbs phase: as many items as the shared-memory budget holds
      * (SER_BIG_SMEM_KB, default 220), at most 1024 columns, never splitting a column */
     int budget_kb = 220;
@@ -509,7 +592,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
                   run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp,
-                  run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts, run->d_unit_tab, run->d_hbits};
+                  run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts, run->d_unit_tab, run->d_hbits, run->d_cl_off, run->d_cl_item, run->d_cl_grp};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   if (run->stream) cudaStreamSynchronize(run->stream);
   if (run->sweep_ev) {
@@ -598,6 +681,19 @@ extern "C" int ser_run_advance_both(ser_run *run, int32_t burn_calls, int32_t sa
     }
     ev0 = (*run->sweep_ev)[run->sweep_ev_used]; ev1 = (*run->sweep_ev)[run->sweep_ev_used + 1];
     run->sweep_ev_used += 2;
+  }
+  if (run->big && run->cl_mode) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = run->cl_R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.gridDim = dim3(run->cl_clusters * run->cl_R, 1, 1); lc.blockDim = dim3(run->big_threads, 1, 1);
+    lc.dynamicSmemBytes = run->smem_cl; lc.stream = run->stream; lc.attrs = at; lc.numAttrs = 1;
+    if (rec) CUDA_TRY(cudaEventRecord(ev0, run->stream));
+    CUDA_TRY(cudaLaunchKernelEx(&lc, ser_sweep_kernel_cl, kp));
+    if (rec) CUDA_TRY(cudaEventRecord(ev1, run->stream));
+    return SER_OK;
   }
   if (run->big) {
     if (rec) CUDA_TRY(cudaEventRecord(ev0, run->stream));
