@@ -454,7 +454,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
      * (SER_BIG_SMEM_KB, default 220), at most 1024 columns, never splitting a column */
     int budget_kb = 220;
     if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(224, atoi(v)));
-    const int gcap = std::max(std::min(M, 1024), run->big_threads); /* also bounds (columns x lanes per column) */
+    const int gcap = std::min(M, 512); /* columns per group: sizes the per-column tables of a group */
     const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
     long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32; /* val 8 + pos 2 bytes per item */
     icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);

@@ -10,13 +10,18 @@ struct BigSmem {
   double *draws_pi, *logdraw, *draws_cd, *H;
   double *lmax; /* gcap: per column of the running group */
   double *val;  /* icap: item weights / cumulative weights of the running group */
-  double *incl; /* gcap: inclusive chunk totals, one per (column, lane) unit of the running group */
+  double *dsl;  /* gcap: per column of the running group: target minus the cumulative weight before the picked item */
   int *red;
   uint16_t *a16, *b16, *hp, *rpi, *tmp16, *perm16;
   uint16_t *st4; /* 4 * gcap */
   uint16_t *gones; /* gcap: ones of the running group's columns */
   int *goff;       /* gcap: first item of each column relative to the group's first item */
   uint16_t *pos; /* icap: postings of the running group's columns */
+  uint16_t *pick16;         /* gcap: the item the column's uniform fell into */
+  double *uab;              /* 2 gcap: the two uniforms (a-step, b-step) of every column of the running group */
+  uint32_t *hcol;           /* W: the hard-site mask in position order (stride 1; never leaves shared memory) */
+  uint16_t *hpre;           /* W+1: its prefix table */
+  uint16_t *hrank, *nhpos;  /* N+2 each: SerHard's tables */
 };
 __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap)
 {
@@ -26,8 +31,13 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
   size_t o_go = take(4 * (size_t)gcap), o_gn = take(2 * (size_t)gcap), o_lm = take(8 * (size_t)gcap), o_in = take(8 * (size_t)gcap), o_val = take(8 * (size_t)icap), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)gcap), o_hp = take(2 * (size_t)(N + 1));
   size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
+  size_t o_pk = take(2 * (size_t)gcap), o_hc = take(4 * (size_t)(N / 32 + 1)), o_hq = take(2 * (size_t)(N / 32 + 2)), o_ua = take(16 * (size_t)gcap);
+  size_t o_hr = take(2 * (size_t)(N + 2)), o_nh = take(2 * (size_t)(N + 2));
   if (s) {
-    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos); s->incl = (double *)(base + o_in);
+    s->uab = (double *)(base + o_ua);
+    s->pick16 = (uint16_t *)(base + o_pk); s->hcol = (uint32_t *)(base + o_hc); s->hpre = (uint16_t *)(base + o_hq);
+    s->hrank = (uint16_t *)(base + o_hr); s->nhpos = (uint16_t *)(base + o_nh);
+    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos); s->dsl = (double *)(base + o_in);
     s->goff = (int *)(base + o_go); s->gones = (uint16_t *)(base + o_gn);
     s->draws_pi = (double *)(base + o_dp); s->logdraw = (double *)(base + o_ld); s->draws_cd = (double *)(base + o_dc);
     s->H = (double *)(base + o_H); s->lmax = (double *)(base + o_lm); s->red = (int *)(base + o_r);
@@ -78,6 +88,19 @@ __device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &s
   return accept;
 }
 
+/* the hard-site tables from the shared-memory copy of the hard mask (as rebuild_hard) */
+__device__ __forceinline__ void big_rebuild_hard(const BigSmem &sm, int N)
+{
+  for (int q = threadIdx.x; q <= N; q += blockDim.x) {
+    const int r = ser_rank1(sm.hcol, sm.hpre, 1, q);
+    sm.hrank[q] = (uint16_t)r;
+    if (q < N) {
+      if ((sm.hcol[q >> 5] >> (q & 31)) & 1u) sm.hp[r] = (uint16_t)q;
+      else sm.nhpos[q - r] = (uint16_t)q;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -103,13 +126,14 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
       for (int w = 0; w < W; w++) {
         uint32_t word = 0;
         const int pend = min(32 * w + 32, N);
-        if (c < M) { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)cell(p, sm.rpi, pos, c) << (pos & 31); }
-        else { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)(p.hard[sm.rpi[pos]] != 0) << (pos & 31); }
-        V[w * Cs + c] = word;
+        if (c < M) { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)cell(p, sm.rpi, pos, c) << (pos & 31); V[w * Cs + c] = word; }
+        else { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)(p.hard[sm.rpi[pos]] != 0) << (pos & 31); sm.hcol[w] = word; }
       }
-      ser_col_build_pre(V + c, PRE + c, Cs, W);
-      if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+      if (c < M) ser_col_build_pre(V + c, PRE + c, Cs, W);
+      else ser_col_build_pre(sm.hcol, sm.hpre, 1, W);
     }
+    __syncthreads();
+    big_rebuild_hard(sm, N);
     __syncthreads();
 
     const double *tape = nullptr;
@@ -122,7 +146,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
     wt.eps = p.eps; wt.H = sm.H; wt.hmax = 0;
     set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
     SerHard hd;
-    hd.hcol = V + M; hd.hpre = PRE + M; hd.hp = sm.hp; hd.C = Cs; hd.W = W; hd.N = N; hd.nh = p.nh; hd.rank_tab = nullptr; hd.nonhard_tab = nullptr;
+    hd.hcol = sm.hcol; hd.hpre = sm.hpre; hd.hp = sm.hp; hd.C = 1; hd.W = W; hd.N = N; hd.nh = p.nh; hd.rank_tab = sm.hrank; hd.nonhard_tab = sm.nhpos;
     PropState ps;
     ps.k = 0; ps.buf = 0;
 
@@ -217,6 +241,15 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               }
             }
           }
+          for (int cl = tid; cl < nc; cl += C) { /* the two uniforms of every column of the group (mcmc.c:951, :963 -> :909) */
+            const int taxon = p.order[c0 + cl];
+            if (p.mode == SER_MODE_REPLAY) { sm.uab[2 * cl] = tape[sc.cursor + 6 + 2 * taxon]; sm.uab[2 * cl + 1] = tape[sc.cursor + 7 + 2 * taxon]; }
+            else {
+              uint32_t o[4];
+              ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+              sm.uab[2 * cl] = ser_u53(o[0], o[1]); sm.uab[2 * cl + 1] = ser_u53(o[2], o[3]);
+            }
+          }
           __syncthreads();
           PHASE_MARK(1);
 #pragma unroll 1
@@ -264,7 +297,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             }
             __syncthreads();
             PHASE_MARK(3);
-            for (int ub = 0; ub < units; ub += C) { /* cumulative weights, chunk-relative: lane `sub` owns items [k0, k1) */
+            for (int ub = 0; ub < units; ub += C) { /* chunk sums, scan over the column's lanes, the item the uniform falls into */
               const int u = ub + tid;
               const bool live = u < units;
               const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
@@ -273,46 +306,37 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               const int chunk = (kb + lpc) >> lsh, k0 = min(kb + 1, sub * chunk), k1 = min(kb + 1, k0 + chunk);
               double tot = 0.0;
               if (live) for (int kk = k0; kk < k1; kk++) { tot = SER_ADD(tot, val[kk]); val[kk] = tot; }
-              /* inclusive totals of the chunks, added left to right so that incl[j] == incl[j-1] + (last
-               * relative prefix of chunk j) bit for bit */
-              double incl = tot;
-              for (int j = 1; j < lpc; j++) {
-                const double t = __shfl_sync(0xffffffffu, incl, (tid & ~(lpc - 1) & 31) + j - 1);
-                if (sub == j) incl = SER_ADD(t, tot);
+              double incl = tot; /* inclusive scan of the chunk totals over the column's lanes */
+              for (int o = 1; o < lpc; o <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (sub >= o) incl = SER_ADD(incl, t);
               }
-              if (live) sm.incl[u] = incl;
+              const int lane = tid & 31;
+              const double total = __shfl_sync(0xffffffffu, incl, lane | (lpc - 1));
+              const double before = __shfl_up_sync(0xffffffffu, incl, 1);
+              const double u01 = live ? sm.uab[2 * cl + step] : 0.0;
+              const double base = sub ? before : 0.0, target = SER_MUL(u01, total);
+              if (live && k0 < k1 && incl >= target && (sub == 0 || base < target)) { /* the first chunk that reaches the target */
+                int lo = k0, hi = k1 - 1;
+                while (lo < hi) {
+                  const int mid = (lo + hi) >> 1;
+                  if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
+                }
+                sm.pick16[cl] = (uint16_t)lo;
+                sm.dsl[cl] = SER_SUB(target, lo > k0 ? SER_ADD(base, val[lo - 1]) : base);
+              }
             }
             __syncthreads();
             PHASE_MARK(7);
-            for (int cl = tid; cl < nc; cl += C) { /* inverse CDF: chunk, item inside the chunk, candidate inside the run */
+            for (int cl = tid; cl < nc; cl += C) { /* closed-form pick inside the item's run */
               const int c = c0 + cl;
               const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
               SerStep st;
               st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = (int)(g4.y >> 16);
               st.nones = sm.gones[cl]; st.N = N; st.rev = step;
-              const uint16_t *pos = sm.pos + sm.goff[cl];
-              const double *val = sm.val + sm.goff[cl], *incl = sm.incl + (cl << lsh);
-              const int taxon = p.order[c];
-              double uu;
-              if (p.mode == SER_MODE_REPLAY) uu = tape[sc.cursor + 6 + 2 * taxon + step];
-              else {
-                uint32_t o[4];
-                ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
-                uu = step == 0 ? ser_u53(o[0], o[1]) : ser_u53(o[2], o[3]);
-              }
-              const double target = SER_MUL(uu, incl[lpc - 1]);
-              int j = 0;
-              while (j < lpc - 1 && incl[j] < target) j++;
-              const double base = j ? incl[j - 1] : 0.0;
-              const int chunk = (st.kb + lpc) >> lsh, k0 = min(st.kb + 1, j * chunk), k1 = min(st.kb + 1, k0 + chunk);
-              int lo = k0, hi = k1 - 1; /* first item of the chunk whose cumulative weight reaches the target */
-              while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
-              }
               int q, n;
-              const double le = SER_SUB(ser_item_eval(wt, st, pos, lo, &q, &n), sm.lmax[cl]);
-              const int pick = q - n + 1 + ser_run_pick<1>(wt, n, le, lo > k0 ? SER_ADD(base, val[lo - 1]) : base, target);
+              const double le = SER_SUB(ser_item_eval(wt, st, sm.pos + sm.goff[cl], (int)sm.pick16[cl], &q, &n), sm.lmax[cl]);
+              const int pick = q - n + 1 + ser_run_pick<1>(wt, n, le, 0.0, sm.dsl[cl]);
               if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
               else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
             }
@@ -365,13 +389,15 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
             if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
             for (int c = tid; c <= M; c += C) {
-              if (c < M) { int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b; }
-              ser_col_rotate(V + c, Cs, W, i, j, PRE + c);
-              if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+              if (c < M) {
+                int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
+                ser_col_rotate(V + c, Cs, W, i, j, PRE + c);
+              } else ser_col_rotate(sm.hcol, 1, W, i, j, sm.hpre);
             }
             for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
             __syncthreads();
             for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
+            big_rebuild_hard(sm, N);
             sc.counters[3]++;
           } else if (kind == 1 || kind == 3) { /* pi2 */
             int i, j;
@@ -399,12 +425,13 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                 ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
                 sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
               }
-              ser_col_reverse(V + c, Cs, W, i, j, PRE + c);
-              if (c == M) ser_hard_list(V + M, Cs, W, sm.hp);
+              if (c < M) ser_col_reverse(V + c, Cs, W, i, j, PRE + c);
+              else ser_col_reverse(sm.hcol, 1, W, i, j, sm.hpre);
             }
             for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
             __syncthreads();
             for (int n = i + tid; n <= j; n += C) sm.rpi[n] = sm.tmp16[n];
+            big_rebuild_hard(sm, N);
             sc.counters[kind == 1 ? 4 : 5]++;
           } else { /* pi3 */
             const int nfree = N - p.nh;
@@ -416,7 +443,11 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             const SerPi3 g = ser_pi3_window(hd, ir, jr);
             const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
             ps.k += 2;
-            auto redo = [&](int c, int *x0, int *x1) { ser_pi3_delta(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1); };
+            const bool hb = p.nh <= 32;
+            auto redo = [&](int c, int *x0, int *x1) {
+              if (hb) ser_pi3_delta<true>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1, __ldg(p.hbits + c));
+              else ser_pi3_delta<false>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1);
+            };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
             if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
             for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
