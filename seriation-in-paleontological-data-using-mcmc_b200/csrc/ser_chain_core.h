@@ -32,6 +32,20 @@
 
 #define SER_MAXW 32 /* words per column: N <= 1024 */
 
+/* Debug builds (NVCC_EXTRA=-DSER_DEBUG, see profiles/r02/README.md): every index into shared memory / a column that is
+ * computed from chain state is range-checked; a violation prints its location and traps the kernel.  Compiled out otherwise. */
+#if defined(SER_DEBUG) && defined(__CUDA_ARCH__)
+#define SER_CHECK(cond)                                                                                              \
+  do {                                                                                                               \
+    if (!(cond)) {                                                                                                   \
+      printf("SER_DEBUG: (%s) failed at %s:%d, block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+      __trap();                                                                                                      \
+    }                                                                                                                \
+  } while (0)
+#else
+#define SER_CHECK(cond) do { } while (0)
+#endif
+
 /* ------------------------------------------------------------------ bit intrinsics */
 #if defined(__CUDA_ARCH__)
 #define SER_POPC(x) __popc((x))
@@ -83,6 +97,7 @@ SER_HD int ser_col_bit(const uint32_t *col, int C, int p) { return (col[(p >> 5)
 /* ones in bits [0, p), p in [0, N]: prefix table + one POPC */
 SER_HD int ser_rank1(const uint32_t *col, const uint16_t *pre, int C, int p)
 {
+  SER_CHECK(p >= 0 && p <= 32 * SER_MAXW);
   const int w = p >> 5;
   return (int)pre[w * C] + SER_POPC(col[w * C] & ser_mask_lo(p & 31));
 }
@@ -117,6 +132,7 @@ SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j, uint16_t 
 {
   uint32_t old[SER_MAXW];
   const int w0 = i >> 5, w1 = j >> 5;
+  SER_CHECK(0 <= i && i <= j && w1 < W);
   if (i + 1 == j && w0 == w1) { /* adjacent swap inside one word: the common (swap) case */
     uint32_t v = col[w0 * C];
     const uint32_t x = ((v >> (i & 31)) ^ (v >> (j & 31))) & 1u;
@@ -147,6 +163,7 @@ SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j, uint16_t *
 {
   const int lo = i < j ? i : j, hi = i < j ? j : i;
   const int w0 = lo >> 5, w1 = hi >> 5;
+  SER_CHECK(lo >= 0 && w1 < W);
   const uint32_t moved = (col[(i >> 5) * C] >> (i & 31)) & 1u;
   if (i < j) { /* new[p] = old[p+1] for p in [i, j-1] */
     int acc = pre ? (int)pre[w0 * C] : 0;
@@ -179,6 +196,7 @@ SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uin
 {
   uint32_t old[SER_MAXW];
   const int w0 = i >> 5, w1 = j >> 5;
+  SER_CHECK(0 <= i && i <= j && w1 < W);
   for (int w = w0; w <= w1; w++) old[w] = col[w * C];
   int acc = pre ? (int)pre[w0 * C] : 0;
   for (int wn = w0; wn <= w1; wn++) {
@@ -186,6 +204,7 @@ SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uin
     const int p0 = (32 * wn > i) ? 32 * wn : i, p1 = (32 * wn + 31 < j) ? 32 * wn + 31 : j;
     for (int p = p0; p <= p1; p++) {
       const int src = perm[p];
+      SER_CHECK(src >= i && src <= j);
       const uint32_t bit = (old[src >> 5] >> (src & 31)) & 1u;
       nw = (nw & ~(1u << (p & 31))) | (bit << (p & 31));
     }
@@ -217,7 +236,7 @@ SER_HD void ser_hard_list(const uint32_t *hcol, int C, int W, uint16_t *hp)
 }
 
 /* number of hard positions < p, p in [0, N] */
-SER_HD int ser_hard_rank(const SerHard &h, int p) { return h.rank_tab ? (int)h.rank_tab[p] : ser_rank1(h.hcol, h.hpre, h.C, p); }
+SER_HD int ser_hard_rank(const SerHard &h, int p) { SER_CHECK(p >= 0 && p <= h.N); return h.rank_tab ? (int)h.rank_tab[p] : ser_rank1(h.hcol, h.hpre, h.C, p); }
 SER_HD int ser_is_hard(const SerHard &h, int p) { return (h.hcol[(p >> 5) * h.C] >> (p & 31)) & 1u; }
 /* number of hard positions in [lo, hi] */
 SER_HD int ser_hard_count(const SerHard &h, int lo, int hi) { return ser_hard_rank(h, hi + 1) - ser_hard_rank(h, lo); }
@@ -226,6 +245,7 @@ SER_HD int ser_hard_count(const SerHard &h, int lo, int hi) { return ser_hard_ra
  * an upper-bound search over the sorted hard list. */
 SER_HD int ser_select_nonhard(const SerHard &h, int r)
 {
+  SER_CHECK(r >= 0 && r < h.N - h.nh);
   if (h.nonhard_tab) return (int)h.nonhard_tab[r];
   int lo = 0, hi = h.nh; /* first k with hp[k] - k > r */
   while (lo < hi) {
@@ -256,6 +276,7 @@ struct SerWeights {
 template <int TAB = 2>
 SER_HD double ser_H(const SerWeights &w, int m)
 {
+  SER_CHECK(m >= 0 && (!(TAB == 1 || (TAB == 2 && w.H)) || m <= w.hmax));
   if (TAB == 1 || (TAB == 2 && w.H)) return w.H[m];
   return SER_MUL(SER_SUB(1.0, exp(-SER_MUL(w.g, (double)m))), w.hs);
 }
@@ -413,6 +434,7 @@ SER_HD SerStep ser_step_b(const uint32_t *col, const uint16_t *pre, int C, int W
 /* logical position of the kk-th logical one (kk < kb); pos[] = ascending physical positions */
 SER_HD int ser_item_q(const SerStep &st, const uint16_t *pos, int kk)
 {
+  SER_CHECK(kk >= 0 && kk < st.nones);
   return st.rev ? st.N - 1 - (int)pos[st.nones - 1 - kk] : (int)pos[kk];
 }
 

@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
               uint32_t v = sm.V[w * C + un.c];
               while (v) { *out++ = (uint16_t)(32 * w + SER_FFS(v) - 1); v &= v - 1u; }
             }
+            SER_CHECK(out <= sm.pos + un.off + (int)sm.ones16[un.c] && un.off + (int)sm.ones16[un.c] <= p.I);
           }
         }
       }
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             SerStep it;
             it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
             if (kk <= it.kb) {
+              SER_CHECK(e - e0 >= 0 && e - e0 <= p.Ival && c < M && it.kb <= (int)sm.ones16[c] && it.bound <= N && it.cur <= it.bound);
               it.nones = sm.ones16[c]; it.N = N; it.rev = step;
               if constexpr (MANY) { /* the column's own weights; geometric sums on the fly */
                 SerWeights w;
@@ -430,6 +432,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             const double u01 = un.live ? sm.terms[un.c] : 0.0;
             double *val = sm.val + (un.off - e0);
             const int chunk = (kb + un.lpc) >> un.lsh, k0 = min(kb + 1, un.sub * chunk), k1 = min(kb + 1, k0 + chunk);
+            SER_CHECK(!un.live || (un.off - e0 >= 0 && un.off - e0 + k1 <= p.Ival + 1 && un.c >= p.grp_c[g] && un.c < p.grp_c[g + 1]));
             double tot = 0.0;
             if (un.live) for (int kk = k0; kk < k1; kk++) { tot = SER_ADD(tot, val[kk]); val[kk] = tot; }
             double incl = tot; /* inclusive scan of the chunk totals over the column's lanes */
@@ -457,6 +460,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
         __syncthreads();
         if (is_taxon) { /* the owner: closed-form pick inside the item's run */
           const SerStep st = unit_step(sm, tid, N, step);
+          SER_CHECK((int)sm.pick16[tid] <= st.kb);
           int q, n;
           const double le = SER_SUB(ser_item_eval(wt, st, sm.pos + off_c, (int)sm.pick16[tid], &q, &n), sm.lmax[tid]);
           const int pick = q - n + 1 + ser_run_pick<MANY ? 0 : 1>(wt, n, le, 0.0, sm.terms[tid]);
@@ -596,6 +600,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
         /* accepted: fold the integer deltas into the totals (the reference recounts, mcmc.c:1303) */
         sc.t0a += D0; sc.f0a -= D0; sc.t1a += D1; sc.f1a -= D1;
         sc.loglik = SER_ADD(sc.loglik, delta);
+        SER_CHECK(ps.k <= SER_PI_DRAWS && a >= 0 && a <= b && b <= N);
         __syncthreads(); /* columns / hard mask / rpi visible before the next proposal */
       }
 

@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               const int cl = (int)(ck >> 16) - c0, kk = (int)(ck & 0xffffu);
               const int kb = (int)sm.st4[4 * cl + 3];
               if (kk <= kb) { /* log-weight -> run weight, in place; the run length from the postings */
+                SER_CHECK(cl >= 0 && cl < nc && e - e0 < p.big_icap && e - kk - e0 >= 0);
                 const uint16_t *pos = sm.pos + (e - kk - e0);
                 const int nones = (int)sm.gones[cl], bound = (int)sm.st4[4 * cl + 1];
                 int q, qprev; /* ser_item_eval's q and qprev */
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                   const int mid = (lo + hi) >> 1;
                   if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
                 }
+                SER_CHECK(lo <= kb && sm.goff[cl] + lo < p.big_icap);
                 sm.pick16[cl] = (uint16_t)lo;
                 sm.dsl[cl] = SER_SUB(target, lo > k0 ? SER_ADD(base, val[lo - 1]) : base);
               }
