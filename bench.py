@@ -44,10 +44,12 @@ ALGO = {
 TOTAL_CHAINS = {"g10s10": 16384, "g10s2": 16384, "g5s5": 16384, "g2s2": 16384, "synthetic": 65536}  # BASELINE.json configs 4, 5
 METRIC = "mcmc_sweeps_per_s_aggregate"
 UNIT = "sweeps/s"
-# DRAM bytes per chain-sweep of the sweep kernels from the committed `ncu --set full` captures
-# (dram__bytes_read.sum + dram__bytes_write.sum of the profiled launch / its chain-sweeps): profiles/r02/README.md
-NCU_DRAM_PER_SWEEP = {"g2s2": ((10.899968e6 + 414.976e3) / 40960, "profiles/r01/sweep_final_ncu_raw_selected.txt"),
-                      "synthetic": ((2.160332e9 + 1.837035e9) / 2960, "profiles/r01/sweep_big_v7_ncu_raw_selected.txt")}
+# DRAM traffic of the sweep kernels from the committed `ncu --set full` captures (profiles/r02/README.md).
+# ser_sweep_kernel: dram__bytes_read.sum + dram__bytes_write.sum = 103.29 MB + 167.47 MB over the 8 192 work items of the profiled
+# launch (4 096 chains x 2 one-call items) = 33.05 KB per work item -- the chain state incl. its bit columns going through HBM at an
+# item boundary; the thinned samples add 2 N bytes each.  ser_sweep_kernel_big: 1.310 GB + 1.220 GB over 2 960 chain-sweeps.
+NCU_DRAM = {"g2s2": dict(per_item=(103.289856e6 + 167.473152e6) / 8192, src="profiles/r02/sweep_r02_ncu_raw_selected.txt"),
+            "synthetic": dict(per_sweep=(1.310332e9 + 1.220131e9) / 2960, src="profiles/r02/sweep_big_r02_ncu_raw_selected.txt")}
 
 
 def workload_name(dataset):
@@ -340,10 +342,18 @@ def main():
         kernel_sweeps_per_s = job.n_local * calls * 10 / (sweep_ms * 1e-3)
         achieved = 10.0 * algo["F"] * kernel_sweeps_per_s / 1e12
         traffic = traffic_src = None
-        if args.dataset in NCU_DRAM_PER_SWEEP:
-            per, src = NCU_DRAM_PER_SWEEP[args.dataset]
-            traffic = per * job.n_local * calls * 10
-            traffic_src = "%s: %.0f B of DRAM traffic per chain-sweep x the %d chain-sweeps of one sweep launch" % (src, per, job.n_local * calls * 10)
+        if args.dataset in NCU_DRAM:
+            nd = NCU_DRAM[args.dataset]
+            if "per_item" in nd:   # one-thread-per-column kernel: work items x state round trip + the thinned samples
+                slots = 148 * 3
+                chunk = max(1, min(calls, job.n_local * calls // (32 * slots)))
+                items = job.n_local * -(-calls // chunk)
+                traffic = items * nd["per_item"] + job.n_local * samp * 2 * job.N
+                traffic_src = ("%s: %.0f B of DRAM traffic per work item x %d items of one launch (%d calls per item) + %d thinned samples x %d B"
+                               % (nd["src"], nd["per_item"], items, chunk, job.n_local * samp, 2 * job.N))
+            else:
+                traffic = nd["per_sweep"] * job.n_local * calls * 10
+                traffic_src = "%s: %.0f B of DRAM traffic per chain-sweep x %d chain-sweeps of one launch" % (nd["src"], nd["per_sweep"], job.n_local * calls * 10)
         if "synthetic_65536" in also and also["synthetic_65536"]["kernel_sweeps_per_s_per_gpu"]:
             also["synthetic_65536"]["fp64_frac"] = 10.0 * ALGO["synthetic"]["F"] * also["synthetic_65536"]["kernel_sweeps_per_s_per_gpu"] / 1e12 / mb["fp64_tflops"]
         roofline = {
