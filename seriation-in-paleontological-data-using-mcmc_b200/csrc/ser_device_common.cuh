@@ -43,6 +43,7 @@ struct KParams {
   const uint16_t *order;    /* [M] column -> taxon (columns are sorted by ones, descending) */
   const int *off;           /* [M+1] first item of each column; a column has ones+1 items */
   const uint32_t *item_col; /* [I] item -> (column << 16) | index of the item inside its column */
+  const uint16_t *col_sites; /* [ones_total] the sites (file order) holding a one, per sorted column; column c starts at off[c] - c */
   const uint32_t *hbits;    /* [M] bit k = the column has a one at the k-th hard site in file order (first 32 hard sites) */
   int I;                    /* ones_total + M */
   /* large-shape path (ser_sweep_kernel_big): per-CTA-slot scratch in global memory */
@@ -280,15 +281,6 @@ __global__ void ser_init_kernel(KParams p)
   __syncthreads();
 
   uint16_t *ab = p.ab + (size_t)chain * 2 * p.Mpad;
-  if (nh == 0) { /* identity-order a/b are kept although pi is shuffled (mcmc.c:486-494) */
-    for (int c = tid; c < M; c += C) {
-      int a, b;
-      taxon_init_ab(p, sm.rpi, c, &a, &b);
-      ab[c] = (uint16_t)a; ab[p.Mpad + c] = (uint16_t)b;
-    }
-    __syncthreads();
-  }
-
   __shared__ int s_used;
   if (tid == 0) {
     int used_draws = 0;
@@ -324,12 +316,25 @@ __global__ void ser_init_kernel(KParams p)
   SerWeights wt;
   wt.eps = p.eps;
   set_weights(wt, p.c0, p.cc0, p.d0, p.dd0);
+  /* mcmc_initab (mcmc.c:440-474) + the alive ones of mcmc_count01 from the column's static site list (the sites that hold a
+   * one, in file order): a = first, b = last + 1 position of a one, so every one is alive.  nh == 0: the identity-order
+   * a, b are kept although pi was shuffled (mcmc.c:486-494) -- then the alive ones have to be counted. */
   int t1 = 0, len = 0;
   for (int c = tid; c < M; c += C) {
-    int a, b;
-    if (nh != 0) { taxon_init_ab(p, sm.rpi, c, &a, &b); ab[c] = (uint16_t)a; ab[p.Mpad + c] = (uint16_t)b; }
-    else { a = ab[c]; b = ab[p.Mpad + c]; }
-    t1 += taxon_count(p, sm.rpi, c, a, b);
+    const uint16_t *cs = p.col_sites + (p.off[c] - c);
+    const int K = p.ones[c];
+    int a = 0, b = N, t1c = 0;
+    if (nh != 0) {
+      int mn = N, mx = -1;
+      for (int k = 0; k < K; k++) { const int q = pi16[cs[k]]; mn = min(mn, q); mx = max(mx, q); }
+      if (K) { a = mn; b = mx + 1; }
+      t1c = K;
+    } else {
+      if (K) { a = cs[0]; b = cs[K - 1] + 1; }
+      for (int k = 0; k < K; k++) { const int q = pi16[cs[k]]; t1c += (a <= q && q < b); }
+    }
+    ab[c] = (uint16_t)a; ab[p.Mpad + c] = (uint16_t)b;
+    t1 += t1c;
     len += b - a;
   }
   int buf = 0, T1, LEN, dummy;

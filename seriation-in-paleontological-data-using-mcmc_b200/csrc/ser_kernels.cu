@@ -60,6 +60,7 @@ struct ser_run {
   uint32_t *d_item_col;
   uint2 *d_unit_tab;
   uint32_t *d_hbits;
+  uint16_t *d_col_sites;
   uint16_t *d_ab, *d_rpi;
   ChainScalars *d_scal;
   double *d_tape;
@@ -282,6 +283,10 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
         k++;
       }
   }
+  std::vector<uint16_t> col_sites((size_t)std::max<long long>(1, ones_total));
+  for (int c = 0, w = 0; c < M; c++)
+    for (int n = 0; n < N; n++)
+      if (ds->X[(size_t)n * M + order[c]]) col_sites[w++] = (uint16_t)n;
   std::vector<uint32_t> item_col(kp.I);
   for (int c = 0; c < M; c++)
     for (int e = off[c]; e < off[c + 1]; e++) item_col[e] = ((uint32_t)c << 16) | (uint32_t)(e - off[c]);
@@ -297,6 +302,8 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
   CUDA_TRY(POOL_ALLOC(&run->d_off, (M + 1) * sizeof(int)));
   CUDA_TRY(POOL_ALLOC(&run->d_order, M * sizeof(uint16_t)));
   CUDA_TRY(POOL_ALLOC(&run->d_item_col, (size_t)kp.I * sizeof(uint32_t)));
+  CUDA_TRY(POOL_ALLOC(&run->d_col_sites, col_sites.size() * sizeof(uint16_t)));
+  CUDA_TRY(cudaMemcpyAsync(run->d_col_sites, col_sites.data(), col_sites.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(POOL_ALLOC(&run->d_hbits, (size_t)M * sizeof(uint32_t)));
   CUDA_TRY(cudaMemcpyAsync(run->d_hbits, hbits.data(), (size_t)M * sizeof(uint32_t), cudaMemcpyHostToDevice, run->stream));
   CUDA_TRY(POOL_ALLOC(&run->d_ab, nc * 2 * kp.Mpad * sizeof(uint16_t)));
@@ -321,7 +328,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     CUDA_TRY(POOL_ALLOC(&run->d_samp_cdl, nc * cfg->max_samples * 3 * sizeof(double)));
   }
   kp.Xs = run->d_Xs; kp.hard = run->d_hard; kp.ones = run->d_ones;
-  kp.order = run->d_order; kp.off = run->d_off; kp.item_col = run->d_item_col; kp.hbits = run->d_hbits;
+  kp.order = run->d_order; kp.off = run->d_off; kp.item_col = run->d_item_col; kp.hbits = run->d_hbits; kp.col_sites = run->d_col_sites;
   kp.ab = run->d_ab; kp.rpi = run->d_rpi; kp.scal = run->d_scal;
   kp.samp_a = run->d_samp_a; kp.samp_b = run->d_samp_b; kp.samp_pi = run->d_samp_pi; kp.samp_cdl = run->d_samp_cdl;
   if (cfg->manycd) { /* per-taxon c, d: state rows and, with the full store, per-sample rows */
@@ -592,7 +599,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
                   run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp,
-                  run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts, run->d_unit_tab, run->d_hbits, run->d_cl_off, run->d_cl_item, run->d_cl_grp};
+                  run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts, run->d_unit_tab, run->d_hbits, run->d_col_sites, run->d_cl_off, run->d_cl_item, run->d_cl_grp};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   if (run->stream) cudaStreamSynchronize(run->stream);
   if (run->sweep_ev) {
