@@ -164,7 +164,14 @@ static void mark_launch(ser_run *run)
 #define SER_SMEM_DYN_MAX (SER_SMEM_OPTIN - 1024) /* the sweep kernels hold 1 KB of static shared memory */
 static cudaError_t allow_max_dynamic_smem(void)
 {
-  cudaError_t e = cudaSuccess;
+  /* once per device: seven driver calls that run creation (the e2e path creates a run per job) need not repeat */
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
   auto allow = [&](const void *f) { /* static + dynamic shared memory share the opt-in limit */
     cudaFuncAttributes fa;
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, f);
@@ -177,6 +184,7 @@ static cudaError_t allow_max_dynamic_smem(void)
   allow((const void *)ser_sweep_kernel<384, 2, true>);
   allow((const void *)ser_sweep_kernel_big);
   allow((const void *)ser_sweep_kernel_cl);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
 }
 
