@@ -74,7 +74,7 @@ typedef struct ser_run_config {
   int32_t store;           /* SER_STORE_*                                                      */
   int32_t max_samples;     /* capacity of the thinned-sample store per chain                   */
   int32_t device;          /* CUDA device ordinal                                              */
-  int32_t manycd;          /* 1: per-taxon c, d (mcmc_readmodel's manycd, mcmc.c:363, :777-785) */
+  int32_t manycd;          /* 1: per-taxon c, d (mcmc_readmodel's manycd, mcmc.c:363, :777-785); any supported shape */
 } ser_run_config;
 
 const char *ser_last_error(void);

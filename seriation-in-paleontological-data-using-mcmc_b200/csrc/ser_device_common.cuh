@@ -77,6 +77,7 @@ struct KParams {
   int manycd;
   double *cd4;         /* [chain][4][Mpad]: c, log(1-e^c), d, log(1-e^d) per column */
   double *samp_cd_all; /* [chain][sample][2][M]: c, d per taxon (SER_STORE_FULL) */
+  int col0;            /* the sorted column that holds taxon 0 (its c, d are what compute_exp_data reads) */
   /* the item weights of a Gibbs step are evaluated group by group of columns through a buffer of
    * Ival doubles: a smaller buffer = more resident chains per SM */
   int n_groups, Ival;

@@ -182,7 +182,8 @@ static cudaError_t allow_max_dynamic_smem(void)
   allow((const void *)ser_sweep_kernel<384, 2, false>);
   allow((const void *)ser_sweep_kernel<1024, 1, true>);
   allow((const void *)ser_sweep_kernel<384, 2, true>);
-  allow((const void *)ser_sweep_kernel_big);
+  allow((const void *)ser_sweep_kernel_big<false>);
+  allow((const void *)ser_sweep_kernel_big<true>);
   allow((const void *)ser_sweep_kernel_cl);
   if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
@@ -282,6 +283,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
       if (ds->X[(size_t)n * M + order[c]]) Xs[(size_t)n * kp.Mw + (c >> 5)] |= 1u << (c & 31);
   }
   kp.I = off[M];
+  for (int c = 0; c < M; c++) if (order[c] == 0) kp.col0 = c;
   std::vector<uint32_t> hbits(M, 0u); /* ones of a column at the hard sites, by hard rank (= file order of the hard sites) */
   {
     int k = 0;
@@ -351,24 +353,21 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
   run->smem_init = run->smem_small + sizeof(double) * 2 * N + sizeof(uint16_t) * 3 * N + 64;
   CUDA_TRY(allow_max_dynamic_smem());
   if (cfg->manycd) {
-    /* per-taxon c, d: one thread per taxon, columns and postings in shared memory -- there is no large-shape
-     * variant.  The per-taxon kernel needs its 80 registers (2.7 M vs 2.5 M sweeps/s on g2s2 with 64): the
-     * groups are sized for the instantiation that will run. */
+    /* per-taxon c, d: one thread per taxon while the chain's columns and postings fit shared memory, else (or with
+     * SER_FORCE_BIG) the large-shape slot kernel's per-taxon instantiation.  The one-thread-per-taxon kernel needs its 80
+     * registers (2.7 M vs 2.5 M sweeps/s on g2s2 with 64): the groups are sized for the instantiation that will run. */
     int rc = SER_E_ARG;
     if (!run->big)
       rc = run->C <= 384 ? choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<384, 2, true>, &run->smem_many)
                          : choose_groups(kp, off, M, N, run->W, run->C, 1, ser_sweep_kernel<1024, 1, true>, &run->smem_many);
     if (rc == SER_E_CUDA) return rc;
-    if (rc != SER_OK) {
-      ser_set_error("ser_run_create: manycd=1 needs one thread per taxon (M <= 1023) and the chain's columns and postings in "
-                    "shared memory (%zu B here, at most %d)", smem_layout(nullptr, nullptr, N, run->W, run->C, run->kp.I, 1, N + 1), SER_SMEM_DYN_MAX);
-      return SER_E_ARG;
+    if (rc != SER_OK) run->big = 1;
+    else {
+      int occ64 = 0, occ85 = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel<1024, 1, true>, run->C, run->smem_many));
+      if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel<384, 2, true>, run->C, run->smem_many));
+      run->variant_many = (occ85 >= occ64 && occ85 > 0) ? 1 : 0;
     }
-    int occ64 = 0, occ85 = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, ser_sweep_kernel<1024, 1, true>, run->C, run->smem_many));
-    if (run->C <= 384) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ85, ser_sweep_kernel<384, 2, true>, run->C, run->smem_many));
-    run->variant_many = (occ85 >= occ64 && occ85 > 0) ? 1 : 0;
-    run->big = 0;
   } else if (!run->big) {
     /* one thread per column while the columns, postings and one group's item weights fit shared memory
      * (SER_PREFER_BIG=1: only while ALL item weights fit, the pre-grouping rule); else the large-shape kernel */
@@ -388,7 +387,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
       if (const char *v = getenv("SER_SWEEP_VARIANT")) run->variant = (atoi(v) == 1 && run->C <= 384) ? 1 : 0;
     }
   }
-  if (run->big && getenv("SER_BIG_MODE") && !strcmp(getenv("SER_BIG_MODE"), "cluster")) {
+  if (run->big && !cfg->manycd && getenv("SER_BIG_MODE") && !strcmp(getenv("SER_BIG_MODE"), "cluster")) {
     /* Cluster path (opt-in, SER_BIG_MODE=cluster): the chain's bit columns sharded over the shared memory of R CTAs
      * (ser_sweep_kernel_cluster.cuh).  It removes the HBM re-streaming of the slot path, but on the 1024 x 4096 matrix it
      * needs R = 8, and the per-proposal latency chain, replicated in 8 CTAs, costs more than the DRAM round trips it saves
@@ -470,7 +469,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     int budget_kb = 220;
     if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(224, atoi(v)));
     const int gcap = std::min(M, 512); /* columns per group: sizes the per-column tables of a group */
-    const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap);
+    const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap, cfg->manycd);
     long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32; /* val 8 + pos 2 bytes per item */
     icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);
     if (icap < std::max(N + 1, M)) { /* one whole column, and the M per-taxon terms of the exact sums */
@@ -493,10 +492,11 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     CUDA_TRY(cudaMemcpyAsync(run->d_bgrp, bgrp.data(), bgrp.size() * sizeof(int), cudaMemcpyHostToDevice, run->stream));
     CUDA_TRY(cudaStreamSynchronize(run->stream));
     kp.bgrp = run->d_bgrp;
-    run->smem_big = big_layout(nullptr, nullptr, N, M, (int)icap, gcap);
+    run->smem_big = big_layout(nullptr, nullptr, N, M, (int)icap, gcap, cfg->manycd);
     if (run->smem_big > SER_SMEM_DYN_MAX) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_big); return SER_E_ARG; }
     int per_sm = 1, n_sm = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big, run->big_threads, run->smem_big));
+    if (cfg->manycd) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big<true>, run->big_threads, run->smem_big));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big<false>, run->big_threads, run->smem_big));
     CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     run->big_slots = std::max(1, std::min(cfg->n_chains, per_sm * n_sm));
     kp.Cs = ((M + 1) + 31) / 32 * 32;
@@ -712,7 +712,8 @@ extern "C" int ser_run_advance_both(ser_run *run, int32_t burn_calls, int32_t sa
   }
   if (run->big) {
     if (rec) CUDA_TRY(cudaEventRecord(ev0, run->stream));
-    ser_sweep_kernel_big<<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+    if (run->cfg.manycd) ser_sweep_kernel_big<true><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+    else ser_sweep_kernel_big<false><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
     CUDA_TRY(cudaGetLastError());
     if (rec) CUDA_TRY(cudaEventRecord(ev1, run->stream));
     return SER_OK;

@@ -19,11 +19,13 @@ struct BigSmem {
   uint16_t *pos; /* icap: postings of the running group's columns */
   uint16_t *pick16;         /* gcap: the item the column's uniform fell into */
   double *uab;              /* 2 gcap: the two uniforms (a-step, b-step) of every column of the running group */
+  double *wcol;             /* manycd: 4 gcap per-column weights A, g, 1/g, 1/(1-e^-g) of the running group */
+  double *redd;             /* manycd: 2 x 32 doubles of reduction scratch */
   uint32_t *hcol;           /* W: the hard-site mask in position order (stride 1; never leaves shared memory) */
   uint16_t *hpre;           /* W+1: its prefix table */
   uint16_t *hrank, *nhpos;  /* N+2 each: SerHard's tables */
 };
-__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap)
+__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap, int manycd = 0)
 {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
@@ -32,9 +34,10 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
   size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)gcap), o_hp = take(2 * (size_t)(N + 1));
   size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
   size_t o_pk = take(2 * (size_t)gcap), o_hc = take(4 * (size_t)(N / 32 + 1)), o_hq = take(2 * (size_t)(N / 32 + 2)), o_ua = take(16 * (size_t)gcap);
+  size_t o_wc = take(manycd ? 32 * (size_t)gcap : 0), o_rd = take(manycd ? 8 * 2 * SER_MAX_WARPS : 0);
   size_t o_hr = take(2 * (size_t)(N + 2)), o_nh = take(2 * (size_t)(N + 2));
   if (s) {
-    s->uab = (double *)(base + o_ua);
+    s->uab = (double *)(base + o_ua); s->wcol = (double *)(base + o_wc); s->redd = (double *)(base + o_rd);
     s->pick16 = (uint16_t *)(base + o_pk); s->hcol = (uint32_t *)(base + o_hc); s->hpre = (uint16_t *)(base + o_hq);
     s->hrank = (uint16_t *)(base + o_hr); s->nhpos = (uint16_t *)(base + o_nh);
     s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos); s->dsl = (double *)(base + o_in);
@@ -48,22 +51,32 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
   return off;
 }
 
-/* MH tail for the large-shape kernel: the thread's deltas are already summed over its columns;
- * the degenerate case re-evaluates the per-taxon deltas through `redo` (a lambda) */
-template <typename Redo>
-__device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &sm, const SerWeights &wt, PropState &ps,
-                                              double *terms, int dt0, int dt1, int nz, bool exact, int *D0, int *D1,
+/* per-column weights (manycd): c, log(1-e^c), d, log(1-e^d) of sorted column col from the chain's cd4 rows */
+__device__ __forceinline__ void big_col_weights(const double *cd4, int Mpad, int col, SerWeights *w)
+{
+  w->c = cd4[col]; w->cc = cd4[Mpad + col]; w->d = cd4[2 * Mpad + col]; w->dd = cd4[3 * Mpad + col];
+}
+
+/* MH tail for the large-shape kernel: the thread's deltas are already summed over its columns (`tsum` = its float
+ * terms, per-taxon c, d only); the degenerate / exact cases re-evaluate the per-taxon deltas through `redo` (a lambda)
+ * and add the terms in taxon order (see mh_decide) */
+template <bool MANY, typename Redo>
+__device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &sm, const SerWeights &wt, const double *cd4, PropState &ps,
+                                              double *terms, int dt0, int dt1, int nz, double tsum, bool exact, int *D0, int *D1,
                                               double *delta_out, Redo redo)
 {
   int NZ;
-  block_sum3(dt0, dt1, nz, sm.red, ps.buf, D0, D1, &NZ);
-  auto reference_sum = [&]() { /* see mh_decide */
+  double delta = 0.0;
+  if constexpr (MANY) block_sum3d(dt0, dt1, nz, tsum, sm.red, sm.redd, ps.buf, D0, D1, &NZ, &delta);
+  else block_sum3(dt0, dt1, nz, sm.red, ps.buf, D0, D1, &NZ);
+  auto reference_sum = [&]() {
     double acc = 0.0;
     __syncthreads();
     for (int c = threadIdx.x; c < p.M; c += blockDim.x) {
       int x0, x1;
       redo(c, &x0, &x1);
-      terms[p.order[c]] = ser_term(wt, x0, x1);
+      if constexpr (MANY) { SerWeights w; big_col_weights(cd4, p.Mpad, c, &w); terms[p.order[c]] = ser_term(w, x0, x1); }
+      else terms[p.order[c]] = ser_term(wt, x0, x1);
     }
     __syncthreads();
     if (threadIdx.x < 32) { /* one warp walks the dependent chain, the others wait (see sequential_term_sum) */
@@ -73,13 +86,17 @@ __device__ __forceinline__ bool mh_decide_big(const KParams &p, const BigSmem &s
     __syncthreads();
     return sm.draws_cd[7];
   };
-  double delta;
   bool seq = false;
-  if (*D0 == 0 && *D1 == 0) {
-    delta = 0.0;
-    if (NZ) { delta = reference_sum(); seq = true; }
+  if constexpr (MANY) {
+    if (!NZ) delta = 0.0;
+    else if (fabs(delta) < 1e-7) { delta = reference_sum(); seq = true; }
   } else {
-    delta = ser_term(wt, *D0, *D1);
+    if (*D0 == 0 && *D1 == 0) {
+      delta = 0.0;
+      if (NZ) { delta = reference_sum(); seq = true; }
+    } else {
+      delta = ser_term(wt, *D0, *D1);
+    }
   }
   bool accept = delta >= 0.0;
   if (!accept) accept = delta > sm.logdraw[ps.k++];
@@ -101,11 +118,15 @@ __device__ __forceinline__ void big_rebuild_hard(const BigSmem &sm, int N)
   }
 }
 
+/* MANY = per-taxon c, d (manycd = 1, mcmc.c:777-785, :807-815): the chain's cd4 rows in HBM hold every column's c, log(1-e^c),
+ * d, log(1-e^d); the weights of a group's columns are staged in shared memory, geometric run sums are evaluated on the fly,
+ * delta / loglik are float sums over taxa (mh_decide_big). */
+template <bool MANY>
 __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BigSmem sm;
-  big_layout(&sm, smem_raw, p.N, p.M, p.big_icap, p.big_gcap);
+  big_layout(&sm, smem_raw, p.N, p.M, p.big_icap, p.big_gcap, MANY ? 1 : 0);
   const int tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, W = p.W, Cs = p.Cs;
   uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
   uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
@@ -113,6 +134,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
 
   for (int chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
     const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
+    double *cd4 = MANY ? p.cd4 + (size_t)chain * 4 * p.Mpad : nullptr;
     __syncthreads(); /* previous chain's state fully saved before the scratch is reused */
     ChainScalars sc = p.scal[chain];
     for (int n = tid; n < N; n += C) sm.rpi[n] = p.rpi[(size_t)chain * p.Npad + n];
@@ -143,7 +165,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
       tape_len = (long long)(p.tape_off[chain + 1] - p.tape_off[chain]);
     }
     SerWeights wt;
-    wt.eps = p.eps; wt.H = sm.H; wt.hmax = 0;
+    wt.eps = p.eps; wt.H = sm.H; wt.hmax = MANY ? N + 1 : 0; /* MANY: geometric sums on the fly, no table bound */
     set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
     SerHard hd;
     hd.hcol = sm.hcol; hd.hpre = sm.hpre; hd.hp = sm.hp; hd.C = 1; hd.W = W; hd.N = N; hd.nh = p.nh; hd.rank_tab = sm.hrank; hd.nonhard_tab = sm.nhpos;
@@ -156,49 +178,91 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         /* ================= stage this sweep's draws ================= */
         __syncthreads();
         PHASE_T0();
-        if (p.mode == SER_MODE_REPLAY) {
-          const long long need = sc.cursor + 6 + 2 * (long long)M;
-          if (need > tape_len) { sc.flags |= 1; break; }
-          if (tid < 6) sm.draws_cd[tid] = tape[sc.cursor + tid];
-          for (int t = tid; t < SER_PI_DRAWS; t += C) {
-            const long long idx = need + t;
-            const double u = idx < tape_len ? tape[idx] : 0.5;
-            sm.draws_pi[t] = u; sm.logdraw[t] = log(u);
-          }
-        } else {
-          if (tid < 4) {
-            const int cnt = tid == 0 ? sc.f1a : tid == 1 ? sc.t0a : tid == 2 ? sc.f0a : sc.t1a;
-            const double g = ser_gamma_ge1(1.0 + (double)cnt, p.seed, gchain, sc.sweep, (uint32_t)tid);
-            const double go = __shfl_xor_sync(0xfu, g, 1);
-            if (tid == 0 || tid == 2) {
-              const double y = ser_beta_from_gammas(g, go);
-              double val = tid == 0 ? sc.c : sc.d, l1m = tid == 0 ? sc.cc : sc.dd;
-              const double lo = tid == 0 ? SER_MINC : SER_MIND, hi = tid == 0 ? SER_MAXC : SER_MAXD;
-              if (y > 0.0) {
-                const double ly = ser_log(y);
-                if (lo <= ly && ly <= hi) { val = ly; l1m = ser_log(SER_SUB(1.0, ser_exp(ly))); }
-              }
-              sm.draws_cd[tid] = val; sm.draws_cd[tid + 1] = l1m;
+        if constexpr (MANY) {
+          /* M Betas for c, M for d (mcmc.c:777-785, :807-815), the pi draws; the a/b uniforms are staged per column group */
+          if (p.mode == SER_MODE_REPLAY) {
+            const long long need = sc.cursor + 8 * (long long)M;
+            if (need > tape_len) { sc.flags |= 1; break; }
+            for (int t = tid; t < SER_PI_DRAWS; t += C) {
+              const long long idx = need + t;
+              const double u = idx < tape_len ? tape[idx] : 0.5;
+              sm.draws_pi[t] = u; sm.logdraw[t] = log(u);
+            }
+          } else {
+            for (int t = tid; t < SER_PI_DRAWS; t += C) {
+              const double u = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+              sm.draws_pi[t] = u; sm.logdraw[t] = log(ser_pos(u));
             }
           }
-          for (int t = tid; t < SER_PI_DRAWS; t += C) {
-            const double u = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
-            sm.draws_pi[t] = u; sm.logdraw[t] = log(ser_pos(u));
+          for (int c = tid; c < M; c += C) { /* Beta(1+f1_m, 1+t0_m) and Beta(1+f0_m, 1+t1_m) from the taxon's own counts */
+            const int taxon = p.order[c];
+            double yc = 0.0, lyc = 0.0, l1c = 0.0, yd = 0.0, lyd = 0.0, l1d = 0.0;
+            if (p.mode == SER_MODE_REPLAY) {
+              const double *tc = tape + sc.cursor + 3 * taxon, *td = tape + sc.cursor + 3 * (long long)M + 3 * taxon;
+              yc = tc[0]; lyc = tc[1]; l1c = tc[2];
+              yd = td[0]; lyd = td[1]; l1d = td[2];
+            } else {
+              const int t1 = ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), len = sm.b16[c] - sm.a16[c];
+              const int f1 = p.ones[c] - t1, f0 = len - t1, t0 = N - len - f1;
+              const uint32_t blk = SER_BLK_MANYCD + 4u * (uint32_t)taxon;
+              yc = ser_beta_from_gammas(ser_gamma_ge1(1.0 + (double)f1, p.seed, gchain, sc.sweep, blk),
+                                        ser_gamma_ge1(1.0 + (double)t0, p.seed, gchain, sc.sweep, blk + 1u));
+              yd = ser_beta_from_gammas(ser_gamma_ge1(1.0 + (double)f0, p.seed, gchain, sc.sweep, blk + 2u),
+                                        ser_gamma_ge1(1.0 + (double)t1, p.seed, gchain, sc.sweep, blk + 3u));
+              if (yc > 0.0) { lyc = ser_log(yc); l1c = ser_log(SER_SUB(1.0, ser_exp(lyc))); }
+              if (yd > 0.0) { lyd = ser_log(yd); l1d = ser_log(SER_SUB(1.0, ser_exp(lyd))); }
+            }
+            if (yc > 0.0 && SER_MINC <= lyc && lyc <= SER_MAXC) { cd4[c] = lyc; cd4[p.Mpad + c] = l1c; }
+            if (yd > 0.0 && SER_MIND <= lyd && lyd <= SER_MAXD) { cd4[2 * p.Mpad + c] = lyd; cd4[3 * p.Mpad + c] = l1d; }
+            if (taxon == 0) { sm.draws_cd[0] = cd4[c]; sm.draws_cd[1] = cd4[2 * p.Mpad + c]; }
           }
-        }
-        __syncthreads();
-        if (p.mode == SER_MODE_REPLAY) {
-          const double yc = sm.draws_cd[0], lyc = sm.draws_cd[1], l1c = sm.draws_cd[2];
-          const double yd = sm.draws_cd[3], lyd = sm.draws_cd[4], l1d = sm.draws_cd[5];
-          if (yc > 0.0 && SER_MINC <= lyc && lyc <= SER_MAXC) { sc.c = lyc; sc.cc = l1c; }
-          if (yd > 0.0 && SER_MIND <= lyd && lyd <= SER_MAXD) { sc.d = lyd; sc.dd = l1d; }
+          sc.counters[0] += M; sc.counters[1] += M;
         } else {
-          sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3];
+          if (p.mode == SER_MODE_REPLAY) {
+            const long long need = sc.cursor + 6 + 2 * (long long)M;
+            if (need > tape_len) { sc.flags |= 1; break; }
+            if (tid < 6) sm.draws_cd[tid] = tape[sc.cursor + tid];
+            for (int t = tid; t < SER_PI_DRAWS; t += C) {
+              const long long idx = need + t;
+              const double u = idx < tape_len ? tape[idx] : 0.5;
+              sm.draws_pi[t] = u; sm.logdraw[t] = log(u);
+            }
+          } else {
+            if (tid < 4) {
+              const int cnt = tid == 0 ? sc.f1a : tid == 1 ? sc.t0a : tid == 2 ? sc.f0a : sc.t1a;
+              const double g = ser_gamma_ge1(1.0 + (double)cnt, p.seed, gchain, sc.sweep, (uint32_t)tid);
+              const double go = __shfl_xor_sync(0xfu, g, 1);
+              if (tid == 0 || tid == 2) {
+                const double y = ser_beta_from_gammas(g, go);
+                double val = tid == 0 ? sc.c : sc.d, l1m = tid == 0 ? sc.cc : sc.dd;
+                const double lo = tid == 0 ? SER_MINC : SER_MIND, hi = tid == 0 ? SER_MAXC : SER_MAXD;
+                if (y > 0.0) {
+                  const double ly = ser_log(y);
+                  if (lo <= ly && ly <= hi) { val = ly; l1m = ser_log(SER_SUB(1.0, ser_exp(ly))); }
+                }
+                sm.draws_cd[tid] = val; sm.draws_cd[tid + 1] = l1m;
+              }
+            }
+            for (int t = tid; t < SER_PI_DRAWS; t += C) {
+              const double u = ser_stream_uniform(p.seed, gchain, sc.sweep, SER_BLK_PI, (uint32_t)t);
+              sm.draws_pi[t] = u; sm.logdraw[t] = log(ser_pos(u));
+            }
+          }
+          __syncthreads();
+          if (p.mode == SER_MODE_REPLAY) {
+            const double yc = sm.draws_cd[0], lyc = sm.draws_cd[1], l1c = sm.draws_cd[2];
+            const double yd = sm.draws_cd[3], lyd = sm.draws_cd[4], l1d = sm.draws_cd[5];
+            if (yc > 0.0 && SER_MINC <= lyc && lyc <= SER_MAXC) { sc.c = lyc; sc.cc = l1c; }
+            if (yd > 0.0 && SER_MIND <= lyd && lyd <= SER_MAXD) { sc.d = lyd; sc.dd = l1d; }
+          } else {
+            sc.c = sm.draws_cd[0]; sc.cc = sm.draws_cd[1]; sc.d = sm.draws_cd[2]; sc.dd = sm.draws_cd[3];
+          }
+          set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
+          sc.counters[0]++; sc.counters[1]++;
+          wt.hmax = ser_hmax(wt.g, N);
+          for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
+
         }
-        set_weights(wt, sc.c, sc.cc, sc.d, sc.dd);
-        sc.counters[0]++; sc.counters[1]++;
-        wt.hmax = ser_hmax(wt.g, N);
-        for (int m = tid; m <= wt.hmax; m += C) sm.H[m] = ser_h_entry(wt.g, m);
 
         /* ================= a/b Gibbs, item formulation, one column group at a time =================
          * The group's postings and item weights live in shared memory (icap items), so the per-column
@@ -243,11 +307,20 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           }
           for (int cl = tid; cl < nc; cl += C) { /* the two uniforms of every column of the group (mcmc.c:951, :963 -> :909) */
             const int taxon = p.order[c0 + cl];
-            if (p.mode == SER_MODE_REPLAY) { sm.uab[2 * cl] = tape[sc.cursor + 6 + 2 * taxon]; sm.uab[2 * cl + 1] = tape[sc.cursor + 7 + 2 * taxon]; }
+            if (p.mode == SER_MODE_REPLAY) {
+              const long long u0 = sc.cursor + (MANY ? 6 * (long long)M : 6) + 2 * taxon;
+              sm.uab[2 * cl] = tape[u0]; sm.uab[2 * cl + 1] = tape[u0 + 1];
+            }
             else {
               uint32_t o[4];
               ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
               sm.uab[2 * cl] = ser_u53(o[0], o[1]); sm.uab[2 * cl + 1] = ser_u53(o[2], o[3]);
+            }
+            if constexpr (MANY) { /* the column's own weights for the passes of this group */
+              SerWeights w;
+              big_col_weights(cd4, p.Mpad, c0 + cl, &w);
+              ser_set_weights_own(&w, w.c, w.cc, w.d, w.dd, N);
+              sm.wcol[4 * cl + 0] = w.A; sm.wcol[4 * cl + 1] = w.g; sm.wcol[4 * cl + 2] = w.inv_g; sm.wcol[4 * cl + 3] = w.hs;
             }
           }
           __syncthreads();
@@ -264,9 +337,11 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               double lm = -1.0e300;
               if (live) { /* every item's log-weight stays in val for the dense pass */
                 double *Lc = sm.val + sm.goff[cl];
+                SerWeights w = wt;
+                if constexpr (MANY) { w.A = sm.wcol[4 * cl + 0]; w.g = sm.wcol[4 * cl + 1]; }
                 for (int kk = sub; kk <= st.kb; kk += lpc) {
                   int q, n;
-                  const double L = ser_item_eval(wt, st, pos, kk, &q, &n);
+                  const double L = ser_item_eval(w, st, pos, kk, &q, &n);
                   Lc[kk] = L;
                   lm = ser_fmax(lm, L);
                 }
@@ -293,7 +368,13 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                 int q, qprev; /* ser_item_eval's q and qprev */
                 if (step) { q = kk < kb ? N - 1 - (int)pos[nones - 1 - kk] : bound; qprev = kk > 0 ? N - 1 - (int)pos[nones - kk] : -1; }
                 else { q = kk < kb ? (int)pos[kk] : bound; qprev = kk > 0 ? (int)pos[kk - 1] : -1; }
-                sm.val[e - e0] = ser_item_weight_cached<1>(wt, sm.val[e - e0], q - qprev, sm.lmax[cl]);
+                if constexpr (MANY) {
+                  SerWeights w = wt;
+                  w.g = sm.wcol[4 * cl + 1]; w.inv_g = sm.wcol[4 * cl + 2]; w.hs = sm.wcol[4 * cl + 3];
+                  sm.val[e - e0] = ser_item_weight_cached<0>(w, sm.val[e - e0], q - qprev, sm.lmax[cl]);
+                } else {
+                  sm.val[e - e0] = ser_item_weight_cached<1>(wt, sm.val[e - e0], q - qprev, sm.lmax[cl]);
+                }
               }
             }
             __syncthreads();
@@ -337,8 +418,10 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = (int)(g4.y >> 16);
               st.nones = sm.gones[cl]; st.N = N; st.rev = step;
               int q, n;
-              const double le = SER_SUB(ser_item_eval(wt, st, sm.pos + sm.goff[cl], (int)sm.pick16[cl], &q, &n), sm.lmax[cl]);
-              const int pick = q - n + 1 + ser_run_pick<1>(wt, n, le, 0.0, sm.dsl[cl]);
+              SerWeights w = wt;
+              if constexpr (MANY) { w.A = sm.wcol[4 * cl + 0]; w.g = sm.wcol[4 * cl + 1]; w.inv_g = sm.wcol[4 * cl + 2]; w.hs = sm.wcol[4 * cl + 3]; }
+              const double le = SER_SUB(ser_item_eval(w, st, sm.pos + sm.goff[cl], (int)sm.pick16[cl], &q, &n), sm.lmax[cl]);
+              const int pick = q - n + 1 + ser_run_pick<MANY ? 0 : 1>(w, n, le, 0.0, sm.dsl[cl]);
               if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
               else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
             }
@@ -350,17 +433,29 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         const bool exact = sampling && s == p.sweeps_per_call - 1;
         {
           int t1 = 0, len = 0, T1, LEN, CH;
+          double tsum = 0.0;
           for (int c = tid; c < M; c += C) {
             const int t1c = ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), lenc = sm.b16[c] - sm.a16[c];
             t1 += t1c; len += lenc;
-            if (exact) { /* mcmc_logl's per-taxon term, mcmc.c:643-644 */
+            if (MANY || exact) { /* mcmc_logl's per-taxon term, mcmc.c:643-644 */
               const int f1 = p.ones[c] - t1c, f0 = lenc - t1c, t0 = N - lenc - f1;
-              TERMS[p.order[c]] = SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)t0, wt.cc), SER_MUL((double)f0, wt.d)), SER_MUL((double)t1c, wt.dd)),
-                                          SER_MUL((double)f1, wt.c));
+              SerWeights w = wt;
+              if constexpr (MANY) big_col_weights(cd4, p.Mpad, c, &w);
+              const double term = SER_ADD(SER_ADD(SER_ADD(SER_MUL((double)t0, w.cc), SER_MUL((double)f0, w.d)), SER_MUL((double)t1c, w.dd)),
+                                          SER_MUL((double)f1, w.c));
+              tsum += term;
+              if (exact) TERMS[p.order[c]] = term;
             }
           }
-          block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
-          totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
+          if constexpr (MANY) {
+            double ll;
+            block_sum3d(t1, len, changed, tsum, sm.red, sm.redd, ps.buf, &T1, &LEN, &CH, &ll);
+            sc.t1a = T1; sc.f1a = (int)p.ones_total - T1; sc.f0a = LEN - T1; sc.t0a = N * M - LEN - sc.f1a;
+            sc.loglik = ll;
+          } else {
+            block_sum3(t1, len, changed, sm.red, ps.buf, &T1, &LEN, &CH);
+            totals_from(p, wt, T1, LEN, &sc.t0a, &sc.f0a, &sc.t1a, &sc.f1a, &sc.loglik);
+          }
           sc.counters[2] += CH;
           if (exact) {
             if (tid < 32) {
@@ -379,7 +474,11 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         for (int prop = 0; prop < 16; prop++) {
           const int kind = prop == 0 ? 3 : ((prop - 1) % 3);
           int dt0 = 0, dt1 = 0, nz = 0, D0, D1;
-          double delta;
+          double delta, tsum = 0.0;
+          auto add = [&](int c, int x0, int x1) { /* a column's deltas into the thread's partial sums */
+            dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0;
+            if constexpr (MANY) if (x0 | x1) { SerWeights w; big_col_weights(cd4, p.Mpad, c, &w); tsum += ser_term(w, x0, x1); }
+          };
           if (kind == 0) { /* pi1 */
             const int i = ser_draw_int(sm.draws_pi[ps.k], N);
             int j = ser_draw_int(sm.draws_pi[ps.k + 1], N - 1);
@@ -388,8 +487,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             const int lo = min(i, j), hi = max(i, j);
             if (ser_is_hard(hd, i) && ser_hard_count(hd, lo, hi) > 1) continue;
             auto redo = [&](int c, int *x0, int *x1) { ser_pi1_delta(V + c, Cs, sm.a16[c], sm.b16[c], i, j, x0, x1); };
-            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
-            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); add(c, x0, x1); }
+            if (!mh_decide_big<MANY>(p, sm, wt, cd4, ps, TERMS, dt0, dt1, nz, tsum, exact, &D0, &D1, &delta, redo)) continue;
             for (int c = tid; c <= M; c += C) {
               if (c < M) {
                 int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
@@ -418,8 +517,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
             ps.k += 2;
             auto redo = [&](int c, int *x0, int *x1) { ser_pi2_delta(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c], i, j, inc1, inc2, x0, x1); };
-            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
-            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); add(c, x0, x1); }
+            if (!mh_decide_big<MANY>(p, sm, wt, cd4, ps, TERMS, dt0, dt1, nz, tsum, exact, &D0, &D1, &delta, redo)) continue;
             for (int c = tid; c <= M; c += C) {
               if (c < M) {
                 int a = sm.a16[c], b = sm.b16[c];
@@ -450,8 +549,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               if (hb) ser_pi3_delta<true>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1, __ldg(p.hbits + c));
               else ser_pi3_delta<false>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1);
             };
-            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); dt0 += x0; dt1 += x1; nz |= (x0 | x1) != 0; }
-            if (!mh_decide_big(p, sm, wt, ps, TERMS, dt0, dt1, nz, exact, &D0, &D1, &delta, redo)) continue;
+            for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); add(c, x0, x1); }
+            if (!mh_decide_big<MANY>(p, sm, wt, cd4, ps, TERMS, dt0, dt1, nz, tsum, exact, &D0, &D1, &delta, redo)) continue;
             for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
             __syncthreads();
             for (int c = tid; c < M; c += C) {
@@ -471,7 +570,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           __syncthreads();
         }
 
-        if (p.mode == SER_MODE_REPLAY) sc.cursor += 6 + 2 * (long long)M + ps.k;
+        if (p.mode == SER_MODE_REPLAY) sc.cursor += (MANY ? 8 * (long long)M : 6 + 2 * (long long)M) + ps.k;
         else sc.sweep++;
         sc.counters[7]++;
         PHASE_MARK(6);
@@ -484,11 +583,16 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           const size_t row = (size_t)chain * p.max_samples + sidx;
           if (p.store >= SER_STORE_PI)
             for (int pos = tid; pos < N; pos += C) p.samp_pi[row * N + sm.rpi[pos]] = (uint16_t)pos;
+          if constexpr (MANY) { sc.c = sm.draws_cd[0]; sc.d = sm.draws_cd[1]; } /* taxon 0's c, d (compute_exp_data, mcmc.c:56-57) */
           if (p.store >= SER_STORE_FULL) {
-            for (int c = tid; c < M; c += C) { p.samp_a[row * M + p.order[c]] = sm.a16[c]; p.samp_b[row * M + p.order[c]] = sm.b16[c]; }
+            for (int c = tid; c < M; c += C) {
+              p.samp_a[row * M + p.order[c]] = sm.a16[c]; p.samp_b[row * M + p.order[c]] = sm.b16[c];
+              if constexpr (MANY) { p.samp_cd_all[(row * 2 + 0) * M + p.order[c]] = cd4[c]; p.samp_cd_all[(row * 2 + 1) * M + p.order[c]] = cd4[2 * p.Mpad + c]; }
+            }
             if (tid == 0) { p.samp_cdl[row * 3 + 0] = sc.c; p.samp_cdl[row * 3 + 1] = sc.d; p.samp_cdl[row * 3 + 2] = sc.loglik; }
           }
         }
+        if constexpr (MANY) { sc.c = sm.draws_cd[0]; sc.d = sm.draws_cd[1]; }
         sc.sum_negll = SER_ADD(sc.sum_negll, -sc.loglik);
         sc.sum_ec = SER_ADD(sc.sum_ec, exp(sc.c));
         sc.sum_ed = SER_ADD(sc.sum_ed, exp(sc.d));
@@ -502,6 +606,11 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
       p.ab[(size_t)chain * 2 * p.Mpad + p.Mpad + c] = sm.b16[c];
     }
     for (int n = tid; n < N; n += C) p.rpi[(size_t)chain * p.Npad + n] = sm.rpi[n];
-    if (tid == 0) p.scal[chain] = sc;
+    if (tid == 0) {
+      if constexpr (MANY) { /* the scalar slots carry taxon 0's c, d */
+        sc.c = cd4[p.col0]; sc.cc = cd4[p.Mpad + p.col0]; sc.d = cd4[2 * p.Mpad + p.col0]; sc.dd = cd4[3 * p.Mpad + p.col0];
+      }
+      p.scal[chain] = sc;
+    }
   }
 }

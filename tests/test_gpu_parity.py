@@ -561,8 +561,9 @@ def test_manycd_free_running_equals_oracle_philox(S, oracle_mod, name, burn, sam
 def test_manycd_errors_and_writers(S, oracle_mod, tmp_path):
     X, hard = load_hex_dataset("g10s10")
     ds = S.Dataset.from_bits(X, hard)
-    with pytest.raises(S.SeriationError):   # one thread per taxon: no large-shape variant
-        S.Run(S.Dataset.from_bits(np.ones((8, 2000), np.uint8)), 1, manycd=True)
+    wide = S.Run(S.Dataset.from_bits(np.ones((8, 2000), np.uint8)), 1, manycd=True).init().advance(1, True).sync()
+    assert wide.check() == 0 and len(set(wide.cd(0)[0])) > 100   # more taxa than threads: the large-shape per-taxon instantiation
+    wide.close()
     plain = S.Run(ds, 1).init()
     with pytest.raises(S.SeriationError):
         plain.cd(0)
@@ -1065,3 +1066,34 @@ def test_cluster_path_config5_and_many_chains(S, oracle_mod, monkeypatch):
     assert run.chain_stats()["e_negloglik"].tobytes() == ref.chain_stats()["e_negloglik"].tobytes()
     for i in (0, 37, 299):
         assert np.array_equal(run.fetch_samples(i, full=False)["pi"], ref.fetch_samples(i, full=False)["pi"])
+
+
+# ----------------------------------------------------------------------------- round 2: per-taxon c, d for large shapes
+@pytest.mark.parametrize("threads", ["64", "1024"])
+def test_manycd_big_path_replay_bit_exact(S, oracle_mod, monkeypatch, threads):
+    """manycd = 1 through the large-shape slot kernel (mcmc.c:777-785, :807-815 work for any M): replay vs the oracle after every
+    call, incl. every per-taxon c, d and the saved log-likelihood bits"""
+    monkeypatch.setenv("SER_FORCE_BIG", threads)
+    for name, burn, samp in (("g10s10", 6, 6), ("g5s5", 2, 2)):
+        X, hard = load_hex_dataset(name)
+        _manycd_replay_case(S, oracle_mod, X, hard, [31, 0], burn, samp)
+    rng = np.random.default_rng(11)
+    for shape in EDGE_SHAPES[1::3]:
+        X, hard = random_dataset(rng, *shape)
+        _manycd_replay_case(S, oracle_mod, X, hard, [4], 5, 5)
+
+
+def test_manycd_wide_matrix_replay_and_free_running(S, oracle_mod):
+    """more taxa than a CTA has threads (200 x 1500): per-taxon c, d on the large-shape kernel, replay and free-running"""
+    X, hard = S.Dataset.synthetic(200, 1500, 6, 11).arrays()
+    _manycd_replay_case(S, oracle_mod, X, hard, [1, 2], 2, 2)
+    seed, offset = 99, 5
+    run = S.Run(S.Dataset.from_bits(X, hard), 3, mode=S.MODE_FREE, seed=seed, chain_offset=offset, manycd=True)
+    run.init().advance(2, False).advance(2, True).sync()
+    assert run.check() == 0
+    for i in range(3):
+        o = _manycd_oracle(oracle_mod, X, hard, philox=(seed, offset + i), detmath=True)
+        for _ in range(4):
+            o.sample()
+        _cmp_manycd(run, i, o.state(), ("free", i), True)
+    run.close()
