@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
   rebuild_hard(p, sm);
   __syncthreads();
 
+  bool pos_dirty = true; /* the postings of this chain are not in shared memory yet */
   const double *tape = nullptr;
   long long tape_len = 0;
   if (p.mode == SER_MODE_REPLAY) {
@@ -343,6 +344,9 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
        * longest serial loop of a pass is ~1/6 of the heaviest column (g2s2: 95 items -> 12-16 per lane).  With one
        * thread per column the warp that owns the 32 heaviest columns was the critical path of every pass while the
        * other nine waited at the barrier (30 % of the sweep's cycles). */
+      /* The postings survive from sweep to sweep: an accepted adjacent swap or site move patches them in place (below);
+       * only a segment reversal or a pi3 move (1 % of the proposals each) marks them for this rebuild. */
+      if (pos_dirty)
       for (int ub = 0; ub < p.n_units; ub += C) { /* postings: lane `sub` expands its share of the column's words */
         const Unit un = unit_load(p, ub + tid, p.n_units);
         if (un.live) {
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           }
         }
       }
+      pos_dirty = false;
       PHASE_MARK(9);
       int changed = 0;
 #pragma unroll 1
@@ -532,6 +537,18 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           if (is_taxon) ser_pi1_delta(col, C, a, b, i, j, &dt0, &dt1);
           if (!mh_decide<MANY>(p, sm, wt, ps, taxon, is_taxon, dt0, dt1, exact, &D0, &D1, &delta)) continue;
           if (is_taxon) ser_pi1_apply_ab(&a, &b, i, j);
+          if (is_taxon && !pos_dirty) { /* the column's postings inside the window: shifted by one, the moved site's one goes to the other end */
+            uint16_t *pc = sm.pos + off_c;
+            const int k0 = ser_rank1(col, pre, C, lo), k1 = ser_rank1(col, pre, C, hi + 1); /* on the column BEFORE the move */
+            const int moved = ser_col_bit(col, C, i);
+            if (i < j) {
+              for (int k = k0 + moved; k < k1; k++) pc[k - moved] = (uint16_t)(pc[k] - 1);
+              if (moved) pc[k1 - 1] = (uint16_t)j;
+            } else {
+              for (int k = k1 - 1 - moved; k >= k0; k--) pc[k + moved] = (uint16_t)(pc[k] + 1);
+              if (moved) pc[k0] = (uint16_t)j;
+            }
+          }
           if (is_col) ser_col_rotate(col, C, W, i, j, pre);
           for (int n = lo + tid; n <= hi; n += C)
             sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
@@ -562,6 +579,12 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             const int ain = ser_in_window(a, i, j + 1, inc1, inc2), bin = ser_in_window(b, i, j + 1, inc1, inc2);
             ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
           }
+          if (kind == 3) { /* adjacent swap: at most one posting of the column changes, between i and i + 1 */
+            if (is_taxon && !pos_dirty) {
+              const int b0 = ser_col_bit(col, C, i), b1 = ser_col_bit(col, C, j);
+              if (b0 != b1) sm.pos[off_c + ser_rank1(col, pre, C, i)] = (uint16_t)(b0 ? j : i);
+            }
+          } else pos_dirty = true;
           if (is_col) ser_col_reverse(col, C, W, i, j, pre);
           for (int n = i + tid; 2 * n < i + j; n += C) { /* mirror the site order: disjoint pairs, no staging */
             const uint16_t t = sm.rpi[n];
@@ -595,6 +618,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             const int m2 = sm.perm16[n];
             if (m2 > n) { const uint16_t t = sm.rpi[n]; sm.rpi[n] = sm.rpi[m2]; sm.rpi[m2] = t; }
           }
+          pos_dirty = true;
           sc.counters[6]++;
         }
         /* accepted: fold the integer deltas into the totals (the reference recounts, mcmc.c:1303) */
