@@ -58,8 +58,8 @@ extern "C" {
 #define SER_STORE_FULL 2  /* + a, b, c, d, loglik of every thinned sample (chain_data.csv) */
 
 /* limits of this build (DESIGN.md "shapes") */
-#define SER_MAX_SITES 1024
-#define SER_MAX_TAXA 4096
+#define SER_MAX_SITES 2048
+#define SER_MAX_TAXA 8192
 
 typedef struct ser_dataset ser_dataset;
 typedef struct ser_run ser_run;

@@ -30,7 +30,7 @@
 #include <math.h>
 #endif
 
-#define SER_MAXW 32 /* words per column: N <= 1024 */
+#define SER_MAXW 64 /* words per column: N <= 2048 */
 
 /* Debug builds (NVCC_EXTRA=-DSER_DEBUG, see profiles/r02/README.md): every index into shared memory / a column that is
  * computed from chain state is range-checked; a violation prints its location and traps the kernel.  Compiled out otherwise. */

@@ -198,8 +198,11 @@ def test_error_paths(S):
     with pytest.raises(S.SeriationError) as e:
         short.state(0)                                      # tape exhausted mid-run
     assert "tape" in str(e.value)
+    with pytest.raises(S.SeriationError) as e:
+        S.Run(S.Dataset.from_bits(np.ones((4, 9000), np.uint8)), 1)  # unsupported shape says so
+    assert "M=9000" in str(e.value)
     with pytest.raises(S.SeriationError):
-        S.Run(S.Dataset.from_bits(np.ones((4, 5000), np.uint8)), 1)  # unsupported shape says so
+        S.Run(S.Dataset.from_bits(np.ones((2049, 3), np.uint8)), 1)
 
 
 def test_reference_file_writers(S, oracle_mod, tmp_path):
@@ -1097,3 +1100,22 @@ def test_manycd_wide_matrix_replay_and_free_running(S, oracle_mod):
             o.sample()
         _cmp_manycd(run, i, o.state(), ("free", i), True)
     run.close()
+
+
+# ----------------------------------------------------------------------------- round 2: shapes beyond 1024 sites / 4096 taxa
+@pytest.mark.parametrize("shape", [(1500, 60, 5, .05), (2048, 150, 12, .03), (2047, 33, 0, .1)])
+def test_more_than_1024_sites_replay(S, oracle_mod, shape):
+    """N up to 2048 (64 words per column) through the one-thread-per-column kernel"""
+    rng = np.random.default_rng(shape[0])
+    X, hard = random_dataset(rng, *shape)
+    _replay_case(S, oracle_mod, X, hard, [1, 2], 2, 2)
+
+
+def test_large_shapes_beyond_round1_limits(S, oracle_mod, monkeypatch):
+    """2048 sites x 1200 taxa and 48 sites x 8000 taxa through the large-shape kernel (scalar and per-taxon c, d)"""
+    rng = np.random.default_rng(5)
+    X, hard = random_dataset(rng, 2048, 1200, 9, .02)
+    _replay_case(S, oracle_mod, X, hard, [3], 1, 1)
+    X, hard = random_dataset(rng, 48, 8000, 4, .15)
+    _replay_case(S, oracle_mod, X, hard, [4], 2, 2)
+    _manycd_replay_case(S, oracle_mod, X, hard, [5], 1, 2)
