@@ -412,17 +412,25 @@ def stationary_regime(S, job, n_chains, local):
     """the reference's own schedule (mcmc.c:107,140-143,180-185) on one GPU: 1000 burn-in calls from the randomised
     start, then 1000 sampling calls with all 1000 thinned samples stored, then the cross-chain step over T = 1000"""
     import numpy as np
+    marks = []
+
+    def mark(what):
+        marks.append((what, time.perf_counter()))
     t0 = time.perf_counter()
     ds = S.Dataset.from_bits(job.X, job.hard)
     run = S.Run(ds, n_chains, mode=S.MODE_FREE, seed=20060206, store=S.STORE_PI, max_samples=1000, device=local)
+    mark("create")
     run.init().advance(1000, False).sync()
+    mark("burn-in")
     burn_ms, _ = run.sweep_time(reset=True)
     acc0 = np.sum([run.counters(i) for i in range(0, n_chains, max(1, n_chains // 64))], axis=0).astype(float)
     run.advance(1000, True).sync()
+    mark("sampling")
     samp_ms, _ = run.sweep_time(reset=True)
     acc1 = np.sum([run.counters(i) for i in range(0, n_chains, max(1, n_chains // 64))], axis=0).astype(float)
     run.elapsed_ms(reset=True)
     res = run.cross_chain(job.k)
+    mark("cross-chain")
     cc_ms = run.elapsed_ms(reset=True)
     d_ch = np.full(job.k, -1, np.int32); d_ch[:len(res["chosen"])] = res["chosen"]
     run.po_counts(d_ch)                                   # the pair-order kernel alone (+ its copies)
@@ -436,7 +444,12 @@ def stationary_regime(S, job, n_chains, local):
     po = S.po_finalize(res["counts"][:max(1, len(res["chosen"]))], job.k) if len(res["chosen"]) else None
     ok = run.check() == 0
     run.close()
+    mark("po probe + check + close")
     wall = time.perf_counter() - t0
+    prev = t0
+    for what, t in marks:
+        print("stationary regime: %-26s %8.1f ms" % (what, (t - prev) * 1e3), file=sys.stderr)
+        prev = t
     d = acc1 - acc0
     sw = max(d[7], 1.0)
     return {
