@@ -112,8 +112,9 @@ struct Smem {
   uint16_t *hp;     /* N+1: hard positions, ascending */
   double *wcol;     /* manycd only: 4*C per-column weights A, g, 1/g, 1/(1-e^-g) for the dense item phase */
   double *redd;     /* manycd only: 2*32 doubles of reduction scratch */
-  uint16_t *rpi, *tmp16, *perm16; /* N each */
+  uint16_t *rpi, *tmp16, *perm16; /* N each; tmp16 / perm16 (staging of an accepted move) share their bytes with ncache */
   uint16_t *pick16; /* C: the item the column's uniform fell into (Gibbs step) */
+  uint16_t *ncache; /* scalar c, d: Ival + 1 run lengths of the running group's items (0 = beyond the step's bound) */
   uint16_t *hrank, *nhpos; /* N+2 each: hard positions before p; position of the r-th non-hard site (SerHard's tables) */
 };
 
@@ -123,20 +124,23 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_ld = take(sizeof(double) * SER_PI_DRAWS);
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
-  size_t o_H = take(sizeof(double) * (N + 2));
+  size_t o_H = take(sizeof(double) * (N + 2 < SER_HCAP ? N + 2 : SER_HCAP));
+  /* the run-length cache of the Gibbs phase and the two staging arrays of an accepted site move are never live together */
+  const size_t nc_bytes = manycd ? 0 : sizeof(uint16_t) * ((Ival < 0 ? I : Ival) + 1), st_bytes = 2 * ((sizeof(uint16_t) * N + 15) & ~(size_t)15);
+  size_t o_nc = take(nc_bytes > st_bytes ? nc_bytes : st_bytes);
   size_t o_val = take(sizeof(double) * ((Ival < 0 ? I : Ival) + 1)), o_lm = take(sizeof(double) * C);
   size_t o_wc = take(manycd ? sizeof(double) * 4 * C : 0), o_rd = take(manycd ? sizeof(double) * 2 * SER_MAX_WARPS : 0);
   size_t o_pos = take(sizeof(uint16_t) * (I + 1)), o_st = take(sizeof(uint16_t) * 4 * C), o_on = take(sizeof(uint16_t) * C);
   size_t o_v = take(sizeof(uint32_t) * (size_t)W * C), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_h = take(sizeof(uint16_t) * (size_t)(W + 1) * C), o_hp = take(sizeof(uint16_t) * (N + 1));
-  size_t o_p = take(sizeof(uint16_t) * N), o_q = take(sizeof(uint16_t) * N), o_m = take(sizeof(uint16_t) * N);
+  size_t o_p = take(sizeof(uint16_t) * N), o_q = o_nc, o_m = o_nc + ((sizeof(uint16_t) * N + 15) & ~(size_t)15);
   size_t o_hr = take(sizeof(uint16_t) * (N + 2)), o_nh = take(sizeof(uint16_t) * (N + 2)), o_pk = take(sizeof(uint16_t) * C);
   if (s) {
     s->pick16 = (uint16_t *)(base + o_pk);
     s->hrank = (uint16_t *)(base + o_hr); s->nhpos = (uint16_t *)(base + o_nh);
     s->logdraw = (double *)(base + o_ld);
     s->draws_pi = (double *)(base + o_dp); s->draws_cd = (double *)(base + o_dc); s->terms = (double *)(base + o_t);
-    s->H = (double *)(base + o_H);
+    s->H = (double *)(base + o_H); s->ncache = (uint16_t *)(base + o_nc);
     s->val = (double *)(base + o_val); s->lmax = (double *)(base + o_lm);
     s->wcol = (double *)(base + o_wc); s->redd = (double *)(base + o_rd);
     s->pos = (uint16_t *)(base + o_pos); s->st4 = (uint16_t *)(base + o_st); s->ones16 = (uint16_t *)(base + o_on);

@@ -22,7 +22,7 @@ S.lib().ser_debug_phase_cycles(out)
 n = chains * 200
 tot = sum(out)
 print("%s: %d chains x 200 sweeps in %.1f ms = %.0f sweeps/s (instrumented build); %.0f cycles per sweep and CTA" % (name, chains, ms, n / (ms * 1e-3), tot / n))
-names = {8: "draws, c/d, H table", 9: "postings (expand_ones)", 10: "step geometry + maximum", 11: "dense item weights", 12: "scan + item of the uniform", 18: "pick inside the run (owner)",
+names = {8: "draws, c/d, H table", 9: "postings (expand_ones)", 10: "step geometry (owner)", 19: "maximum + cached log-weights", 11: "dense item weights", 12: "scan + item of the uniform", 18: "pick inside the run (owner)",
          13: "totals / loglik", 14: "pi1 proposals", 15: "pi2 proposals", 16: "pi3 proposals (+ sweep tail)", 17: "swap proposal"}
 print("  items evaluated per sweep %.0f, above the LOGEPSILON floor %.1f %%" % (out[20] / n, 100.0 * out[21] / max(1, out[20])))
 tot -= out[20] + out[21]
