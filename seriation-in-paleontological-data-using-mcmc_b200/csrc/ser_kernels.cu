@@ -507,38 +507,41 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
   }
   kp.n_chains = cfg->n_chains;
   if (!run->big) {
-    /* Units of the Gibbs phase: a column with many items is served by 2, 4 or 8 adjacent lanes.  Columns are sorted by
-     * occurrence count, so the lane counts are non-increasing along the table and every lane group is aligned inside
-     * its warp.  T = items per lane aimed at: the value that minimises the summed critical path of the rounds
-     * (a round = C units); SER_UNIT_ITEMS forces it. */
-    int bestT = 1 << 30;
-    long long best_cost = -1;
-    auto lsh_of = [](int items, int T) { int l = 0; while (l < 3 && ((items + (1 << l) - 1) >> l) > T) l++; return l; };
-    for (int T = 4; T <= 1024; T++) {
-      std::vector<int> chunk;
-      for (int c = 0; c < M; c++) {
-        const int items = ones[c] + 1, l = lsh_of(items, T);
-        for (int q = 0; q < (1 << l); q++) chunk.push_back((items + (1 << l) - 1) >> l);
-      }
-      long long cost = 0;
-      for (size_t u0 = 0; u0 < chunk.size(); u0 += run->C) {
-        int mx = 0;
-        for (size_t u = u0; u < std::min(chunk.size(), u0 + run->C); u++) mx = std::max(mx, chunk[u]);
-        cost += mx + 6; /* + the fixed cost of a round */
-      }
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; bestT = T; }
-      if (T >= ones[0] + 1) break; /* one lane per column from here on */
-    }
-    if (const char *v = getenv("SER_UNIT_ITEMS")) bestT = std::max(1, atoi(v));
+    /* Units of the Gibbs phase: a column with many items is served by 2, 4, .. 32 adjacent lanes.  Columns are sorted by
+     * occurrence count and every column group starts its own round at lane 0, so inside a group the lane counts are
+     * non-increasing and every lane group is aligned inside its warp.  T = items per lane aimed at, chosen per group:
+     * the value that minimises the summed critical path of the group's rounds (a round = C units) -- light groups
+     * take few items per lane and still fit one round; SER_UNIT_ITEMS forces it. */
+    auto lsh_of = [](int items, int T) { int l = 0; while (l < 5 && ((items + (1 << l) - 1) >> l) > T) l++; return l; };
+    int forceT = 0;
+    if (const char *v = getenv("SER_UNIT_ITEMS")) forceT = std::max(1, atoi(v));
     std::vector<uint2> units;
-    int g = 0;
     kp.grp_u[0] = 0;
-    for (int c = 0; c < M; c++) {
-      while (g < kp.n_groups && c == kp.grp_c[g + 1]) kp.grp_u[++g] = (int)units.size();
-      const int l = lsh_of(ones[c] + 1, bestT);
-      for (int q = 0; q < (1 << l); q++) units.push_back(make_uint2((uint32_t)c | ((uint32_t)q << 16) | ((uint32_t)l << 24), (uint32_t)off[c]));
+    for (int g = 0; g < kp.n_groups; g++) {
+      const int c0 = kp.grp_c[g], c1 = kp.grp_c[g + 1];
+      int bestT = 1 << 30;
+      long long best_cost = -1;
+      for (int T = 1; T <= 1024; T++) {
+        long long cost = 0;
+        int in_round = 0, mx = 0;
+        for (int c = c0; c < c1; c++) {
+          const int items = ones[c] + 1, l = lsh_of(items, T), chunk = (items + (1 << l) - 1) >> l;
+          for (int q = 0; q < (1 << l); q++) {
+            if (in_round == run->C) { cost += mx + 6; in_round = 0; mx = 0; } /* + the fixed cost of a round */
+            in_round++; mx = std::max(mx, chunk);
+          }
+        }
+        if (in_round) cost += mx + 6;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; bestT = T; }
+        if (c0 < c1 && T >= ones[c0] + 1) break; /* one lane per column from here on */
+      }
+      if (forceT) bestT = forceT;
+      for (int c = c0; c < c1; c++) {
+        const int l = lsh_of(ones[c] + 1, bestT);
+        for (int q = 0; q < (1 << l); q++) units.push_back(make_uint2((uint32_t)c | ((uint32_t)q << 16) | ((uint32_t)l << 24), (uint32_t)off[c]));
+      }
+      kp.grp_u[g + 1] = (int)units.size();
     }
-    while (g < kp.n_groups) kp.grp_u[++g] = (int)units.size();
     kp.n_units = (int)units.size();
     CUDA_TRY(POOL_ALLOC(&run->d_unit_tab, units.size() * sizeof(uint2)));
     CUDA_TRY(cudaMemcpyAsync(run->d_unit_tab, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice, run->stream));

@@ -90,6 +90,7 @@ __device__ __forceinline__ bool mh_decide(const KParams &p, const Smem &sm, cons
   return accept;
 }
 
+#define SER_UNIT_MAXL 32 /* most lanes that serve one column (a whole warp) */
 /* A unit of the Gibbs phase: `lpc` = 1 << lsh adjacent lanes serve column c, this lane is number `sub` of them;
  * off = first item of the column (KParams::unit_tab, built by ser_run_create) */
 struct Unit {
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
               }
             }
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
+            for (int o = 1; o < SER_UNIT_MAXL; o <<= 1) {
               const double t = __shfl_xor_sync(0xffffffffu, lm, o);
               if (o < un.lpc) lm = ser_fmax(lm, t);
             }
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
             if (un.live) for (int kk = k0; kk < k1; kk++) { tot = SER_ADD(tot, val[kk]); val[kk] = tot; }
             double incl = tot; /* inclusive scan of the chunk totals over the column's lanes */
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
+            for (int o = 1; o < SER_UNIT_MAXL; o <<= 1) {
               const double t = __shfl_up_sync(0xffffffffu, incl, o);
               if (o < un.lpc && un.sub >= o) incl = SER_ADD(incl, t);
             }
