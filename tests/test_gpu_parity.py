@@ -298,6 +298,18 @@ def test_big_path_replay_bit_exact(S, oracle_mod, monkeypatch, name, burn, samp,
     _replay_case(S, oracle_mod, X, hard, [5, 6, 7], burn, samp)
 
 
+@pytest.mark.parametrize("threads,kb", [("256", "40"), ("1024", "48"), ("320", "64")])
+def test_big_path_small_budget_replay_bit_exact(S, oracle_mod, monkeypatch, threads, kb):
+    """the large-shape Gibbs phase with a small shared-memory budget: several column groups per step even on the NOW subsets"""
+    monkeypatch.setenv("SER_FORCE_BIG", threads)
+    monkeypatch.setenv("SER_BIG_SMEM_KB", kb)
+    for name, burn, samp in (("g10s10", 6, 6), ("g2s2", 2, 2)):
+        X, hard = load_hex_dataset(name)
+        _replay_case(S, oracle_mod, X, hard, [5, 6, 7], burn, samp)
+    X, hard = load_hex_dataset("g5s5")
+    _manycd_replay_case(S, oracle_mod, X, hard, [3], 3, 3)
+
+
 @pytest.mark.parametrize("shape", EDGE_SHAPES[::2])
 def test_big_path_edge_shapes(S, oracle_mod, monkeypatch, shape):
     monkeypatch.setenv("SER_FORCE_BIG", "32")
