@@ -48,7 +48,7 @@ UNIT = "sweeps/s"
 # ser_sweep_kernel: dram__bytes_read.sum + dram__bytes_write.sum = 103.29 MB + 167.47 MB over the 8 192 work items of the profiled
 # launch (4 096 chains x 2 one-call items) = 33.05 KB per work item -- the chain state incl. its bit columns going through HBM at an
 # item boundary; the thinned samples add 2 N bytes each.  ser_sweep_kernel_big: 1.310 GB + 1.220 GB over 2 960 chain-sweeps.
-NCU_DRAM = {"g2s2": dict(per_item=(103.289856e6 + 167.473152e6) / 8192, src="profiles/r02/sweep_r02_ncu_raw_selected.txt"),
+NCU_DRAM = {"g2s2": dict(per_item=(102.342656e6 + 163.281920e6) / 8192, src="profiles/r02/sweep_r02_v3_ncu_raw_selected.txt"),
             "synthetic": dict(per_sweep=(1.310332e9 + 1.220131e9) / 2960, src="profiles/r02/sweep_big_r02_ncu_raw_selected.txt")}
 
 
