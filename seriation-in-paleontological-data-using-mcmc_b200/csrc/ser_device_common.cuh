@@ -114,7 +114,7 @@ struct Smem {
   double *redd;     /* manycd only: 2*32 doubles of reduction scratch */
   uint16_t *rpi, *tmp16, *perm16; /* N each; tmp16 / perm16 (staging of an accepted move) share their bytes with ncache */
   uint16_t *pick16; /* C: the item the column's uniform fell into (Gibbs step) */
-  uint16_t *ncache; /* scalar c, d: Ival + 1 run lengths of the running group's items (0 = beyond the step's bound) */
+  uint16_t *ncache; /* Ival + 1 run lengths of the running group's items (written by the maximum pass, read by the dense pass) */
   uint16_t *hrank, *nhpos; /* N+2 each: hard positions before p; position of the r-th non-hard site (SerHard's tables) */
 };
 
@@ -126,7 +126,7 @@ __host__ __device__ inline size_t smem_layout(Smem *s, unsigned char *base, int 
   size_t o_dp = take(sizeof(double) * SER_PI_DRAWS), o_dc = take(sizeof(double) * 8), o_t = take(sizeof(double) * C);
   size_t o_H = take(sizeof(double) * (N + 2 < SER_HCAP ? N + 2 : SER_HCAP));
   /* the run-length cache of the Gibbs phase and the two staging arrays of an accepted site move are never live together */
-  const size_t nc_bytes = manycd ? 0 : sizeof(uint16_t) * ((Ival < 0 ? I : Ival) + 1), st_bytes = 2 * ((sizeof(uint16_t) * N + 15) & ~(size_t)15);
+  const size_t nc_bytes = sizeof(uint16_t) * ((Ival < 0 ? I : Ival) + 1), st_bytes = 2 * ((sizeof(uint16_t) * N + 15) & ~(size_t)15);
   size_t o_nc = take(nc_bytes > st_bytes ? nc_bytes : st_bytes);
   size_t o_val = take(sizeof(double) * ((Ival < 0 ? I : Ival) + 1)), o_lm = take(sizeof(double) * C);
   size_t o_wc = take(manycd ? sizeof(double) * 4 * C : 0), o_rd = take(manycd ? sizeof(double) * 2 * SER_MAX_WARPS : 0);

@@ -379,9 +379,9 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
         for (int g = 0; g < p.n_groups; g++) { /* columns grp_c[g]..grp_c[g+1] = items grp_e[g]..grp_e[g+1] = units grp_u[g]..grp_u[g+1] */
           const int e0 = p.grp_e[g], e1 = p.grp_e[g + 1], ug1 = p.grp_u[g + 1];
           if (g) __syncthreads(); /* the previous group's scans are done with val */
-          /* maximum log-weight per column (the reference's z, mcmc.c:727-730).  With scalar c, d the lanes also leave
-           * every item's log-weight in val[] and its run length in ncache[], so that the dense pass below needs neither
-           * the step geometry nor the postings. */
+          /* maximum log-weight per column (the reference's z, mcmc.c:727-730).  The lanes also leave every item's
+           * log-weight in val[] and its run length in ncache[], so that the dense pass below needs neither the step
+           * geometry nor the postings. */
           for (int ub = p.grp_u[g]; ub < ug1; ub += C) {
             const Unit un = unit_load(p, ub + tid, ug1);
             double lm = -1.0e300;
@@ -389,22 +389,15 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
               const SerStep it = unit_step(sm, un.c, N, step);
               const uint16_t *pos = sm.pos + un.off;
               SerWeights w = wt;
-              if constexpr (MANY) {
-                w.A = sm.wcol[4 * un.c + 0]; w.g = sm.wcol[4 * un.c + 1];
-                for (int kk = un.sub; kk <= it.kb; kk += un.lpc) {
-                  int q, n;
-                  lm = ser_fmax(lm, ser_item_eval(w, it, pos, kk, &q, &n));
-                }
-              } else {
-                double *Lc = sm.val + (un.off - e0);
-                uint16_t *nc = sm.ncache + (un.off - e0);
-                SER_CHECK(un.off - e0 >= 0 && un.off - e0 + it.kb <= p.Ival);
-                for (int kk = un.sub; kk <= it.kb; kk += un.lpc) {
-                  int q, n;
-                  const double L = ser_item_eval(w, it, pos, kk, &q, &n);
-                  Lc[kk] = L; nc[kk] = (uint16_t)n;
-                  lm = ser_fmax(lm, L);
-                }
+              if constexpr (MANY) { w.A = sm.wcol[4 * un.c + 0]; w.g = sm.wcol[4 * un.c + 1]; }
+              double *Lc = sm.val + (un.off - e0);
+              uint16_t *nc = sm.ncache + (un.off - e0);
+              SER_CHECK(un.off - e0 >= 0 && un.off - e0 + it.kb <= p.Ival);
+              for (int kk = un.sub; kk <= it.kb; kk += un.lpc) {
+                int q, n;
+                const double L = ser_item_eval(w, it, pos, kk, &q, &n);
+                Lc[kk] = L; nc[kk] = (uint16_t)n;
+                lm = ser_fmax(lm, L);
               }
             }
 #pragma unroll
@@ -416,33 +409,23 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
           }
           __syncthreads();
           PHASE_MARK(19);
-          if constexpr (MANY) {
-            uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u; /* item -> column map, fetched one iteration ahead */
-            for (int e = e0 + tid; e < e1; e += C) {
-              const uint32_t ck = ck_next;
-              if (e + C < e1) ck_next = p.item_col[e + C];
-              const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
-              const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * c); /* cur, bound | ocur, kb */
-              SerStep it;
-              it.cur = (int)(g4.x & 0xffffu); it.bound = (int)(g4.x >> 16); it.ocur = (int)(g4.y & 0xffffu); it.kb = (int)(g4.y >> 16);
-              if (kk <= it.kb) { /* the column's own weights; geometric sums on the fly */
-                SER_CHECK(e - e0 >= 0 && e - e0 <= p.Ival && c < M && it.kb <= (int)sm.ones16[c] && it.bound <= N && it.cur <= it.bound);
-                it.nones = sm.ones16[c]; it.N = N; it.rev = step;
-                SerWeights w;
-                w.A = sm.wcol[4 * c + 0]; w.g = sm.wcol[4 * c + 1]; w.inv_g = sm.wcol[4 * c + 2]; w.hs = sm.wcol[4 * c + 3];
-                w.eps = p.eps; w.H = nullptr; w.hmax = N + 1;
-                sm.val[e - e0] = ser_item_weight<0>(w, it, sm.pos + (e - kk), kk, sm.lmax[c]);
-              }
-            }
-          } else {
+          {
             uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u; /* item -> column map, fetched one iteration ahead */
             for (int e = e0 + tid; e < e1; e += C) { /* log-weight -> run weight, in place */
               const uint32_t ck = ck_next;
               if (e + C < e1) ck_next = p.item_col[e + C];
               const int c = (int)(ck >> 16), kk = (int)(ck & 0xffffu);
               if (kk <= (int)sm.st4[4 * c + 3]) { /* inside the step's bound */
+                SER_CHECK(e - e0 >= 0 && e - e0 <= p.Ival && c < M);
                 int m; double ye;
-                sm.val[e - e0] = ser_run_sum<1>(wt, (int)sm.ncache[e - e0], SER_SUB(sm.val[e - e0], sm.lmax[c]), &m, &ye);
+                if constexpr (MANY) { /* the column's own weights; geometric sums on the fly */
+                  SerWeights w;
+                  w.g = sm.wcol[4 * c + 1]; w.inv_g = sm.wcol[4 * c + 2]; w.hs = sm.wcol[4 * c + 3];
+                  w.eps = p.eps; w.H = nullptr; w.hmax = N + 1;
+                  sm.val[e - e0] = ser_run_sum<0>(w, (int)sm.ncache[e - e0], SER_SUB(sm.val[e - e0], sm.lmax[c]), &m, &ye);
+                } else {
+                  sm.val[e - e0] = ser_run_sum<1>(wt, (int)sm.ncache[e - e0], SER_SUB(sm.val[e - e0], sm.lmax[c]), &m, &ye);
+                }
 #if defined(SER_PHASE_TIMING) && defined(SER_COUNT_ITEMS) /* how many items are evaluated / lie above the LOGEPSILON floor */
                 atomicAdd(&ser_phase_cycles[20], 1ull); if (m) atomicAdd(&ser_phase_cycles[21], 1ull);
 #endif

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             for (int ub = 0; ub < units; ub += C) { /* chunk sums, scan over the column's lanes, the item the uniform falls into */
               const int u = ub + tid;
               const bool live = u < units;
-              const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
+              const int cl = live ? (u >> lsh) : 0;
               const int kb = (int)sm.st4[4 * cl + 3];
               double *val = sm.val + sm.goff[cl];
               const int chunk = (kb + lpc) >> lsh, k0 = min(kb + 1, sub * chunk), k1 = min(kb + 1, k0 + chunk);
