@@ -468,24 +468,32 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
      * (SER_BIG_SMEM_KB, default 220), at most 1024 columns, never splitting a column */
     int budget_kb = 220;
     if (const char *v = getenv("SER_BIG_SMEM_KB")) budget_kb = std::max(16, std::min(224, atoi(v)));
-    const int gcap = std::min(M, 512); /* columns per group: sizes the per-column tables of a group */
-    const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap, cfg->manycd);
-    long long icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32; /* val 8 + pos 2 bytes per item */
-    icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);
-    if (icap < std::max(N + 1, M)) { /* one whole column, and the M per-taxon terms of the exact sums */
-      ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain before any item", fixed);
-      return SER_E_ARG;
-    }
+    /* gcap = columns per group (sizes the per-column tables of a group), icap = items per group (val 8 + pos 2 bytes each):
+     * start from 512 columns, build the groups, shrink gcap to what the widest group uses and give the bytes to icap */
+    int gcap = std::min((M + 31) / 32 * 32, 512);
+    long long icap = 0;
     std::vector<int> bgrp;
-    {
-      int c0 = 0;
-      while (c0 < M) {
+    for (int pass = 0; pass < 4; pass++) {
+      const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap, cfg->manycd);
+      icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32;
+      icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);
+      if (icap < std::max(N + 1, M)) { /* one whole column, and the M per-taxon terms of the exact sums */
+        ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain before any item", fixed);
+        return SER_E_ARG;
+      }
+      bgrp.clear();
+      int widest = 0;
+      for (int c0 = 0; c0 < M;) {
         int c1 = c0;
         while (c1 < M && c1 - c0 < gcap && off[c1 + 1] - off[c0] <= icap) c1++;
         bgrp.push_back(c0); bgrp.push_back(off[c0]);
+        widest = std::max(widest, c1 - c0);
         c0 = c1;
       }
       bgrp.push_back(M); bgrp.push_back(off[M]);
+      const int tight = std::min(gcap, (widest + widest / 8 + 31) / 32 * 32); /* head room: larger groups follow from the larger icap */
+      if (tight == gcap) break;
+      gcap = tight;
     }
     kp.big_ng = (int)bgrp.size() / 2 - 1; kp.big_icap = (int)icap; kp.big_gcap = gcap;
     CUDA_TRY(POOL_ALLOC(&run->d_bgrp, bgrp.size() * sizeof(int)));
