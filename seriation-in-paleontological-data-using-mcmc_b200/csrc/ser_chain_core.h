@@ -282,7 +282,7 @@ SER_HD double ser_H(const SerWeights &w, int m)
 }
 
 /* number of entries (-1) the per-sweep table H needs for a given g and N.  With the reference's prior bounds
- * (c <= log .1, d <= log .8: mcmc.h:17-20) g = log(1 - e^c) - d >= log .9 - log .8 = 0.1178, so the table never needs
+ * (c <= log .1, d <= log .8: mcmc.h:27-30) g = log(1 - e^c) - d >= log .9 - log .8 = 0.1178, so the table never needs
  * more than 277 entries; the small-shape kernel sizes its shared-memory copy with SER_HCAP. */
 #define SER_HCAP 288
 SER_HD int ser_hmax(double g, int N)
