@@ -88,7 +88,7 @@ struct KParams {
   const uint32_t *cl_item;  /* per rank, concatenated: item -> (local column << 16) | index inside the column */
   const int *cl_grp;        /* per rank, concatenated: column groups as {first local column, first item} pairs */
   int cl_item_base[9], cl_grp_base[9]; /* [rank] first entry of the rank's part (cl_grp_base in pairs) */
-  /* units of the Gibbs phase: heavy columns are served by 2 / 4 / 8 adjacent lanes (ser_sweep_kernel.cuh) */
+  /* units of the Gibbs phase: heavy columns are served by 2, 4, .. 32 adjacent lanes (ser_sweep_kernel.cuh) */
   const uint2 *unit_tab; /* [n_units] = {column | sub << 16 | lsh << 24, first item of the column} */
   int n_units;
   int grp_u[SER_MAX_GROUPS + 1]; /* units of column group g = [grp_u[g], grp_u[g+1]) */

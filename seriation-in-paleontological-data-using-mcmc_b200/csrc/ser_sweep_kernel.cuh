@@ -337,12 +337,12 @@ __global__ void __launch_bounds__(MAXT, MINB) ser_sweep_kernel(KParams p)
 
       /* ================= a/b Gibbs (mcmc_sampleab, mcmc.c:918-996) =================
        * item formulation (ser_chain_core.h): postings of the column, then for the a-step and
-       * the b-step: per-column maximum (own thread), item weights (dense over the CTA),
-       * per-column scan + inverse CDF (own thread). */
+       * the b-step, per column group: per-column maximum + cached log-weights (units), item weights
+       * (dense over the CTA), per-column scan + item search (units), pick inside the run (owner). */
       PHASE_MARK(8);
       /* The per-column loops of this phase -- postings, maximum, cumulative weights -- are served by UNITS: a column
-       * with many ones gets 2, 4 or 8 adjacent lanes (static table, built from the column's item count), so the
-       * longest serial loop of a pass is ~1/6 of the heaviest column (g2s2: 95 items -> 12-16 per lane).  With one
+       * with many ones gets 2, 4, .. 32 adjacent lanes (static table, built per column group from the columns' item
+       * counts), so the longest serial loop of a pass is a few items (g2s2: 95 items in the heaviest column).  With one
        * thread per column the warp that owns the 32 heaviest columns was the critical path of every pass while the
        * other nine waited at the barrier (30 % of the sweep's cycles). */
       /* The postings survive from sweep to sweep: an accepted adjacent swap or site move patches them in place (below);
