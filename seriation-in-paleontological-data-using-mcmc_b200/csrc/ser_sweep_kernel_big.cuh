@@ -10,14 +10,12 @@ struct BigSmem {
   double *draws_pi, *logdraw, *draws_cd, *H;
   double *lmax; /* gcap: per column of the running group */
   double *val;  /* icap: item weights / cumulative weights of the running group */
-  double *dsl;  /* gcap: per column of the running group: target minus the cumulative weight before the picked item */
   int *red;
   uint16_t *a16, *b16, *hp, *rpi, *tmp16, *perm16;
   uint16_t *st4; /* 4 * gcap */
   uint16_t *gones; /* gcap: ones of the running group's columns */
   int *goff;       /* gcap: first item of each column relative to the group's first item */
   uint16_t *pos; /* icap: postings of the running group's columns */
-  uint16_t *pick16;         /* gcap: the item the column's uniform fell into */
   double *uab;              /* 2 gcap: the two uniforms (a-step, b-step) of every column of the running group */
   double *wcol;             /* manycd: 4 gcap per-column weights A, g, 1/g, 1/(1-e^-g) of the running group */
   double *redd;             /* manycd: 2 x 32 doubles of reduction scratch */
@@ -30,17 +28,17 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
   size_t o_dp = take(8 * SER_PI_DRAWS), o_ld = take(8 * SER_PI_DRAWS), o_dc = take(8 * 8), o_H = take(8 * (size_t)(N + 2 < SER_HCAP ? N + 2 : SER_HCAP));
-  size_t o_go = take(4 * (size_t)gcap), o_gn = take(2 * (size_t)gcap), o_lm = take(8 * (size_t)gcap), o_in = take(8 * (size_t)gcap), o_val = take(8 * (size_t)icap), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
+  size_t o_go = take(4 * (size_t)gcap), o_gn = take(2 * (size_t)gcap), o_lm = take(8 * (size_t)gcap), o_val = take(8 * (size_t)icap), o_r = take(sizeof(int) * 2 * SER_MAX_WARPS * 4);
   size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)gcap), o_hp = take(2 * (size_t)(N + 1));
   size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
-  size_t o_pk = take(2 * (size_t)gcap), o_hc = take(4 * (size_t)(N / 32 + 1)), o_hq = take(2 * (size_t)(N / 32 + 2)), o_ua = take(16 * (size_t)gcap);
+  size_t o_hc = take(4 * (size_t)(N / 32 + 1)), o_hq = take(2 * (size_t)(N / 32 + 2)), o_ua = take(16 * (size_t)gcap);
   size_t o_wc = take(manycd ? 32 * (size_t)gcap : 0), o_rd = take(manycd ? 8 * 2 * SER_MAX_WARPS : 0);
   size_t o_hr = take(2 * (size_t)(N + 2)), o_nh = take(2 * (size_t)(N + 2));
   if (s) {
     s->uab = (double *)(base + o_ua); s->wcol = (double *)(base + o_wc); s->redd = (double *)(base + o_rd);
-    s->pick16 = (uint16_t *)(base + o_pk); s->hcol = (uint32_t *)(base + o_hc); s->hpre = (uint16_t *)(base + o_hq);
+    s->hcol = (uint32_t *)(base + o_hc); s->hpre = (uint16_t *)(base + o_hq);
     s->hrank = (uint16_t *)(base + o_hr); s->nhpos = (uint16_t *)(base + o_nh);
-    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos); s->dsl = (double *)(base + o_in);
+    s->val = (double *)(base + o_val); s->pos = (uint16_t *)(base + o_pos);
     s->goff = (int *)(base + o_go); s->gones = (uint16_t *)(base + o_gn);
     s->draws_pi = (double *)(base + o_dp); s->logdraw = (double *)(base + o_ld); s->draws_cd = (double *)(base + o_dc);
     s->H = (double *)(base + o_H); s->lmax = (double *)(base + o_lm); s->red = (int *)(base + o_r);
@@ -280,11 +278,12 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           const int units = nc << lsh, sub = tid & (lpc - 1);
           __syncthreads(); /* previous group is done with pos / val; first group: publishes H */
           PHASE_MARK(0);
-          { /* postings: a unit = (run of wq words, column), column fastest so that a warp reads 32
-             * consecutive columns of one word row; the prefix table gives the unit's first slot */
+          { /* postings: lane qq of a column's lpc lanes expands a run of wq words (a warp reads 32 / lpc consecutive
+             * columns of lpc word rows: whole 32-byte sectors); the prefix table gives the lane's first slot.  Columns
+             * map to lanes exactly as in the passes below, so what a column's lanes write here is read by the same warp. */
             const int wq = (W + lpc - 1) >> lsh;
             for (int u = tid; u < units; u += C) {
-              const int qq = u / nc, cl = u - qq * nc, c = c0 + cl, w0 = qq * wq, w1 = min(W, w0 + wq);
+              const int qq = u & (lpc - 1), cl = u >> lsh, c = c0 + cl, w0 = qq * wq, w1 = min(W, w0 + wq);
               /* every load of the unit is issued before the first one is needed */
               uint32_t vv[8];
 #pragma unroll
@@ -323,7 +322,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               sm.wcol[4 * cl + 0] = w.A; sm.wcol[4 * cl + 1] = w.g; sm.wcol[4 * cl + 2] = w.inv_g; sm.wcol[4 * cl + 3] = w.hs;
             }
           }
-          __syncthreads();
+          if constexpr (MANY) __syncthreads(); /* the columns' weights were staged by other threads */
+          else __syncwarp();                   /* postings and column table: written and read by the same warp */
           PHASE_MARK(1);
 #pragma unroll 1
           for (int step = 0; step < 2; step++) {
@@ -405,27 +405,24 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                   if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
                 }
                 SER_CHECK(lo <= kb && sm.goff[cl] + lo < p.big_icap);
-                sm.pick16[cl] = (uint16_t)lo;
-                sm.dsl[cl] = SER_SUB(target, lo > k0 ? SER_ADD(base, val[lo - 1]) : base);
+                /* ... and the same lane finishes the column: closed-form pick inside the item's run, new a or b */
+                const double rest = SER_SUB(target, lo > k0 ? SER_ADD(base, val[lo - 1]) : base);
+                const int c = c0 + cl;
+                const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
+                SerStep st;
+                st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = kb;
+                st.nones = sm.gones[cl]; st.N = N; st.rev = step;
+                int q, n;
+                SerWeights w = wt;
+                if constexpr (MANY) { w.A = sm.wcol[4 * cl + 0]; w.g = sm.wcol[4 * cl + 1]; w.inv_g = sm.wcol[4 * cl + 2]; w.hs = sm.wcol[4 * cl + 3]; }
+                const double le = SER_SUB(ser_item_eval(w, st, sm.pos + sm.goff[cl], lo, &q, &n), sm.lmax[cl]);
+                const int pick = q - n + 1 + ser_run_pick<MANY ? 0 : 1>(w, n, le, 0.0, rest);
+                if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
+                else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
               }
+              __syncwarp(); /* the column's lanes (one warp, the same ones in the next pass) see its new boundary */
             }
-            __syncthreads();
-            PHASE_MARK(7);
-            for (int cl = tid; cl < nc; cl += C) { /* closed-form pick inside the item's run */
-              const int c = c0 + cl;
-              const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
-              SerStep st;
-              st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = (int)(g4.y >> 16);
-              st.nones = sm.gones[cl]; st.N = N; st.rev = step;
-              int q, n;
-              SerWeights w = wt;
-              if constexpr (MANY) { w.A = sm.wcol[4 * cl + 0]; w.g = sm.wcol[4 * cl + 1]; w.inv_g = sm.wcol[4 * cl + 2]; w.hs = sm.wcol[4 * cl + 3]; }
-              const double le = SER_SUB(ser_item_eval(w, st, sm.pos + sm.goff[cl], (int)sm.pick16[cl], &q, &n), sm.lmax[cl]);
-              const int pick = q - n + 1 + ser_run_pick<MANY ? 0 : 1>(w, n, le, 0.0, sm.dsl[cl]);
-              if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
-              else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
-            }
-            __syncthreads(); /* the b-step's geometry is computed under a different column -> thread map */
+            /* no CTA barrier between the steps: the b-step's geometry + maximum pass maps columns to the same lanes */
             PHASE_MARK(4);
           }
         }
