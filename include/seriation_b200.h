@@ -115,6 +115,9 @@ int ser_run_sync(ser_run *run);
 /* CUDA-event time of all kernels launched by this run since creation / last reset, in ms */
 int ser_run_elapsed_ms(ser_run *run, double *ms, int32_t reset);
 int ser_run_kernel_launches(const ser_run *run, int64_t *n);
+/* which sweep kernel serves this run's shape: 0 = one thread per taxon (ser_sweep_kernel), 1 = large-shape kernel with
+ * CTA-wide column groups, 2 = large-shape kernel with warp batches, 3 = cluster kernel */
+int ser_run_kernel_path(const ser_run *run, int32_t *path);
 /* CUDA-event time of the SWEEP launches alone since the last reset, and how many there were.  The events are
  * recorded around every launch and only read here, so measuring the dominant kernel puts no host
  * synchronisation between the launches of a timed region. */

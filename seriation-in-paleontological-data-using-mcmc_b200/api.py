@@ -58,6 +58,7 @@ SYMBOLS = [
     ("ser_run_sync", C.c_int, [_vp]),
     ("ser_run_elapsed_ms", C.c_int, [_vp, _dp, C.c_int32]),
     ("ser_run_kernel_launches", C.c_int, [_vp, _i64p]),
+    ("ser_run_kernel_path", C.c_int, [_vp, _i32p]),
     ("ser_run_get_state", C.c_int, [_vp, C.c_int32] + [_i32p] * 9 + [_dp, _i64p]),
     ("ser_run_get_counters", C.c_int, [_vp, C.c_int32, _i64p]),
     ("ser_run_check", C.c_int, [_vp, _i32p]),
@@ -251,6 +252,13 @@ class Run:
     def kernel_launches(self) -> int:
         n = C.c_int64()
         _check(lib().ser_run_kernel_launches(self._h, C.byref(n)))
+        return n.value
+
+    def kernel_path(self) -> int:
+        """0 = one thread per taxon, 1 = large-shape kernel (CTA-wide column groups), 2 = large-shape kernel (warp batches),
+        3 = cluster kernel"""
+        n = C.c_int32()
+        _check(lib().ser_run_kernel_path(self._h, C.byref(n)))
         return n.value
 
     def state(self, chain: int) -> dict:

@@ -52,6 +52,9 @@ struct KParams {
   uint16_t *gpre;           /* [slot][W+1][Cs] */
   const int *bgrp;          /* large-shape column groups: [g] = {first column, first item}, big_ng + 1 entries */
   int big_ng, big_icap, big_gcap;
+  /* warp-batch Gibbs phase (ser_sweep_kernel_big<.., WB = true>): a batch = consecutive columns one warp serves on its own */
+  const int4 *bbat;         /* [big_nb] = {first column, columns | lane shift << 16, first item, last item + 1} */
+  int big_nb, big_wcap;     /* batches; items per warp slice of the item buffers */
   int n_chains;
   uint16_t *ab;        /* [chain][2][Mpad] */
   uint16_t *rpi;       /* [chain][Npad] */

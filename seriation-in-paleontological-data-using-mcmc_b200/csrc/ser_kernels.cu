@@ -80,6 +80,8 @@ struct ser_run {
   uint32_t *d_gV;
   uint16_t *d_gpre;
   int *d_bgrp;
+  int4 *d_bbat;
+  int big_warp; /* the Gibbs phase of the large-shape kernel runs warp batches (else CTA-wide column groups) */
   /* cluster path of the large shapes */
   int cl_mode, cl_R, cl_clusters;
   size_t smem_cl;
@@ -182,8 +184,10 @@ static cudaError_t allow_max_dynamic_smem(void)
   allow((const void *)ser_sweep_kernel<384, 2, false>);
   allow((const void *)ser_sweep_kernel<1024, 1, true>);
   allow((const void *)ser_sweep_kernel<384, 2, true>);
-  allow((const void *)ser_sweep_kernel_big<false>);
-  allow((const void *)ser_sweep_kernel_big<true>);
+  allow((const void *)ser_sweep_kernel_big<false, false>);
+  allow((const void *)ser_sweep_kernel_big<true, false>);
+  allow((const void *)ser_sweep_kernel_big<false, true>);
+  allow((const void *)ser_sweep_kernel_big<true, true>);
   allow((const void *)ser_sweep_kernel_cl);
   if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
   return e;
@@ -495,6 +499,47 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
       if (tight == gcap) break;
       gcap = tight;
     }
+    /* Warp batches (default whenever every column's items fit a warp's slice of the item buffers; SER_BIG_WARP=0 keeps the
+     * CTA-wide groups): the per-column tables hold 32 columns per warp, the item buffers are cut into one slice per warp.
+     * A batch = consecutive columns whose items fit the slice, at most 32; a column gets 32 / columns lanes (a power of two).
+     * When the columns that fit would leave more than 4 lanes idle, the batch shrinks to a power of two of columns. */
+    run->big_warp = 0;
+    std::vector<int4> bbat;
+    {
+      const char *bw = getenv("SER_BIG_WARP");
+      const int nwarps = run->big_threads / 32, wgcap = 32 * nwarps;
+      const size_t wfixed = big_layout(nullptr, nullptr, N, M, 0, wgcap, cfg->manycd);
+      int widest_col = 0;
+      for (int c = 0; c < M; c++) widest_col = std::max(widest_col, off[c + 1] - off[c]);
+      long long wcap = ((long long)budget_kb * 1024 - (long long)wfixed - 64) / 10 / nwarps / 8 * 8;
+      wcap = std::min<long long>(wcap, (long long)(kp.I + 7) / 8 * 8);
+      /* val also holds the M per-taxon terms of the exact sums */
+      const long long wicap = std::max<long long>(wcap * nwarps, (std::max(N + 1, M) + 31) / 32 * 32);
+      if (!(bw && atoi(bw) == 0) && wcap >= widest_col &&
+          big_layout(nullptr, nullptr, N, M, (int)wicap, wgcap, cfg->manycd) <= (size_t)budget_kb * 1024) {
+        for (int c0 = 0; c0 < M;) {
+          int c1 = c0;
+          while (c1 < M && c1 - c0 < 32 && off[c1 + 1] - off[c0] <= wcap) c1++;
+          int nc = c1 - c0, lsh = 0;
+          while ((nc << (lsh + 1)) <= 32) lsh++;
+          if ((nc << lsh) < 28) { /* a power of two of columns keeps all 32 lanes busy */
+            int p2 = 1;
+            while (p2 * 2 <= nc) p2 *= 2;
+            if (c0 + p2 < M) { nc = p2; lsh = 0; while ((nc << (lsh + 1)) <= 32) lsh++; }
+          }
+          c1 = c0 + nc;
+          bbat.push_back(make_int4(c0, nc | (lsh << 16), off[c0], off[c1]));
+          c0 = c1;
+        }
+        run->big_warp = 1;
+        gcap = wgcap;
+        icap = wicap;
+        kp.big_wcap = (int)wcap; kp.big_nb = (int)bbat.size();
+        CUDA_TRY(POOL_ALLOC(&run->d_bbat, bbat.size() * sizeof(int4)));
+        CUDA_TRY(cudaMemcpyAsync(run->d_bbat, bbat.data(), bbat.size() * sizeof(int4), cudaMemcpyHostToDevice, run->stream));
+        kp.bbat = run->d_bbat;
+      }
+    }
     kp.big_ng = (int)bgrp.size() / 2 - 1; kp.big_icap = (int)icap; kp.big_gcap = gcap;
     CUDA_TRY(POOL_ALLOC(&run->d_bgrp, bgrp.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpyAsync(run->d_bgrp, bgrp.data(), bgrp.size() * sizeof(int), cudaMemcpyHostToDevice, run->stream));
@@ -503,8 +548,8 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     run->smem_big = big_layout(nullptr, nullptr, N, M, (int)icap, gcap, cfg->manycd);
     if (run->smem_big > SER_SMEM_DYN_MAX) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_big); return SER_E_ARG; }
     int per_sm = 1, n_sm = 1;
-    if (cfg->manycd) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big<true>, run->big_threads, run->smem_big));
-    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big<false>, run->big_threads, run->smem_big));
+    if (cfg->manycd) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big<true, false>, run->big_threads, run->smem_big));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big<false, false>, run->big_threads, run->smem_big));
     CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     run->big_slots = std::max(1, std::min(cfg->n_chains, per_sm * n_sm));
     kp.Cs = ((M + 1) + 31) / 32 * 32;
@@ -617,7 +662,7 @@ extern "C" void ser_run_destroy(ser_run *run)
   cudaSetDevice(run->cfg.device);
   void *bufs[] = {run->d_Xs, run->d_hard, run->d_ones, run->d_off, run->d_order, run->d_item_col, run->d_ab, run->d_rpi,
                   run->d_scal, run->d_tape, run->d_tape_off, run->d_samp_a, run->d_samp_b, run->d_samp_pi, run->d_samp_cdl,
-                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp,
+                  run->d_scratch_i, run->d_bad, run->d_cd4, run->d_samp_cd_all, run->d_gV, run->d_gpre, run->d_bgrp, run->d_bbat,
                   run->d_V, run->d_queue, run->d_done, run->d_e_all, run->d_info, run->d_chosen, run->d_counts, run->d_unit_tab, run->d_hbits, run->d_col_sites, run->d_cl_off, run->d_cl_item, run->d_cl_grp};
   for (void *b : bufs) if (b) cudaFreeAsync(b, run->stream);
   if (run->stream) cudaStreamSynchronize(run->stream);
@@ -723,8 +768,13 @@ extern "C" int ser_run_advance_both(ser_run *run, int32_t burn_calls, int32_t sa
   }
   if (run->big) {
     if (rec) CUDA_TRY(cudaEventRecord(ev0, run->stream));
-    if (run->cfg.manycd) ser_sweep_kernel_big<true><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
-    else ser_sweep_kernel_big<false><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+    if (run->big_warp) {
+      if (run->cfg.manycd) ser_sweep_kernel_big<true, true><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+      else ser_sweep_kernel_big<false, true><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+    } else {
+      if (run->cfg.manycd) ser_sweep_kernel_big<true, false><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+      else ser_sweep_kernel_big<false, false><<<run->big_slots, run->big_threads, run->smem_big, run->stream>>>(kp);
+    }
     CUDA_TRY(cudaGetLastError());
     if (rec) CUDA_TRY(cudaEventRecord(ev1, run->stream));
     return SER_OK;
@@ -801,6 +851,13 @@ extern "C" int ser_run_kernel_launches(const ser_run *run, int64_t *n)
 {
   if (!run || !n) return SER_E_ARG;
   *n = run->launches;
+  return SER_OK;
+}
+
+extern "C" int ser_run_kernel_path(const ser_run *run, int32_t *path)
+{
+  if (!run || !path) return SER_E_ARG;
+  *path = !run->big ? 0 : run->cl_mode ? 3 : run->big_warp ? 2 : 1;
   return SER_OK;
 }
 

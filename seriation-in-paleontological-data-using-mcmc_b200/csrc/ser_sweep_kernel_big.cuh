@@ -22,6 +22,12 @@ struct BigSmem {
   uint32_t *hcol;           /* W: the hard-site mask in position order (stride 1; never leaves shared memory) */
   uint16_t *hpre;           /* W+1: its prefix table */
   uint16_t *hrank, *nhpos;  /* N+2 each: SerHard's tables */
+  int *bctr;                /* next column batch of the running sweep (warp-batch Gibbs phase) */
+};
+/* what one team of the Gibbs phase works in: the whole group-local arrays (team = CTA) or a warp's slices of them */
+struct BigTeam {
+  uint16_t *pos; double *val; int cap;
+  int *goff; uint16_t *gones; double *lmax; uint16_t *st4; double *uab; double *wcol;
 };
 __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap, int manycd = 0)
 {
@@ -33,8 +39,9 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
   size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
   size_t o_hc = take(4 * (size_t)(N / 32 + 1)), o_hq = take(2 * (size_t)(N / 32 + 2)), o_ua = take(16 * (size_t)gcap);
   size_t o_wc = take(manycd ? 32 * (size_t)gcap : 0), o_rd = take(manycd ? 8 * 2 * SER_MAX_WARPS : 0);
-  size_t o_hr = take(2 * (size_t)(N + 2)), o_nh = take(2 * (size_t)(N + 2));
+  size_t o_hr = take(2 * (size_t)(N + 2)), o_nh = take(2 * (size_t)(N + 2)), o_bc = take(16);
   if (s) {
+    s->bctr = (int *)(base + o_bc);
     s->uab = (double *)(base + o_ua); s->wcol = (double *)(base + o_wc); s->redd = (double *)(base + o_rd);
     s->hcol = (uint32_t *)(base + o_hc); s->hpre = (uint16_t *)(base + o_hq);
     s->hrank = (uint16_t *)(base + o_hr); s->nhpos = (uint16_t *)(base + o_nh);
@@ -119,7 +126,7 @@ __device__ __forceinline__ void big_rebuild_hard(const BigSmem &sm, int N)
 /* MANY = per-taxon c, d (manycd = 1, mcmc.c:777-785, :807-815): the chain's cd4 rows in HBM hold every column's c, log(1-e^c),
  * d, log(1-e^d); the weights of a group's columns are staged in shared memory, geometric run sums are evaluated on the fly,
  * delta / loglik are float sums over taxa (mh_decide_big). */
-template <bool MANY>
+template <bool MANY, bool WB>
 __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,6 +136,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
   uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
   uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
   double *TERMS = sm.val; /* per-taxon terms of the exact sums: the item-weight buffer is idle outside the Gibbs phase (icap >= M) */
+  if (WB && tid == 0) *sm.bctr = 0;
 
   for (int chain = blockIdx.x; chain < p.n_chains; chain += gridDim.x) {
     const unsigned int gchain = (unsigned int)(p.chain_offset + chain);
@@ -270,27 +278,31 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
          * shuffle scan of the lane totals.  Per group: postings; then for the a-step and the b-step:
          * geometry + maximum, run weights (dense over the group's items), scan + inverse CDF. */
         int changed = 0;
-#pragma unroll 1
-        for (int g = 0; g < p.big_ng; g++) {
-          const int c0 = p.bgrp[2 * g], e0 = p.bgrp[2 * g + 1], c1 = p.bgrp[2 * g + 2], e1 = p.bgrp[2 * g + 3], nc = c1 - c0;
-          int lpc = 1, lsh = 0;
-          while (lpc < 8 && nc * lpc * 2 <= C) { lpc <<= 1; lsh++; }
-          const int units = nc << lsh, sub = tid & (lpc - 1);
-          __syncthreads(); /* previous group is done with pos / val; first group: publishes H */
+        /* One team = the threads that share a set of columns: the whole CTA (a column group, CTA barriers between the
+         * passes) or ONE WARP (a column batch, __syncwarp only: the warps of the CTA drift through their batches
+         * independently, so one warp's dependent chains and pass boundaries are the other warps' issue slots).
+         * t / T = thread index / size of the team; TM = the team's slices of the group-local arrays. */
+        auto gibbs_team = [&](auto warp_tag, const BigTeam &TM, const int t, const int T, const int c0, const int e0, const int c1,
+                              const int e1, const int lsh) {
+          constexpr bool WARP = decltype(warp_tag)::value;
+          auto team_sync = [&]() { if constexpr (WARP) __syncwarp(); else __syncthreads(); };
+          const int nc = c1 - c0, lpc = 1 << lsh;
+          const int units = nc << lsh, sub = t & (lpc - 1);
+          team_sync(); /* the team's previous columns are done with pos / val; first group: publishes H */
           PHASE_MARK(0);
           { /* postings: lane qq of a column's lpc lanes expands a run of wq words (a warp reads 32 / lpc consecutive
              * columns of lpc word rows: whole 32-byte sectors); the prefix table gives the lane's first slot.  Columns
              * map to lanes exactly as in the passes below, so what a column's lanes write here is read by the same warp. */
             const int wq = (W + lpc - 1) >> lsh;
-            for (int u = tid; u < units; u += C) {
+            for (int u = t; u < units; u += T) {
               const int qq = u & (lpc - 1), cl = u >> lsh, c = c0 + cl, w0 = qq * wq, w1 = min(W, w0 + wq);
               /* every load of the unit is issued before the first one is needed */
               uint32_t vv[8];
 #pragma unroll
               for (int k = 0; k < 8; k++) vv[k] = w0 + k < w1 ? V[(w0 + k) * Cs + c] : 0u;
               const int first = w0 < w1 ? (int)PRE[w0 * Cs + c] : 0, off_c = p.off[c] - e0;
-              if (qq == 0) { sm.goff[cl] = off_c; sm.gones[cl] = (uint16_t)p.ones[c]; } /* the group's column table */
-              uint16_t *out = sm.pos + off_c + first;
+              if (qq == 0) { TM.goff[cl] = off_c; TM.gones[cl] = (uint16_t)p.ones[c]; } /* the team's column table */
+              uint16_t *out = TM.pos + off_c + first;
               for (int wb = w0; wb < w1; wb += 8) {
                 if (wb > w0) {
 #pragma unroll
@@ -304,41 +316,41 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               }
             }
           }
-          for (int cl = tid; cl < nc; cl += C) { /* the two uniforms of every column of the group (mcmc.c:951, :963 -> :909) */
+          for (int cl = t; cl < nc; cl += T) { /* the two uniforms of every column of the team (mcmc.c:951, :963 -> :909) */
             const int taxon = p.order[c0 + cl];
             if (p.mode == SER_MODE_REPLAY) {
               const long long u0 = sc.cursor + (MANY ? 6 * (long long)M : 6) + 2 * taxon;
-              sm.uab[2 * cl] = tape[u0]; sm.uab[2 * cl + 1] = tape[u0 + 1];
+              TM.uab[2 * cl] = tape[u0]; TM.uab[2 * cl + 1] = tape[u0 + 1];
             }
             else {
               uint32_t o[4];
               ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
-              sm.uab[2 * cl] = ser_u53(o[0], o[1]); sm.uab[2 * cl + 1] = ser_u53(o[2], o[3]);
+              TM.uab[2 * cl] = ser_u53(o[0], o[1]); TM.uab[2 * cl + 1] = ser_u53(o[2], o[3]);
             }
             if constexpr (MANY) { /* the column's own weights for the passes of this group */
               SerWeights w;
               big_col_weights(cd4, p.Mpad, c0 + cl, &w);
               ser_set_weights_own(&w, w.c, w.cc, w.d, w.dd, N);
-              sm.wcol[4 * cl + 0] = w.A; sm.wcol[4 * cl + 1] = w.g; sm.wcol[4 * cl + 2] = w.inv_g; sm.wcol[4 * cl + 3] = w.hs;
+              TM.wcol[4 * cl + 0] = w.A; TM.wcol[4 * cl + 1] = w.g; TM.wcol[4 * cl + 2] = w.inv_g; TM.wcol[4 * cl + 3] = w.hs;
             }
           }
-          if constexpr (MANY) __syncthreads(); /* the columns' weights were staged by other threads */
-          else __syncwarp();                   /* postings and column table: written and read by the same warp */
+          if constexpr (MANY && !WARP) __syncthreads(); /* the columns' weights were staged by other threads */
+          else __syncwarp();                            /* postings and column table: written and read by the same warp */
           PHASE_MARK(1);
 #pragma unroll 1
           for (int step = 0; step < 2; step++) {
-            for (int ub = 0; ub < units; ub += C) { /* warp-uniform trip count: the shuffles need every lane */
-              const int u = ub + tid;
+            for (int ub = 0; ub < units; ub += T) { /* warp-uniform trip count: the shuffles need every lane */
+              const int u = ub + t;
               const bool live = u < units;
               const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
               const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
                                            : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
-              const uint16_t *pos = sm.pos + sm.goff[cl];
+              const uint16_t *pos = TM.pos + TM.goff[cl];
               double lm = -1.0e300;
               if (live) { /* every item's log-weight stays in val for the dense pass */
-                double *Lc = sm.val + sm.goff[cl];
+                double *Lc = TM.val + TM.goff[cl];
                 SerWeights w = wt;
-                if constexpr (MANY) { w.A = sm.wcol[4 * cl + 0]; w.g = sm.wcol[4 * cl + 1]; }
+                if constexpr (MANY) { w.A = TM.wcol[4 * cl + 0]; w.g = TM.wcol[4 * cl + 1]; }
                 for (int kk = sub; kk <= st.kb; kk += lpc) {
                   int q, n;
                   const double L = ser_item_eval(w, st, pos, kk, &q, &n);
@@ -348,55 +360,55 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               }
               for (int o = lpc >> 1; o > 0; o >>= 1) lm = ser_fmax(lm, __shfl_xor_sync(0xffffffffu, lm, o));
               if (live && sub == 0) {
-                sm.lmax[cl] = lm;
-                *reinterpret_cast<uint2 *>(sm.st4 + 4 * cl) =
+                TM.lmax[cl] = lm;
+                *reinterpret_cast<uint2 *>(TM.st4 + 4 * cl) =
                     make_uint2((uint32_t)st.cur | ((uint32_t)st.bound << 16), (uint32_t)st.ocur | ((uint32_t)st.kb << 16));
               }
             }
-            __syncthreads();
+            team_sync();
             PHASE_MARK(2);
-            uint32_t ck_next = e0 + tid < e1 ? p.item_col[e0 + tid] : 0u; /* fetched one iteration ahead */
-            for (int e = e0 + tid; e < e1; e += C) {
+            uint32_t ck_next = e0 + t < e1 ? p.item_col[e0 + t] : 0u; /* fetched one iteration ahead */
+            for (int e = e0 + t; e < e1; e += T) {
               const uint32_t ck = ck_next;
-              if (e + C < e1) ck_next = p.item_col[e + C];
+              if (e + T < e1) ck_next = p.item_col[e + T];
               const int cl = (int)(ck >> 16) - c0, kk = (int)(ck & 0xffffu);
-              const int kb = (int)sm.st4[4 * cl + 3];
+              const int kb = (int)TM.st4[4 * cl + 3];
               if (kk <= kb) { /* log-weight -> run weight, in place; the run length from the postings */
-                SER_CHECK(cl >= 0 && cl < nc && e - e0 < p.big_icap && e - kk - e0 >= 0);
-                const uint16_t *pos = sm.pos + (e - kk - e0);
-                const int nones = (int)sm.gones[cl], bound = (int)sm.st4[4 * cl + 1];
+                SER_CHECK(cl >= 0 && cl < nc && e - e0 < TM.cap && e - kk - e0 >= 0);
+                const uint16_t *pos = TM.pos + (e - kk - e0);
+                const int nones = (int)TM.gones[cl], bound = (int)TM.st4[4 * cl + 1];
                 int q, qprev; /* ser_item_eval's q and qprev */
                 if (step) { q = kk < kb ? N - 1 - (int)pos[nones - 1 - kk] : bound; qprev = kk > 0 ? N - 1 - (int)pos[nones - kk] : -1; }
                 else { q = kk < kb ? (int)pos[kk] : bound; qprev = kk > 0 ? (int)pos[kk - 1] : -1; }
                 if constexpr (MANY) {
                   SerWeights w = wt;
-                  w.g = sm.wcol[4 * cl + 1]; w.inv_g = sm.wcol[4 * cl + 2]; w.hs = sm.wcol[4 * cl + 3];
-                  sm.val[e - e0] = ser_item_weight_cached<0>(w, sm.val[e - e0], q - qprev, sm.lmax[cl]);
+                  w.g = TM.wcol[4 * cl + 1]; w.inv_g = TM.wcol[4 * cl + 2]; w.hs = TM.wcol[4 * cl + 3];
+                  TM.val[e - e0] = ser_item_weight_cached<0>(w, TM.val[e - e0], q - qprev, TM.lmax[cl]);
                 } else {
-                  sm.val[e - e0] = ser_item_weight_cached<1>(wt, sm.val[e - e0], q - qprev, sm.lmax[cl]);
+                  TM.val[e - e0] = ser_item_weight_cached<1>(wt, TM.val[e - e0], q - qprev, TM.lmax[cl]);
                 }
               }
             }
-            __syncthreads();
+            team_sync();
             PHASE_MARK(3);
-            for (int ub = 0; ub < units; ub += C) { /* chunk sums, scan over the column's lanes, the item the uniform falls into */
-              const int u = ub + tid;
+            for (int ub = 0; ub < units; ub += T) { /* chunk sums, scan over the column's lanes, the item the uniform falls into */
+              const int u = ub + t;
               const bool live = u < units;
               const int cl = live ? (u >> lsh) : 0;
-              const int kb = (int)sm.st4[4 * cl + 3];
-              double *val = sm.val + sm.goff[cl];
+              const int kb = (int)TM.st4[4 * cl + 3];
+              double *val = TM.val + TM.goff[cl];
               const int chunk = (kb + lpc) >> lsh, k0 = min(kb + 1, sub * chunk), k1 = min(kb + 1, k0 + chunk);
               double tot = 0.0;
               if (live) for (int kk = k0; kk < k1; kk++) { tot = SER_ADD(tot, val[kk]); val[kk] = tot; }
               double incl = tot; /* inclusive scan of the chunk totals over the column's lanes */
               for (int o = 1; o < lpc; o <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (sub >= o) incl = SER_ADD(incl, t);
+                const double tt = __shfl_up_sync(0xffffffffu, incl, o);
+                if (sub >= o) incl = SER_ADD(incl, tt);
               }
-              const int lane = tid & 31;
+              const int lane = t & 31;
               const double total = __shfl_sync(0xffffffffu, incl, lane | (lpc - 1));
               const double before = __shfl_up_sync(0xffffffffu, incl, 1);
-              const double u01 = live ? sm.uab[2 * cl + step] : 0.0;
+              const double u01 = live ? TM.uab[2 * cl + step] : 0.0;
               const double base = sub ? before : 0.0, target = SER_MUL(u01, total);
               if (live && k0 < k1 && incl >= target && (sub == 0 || base < target)) { /* the first chunk that reaches the target */
                 int lo = k0, hi = k1 - 1;
@@ -404,29 +416,58 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                   const int mid = (lo + hi) >> 1;
                   if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
                 }
-                SER_CHECK(lo <= kb && sm.goff[cl] + lo < p.big_icap);
+                SER_CHECK(lo <= kb && TM.goff[cl] + lo < TM.cap);
                 /* ... and the same lane finishes the column: closed-form pick inside the item's run, new a or b */
                 const double rest = SER_SUB(target, lo > k0 ? SER_ADD(base, val[lo - 1]) : base);
                 const int c = c0 + cl;
-                const uint2 g4 = *reinterpret_cast<const uint2 *>(sm.st4 + 4 * cl);
+                const uint2 g4 = *reinterpret_cast<const uint2 *>(TM.st4 + 4 * cl);
                 SerStep st;
                 st.cur = (int)(g4.x & 0xffffu); st.bound = (int)(g4.x >> 16); st.ocur = (int)(g4.y & 0xffffu); st.kb = kb;
-                st.nones = sm.gones[cl]; st.N = N; st.rev = step;
+                st.nones = TM.gones[cl]; st.N = N; st.rev = step;
                 int q, n;
                 SerWeights w = wt;
-                if constexpr (MANY) { w.A = sm.wcol[4 * cl + 0]; w.g = sm.wcol[4 * cl + 1]; w.inv_g = sm.wcol[4 * cl + 2]; w.hs = sm.wcol[4 * cl + 3]; }
-                const double le = SER_SUB(ser_item_eval(w, st, sm.pos + sm.goff[cl], lo, &q, &n), sm.lmax[cl]);
+                if constexpr (MANY) { w.A = TM.wcol[4 * cl + 0]; w.g = TM.wcol[4 * cl + 1]; w.inv_g = TM.wcol[4 * cl + 2]; w.hs = TM.wcol[4 * cl + 3]; }
+                const double le = SER_SUB(ser_item_eval(w, st, TM.pos + TM.goff[cl], lo, &q, &n), TM.lmax[cl]);
                 const int pick = q - n + 1 + ser_run_pick<MANY ? 0 : 1>(w, n, le, 0.0, rest);
                 if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
                 else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
               }
               __syncwarp(); /* the column's lanes (one warp, the same ones in the next pass) see its new boundary */
             }
-            /* no CTA barrier between the steps: the b-step's geometry + maximum pass maps columns to the same lanes */
+            /* no team barrier between the steps: the b-step's geometry + maximum pass maps columns to the same lanes */
             PHASE_MARK(4);
+          }
+        };
+        if constexpr (WB) {
+          /* column batches, one warp each, claimed from a shared-memory counter (largest batches first) */
+          const int warp = tid >> 5, lane = tid & 31, wcap = p.big_wcap;
+          BigTeam TM;
+          TM.pos = sm.pos + (size_t)warp * wcap; TM.val = sm.val + (size_t)warp * wcap; TM.cap = wcap;
+          TM.goff = sm.goff + 32 * warp; TM.gones = sm.gones + 32 * warp; TM.lmax = sm.lmax + 32 * warp;
+          TM.st4 = sm.st4 + 128 * warp; TM.uab = sm.uab + 64 * warp; TM.wcol = sm.wcol + (MANY ? 128 * warp : 0);
+          __syncthreads(); /* publishes H and this sweep's weights; the batch counter is zero (reset behind the last barrier) */
+          for (;;) {
+            int bt = 0;
+            if (lane == 0) bt = atomicAdd(sm.bctr, 1);
+            bt = __shfl_sync(0xffffffffu, bt, 0);
+            if (bt >= p.big_nb) break;
+            const int4 bd = __ldg(p.bbat + bt);
+            gibbs_team(std::true_type{}, TM, lane, 32, bd.x, bd.z, bd.x + (bd.y & 0xffff), bd.w, bd.y >> 16);
+          }
+        } else {
+          BigTeam TM;
+          TM.pos = sm.pos; TM.val = sm.val; TM.cap = p.big_icap; TM.goff = sm.goff; TM.gones = sm.gones; TM.lmax = sm.lmax;
+          TM.st4 = sm.st4; TM.uab = sm.uab; TM.wcol = sm.wcol;
+#pragma unroll 1
+          for (int g = 0; g < p.big_ng; g++) {
+            const int c0 = p.bgrp[2 * g], e0 = p.bgrp[2 * g + 1], c1 = p.bgrp[2 * g + 2], e1 = p.bgrp[2 * g + 3], nc = c1 - c0;
+            int lpc = 1, lsh = 0;
+            while (lpc < 8 && nc * lpc * 2 <= C) { lpc <<= 1; lsh++; }
+            gibbs_team(std::false_type{}, TM, tid, C, c0, e0, c1, e1, lsh);
           }
         }
         __syncthreads();
+        if (WB && tid == 0) *sm.bctr = 0; /* every warp has left the batch loop; the next sweep's loop starts behind several barriers */
         const bool exact = sampling && s == p.sweeps_per_call - 1;
         {
           int t1 = 0, len = 0, T1, LEN, CH;

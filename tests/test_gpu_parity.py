@@ -290,12 +290,35 @@ def test_cli_batch_mode(S, tmp_path):
 # ------------------------------------------------------------------------------------------------
 # large-shape path (ser_sweep_kernel_big): several columns per thread, bit columns / items in
 # L2-resident global scratch.  SER_FORCE_BIG=<threads> routes small shapes through it.
+@pytest.mark.parametrize("warp", ["0", "1"])
 @pytest.mark.parametrize("threads", ["64", "1024"])
 @pytest.mark.parametrize("name,burn,samp", [("g10s10", 8, 8), ("g2s2", 2, 2)])
-def test_big_path_replay_bit_exact(S, oracle_mod, monkeypatch, name, burn, samp, threads):
+def test_big_path_replay_bit_exact(S, oracle_mod, monkeypatch, name, burn, samp, threads, warp):
+    """both forms of the Gibbs phase: CTA-wide column groups (SER_BIG_WARP=0) and warp batches (the default when every
+    column's items fit a warp's slice of the item buffers)"""
     monkeypatch.setenv("SER_FORCE_BIG", threads)
+    monkeypatch.setenv("SER_BIG_WARP", warp)
     X, hard = load_hex_dataset(name)
+    probe = S.Run(S.Dataset.from_bits(X, hard), 1)
+    assert probe.kernel_path() == (2 if warp == "1" else 1)
+    probe.close()
     _replay_case(S, oracle_mod, X, hard, [5, 6, 7], burn, samp)
+
+
+def test_big_path_warp_batches_fall_back_when_a_column_is_too_wide(S, oracle_mod, monkeypatch):
+    """a full column of 700 sites = 701 items does not fit a warp's slice at 1024 threads / 100 KB: the CTA-wide groups serve
+    the shape; with 64 threads the slice is large enough and the warp batches do"""
+    rng = np.random.default_rng(5)
+    X = (rng.random((700, 40)) < 0.2).astype(np.uint8)
+    X[:, 3] = 1
+    hard = np.zeros(700, np.uint8); hard[[10, 300, 650]] = 1
+    monkeypatch.setenv("SER_BIG_SMEM_KB", "100")
+    for threads, path in (("1024", 1), ("64", 2)):
+        monkeypatch.setenv("SER_FORCE_BIG", threads)
+        probe = S.Run(S.Dataset.from_bits(X, hard), 1)
+        assert probe.kernel_path() == path
+        probe.close()
+        _replay_case(S, oracle_mod, X, hard, [1, 2], 3, 3)
 
 
 @pytest.mark.parametrize("threads,kb", [("256", "40"), ("1024", "48"), ("320", "64")])
@@ -346,7 +369,21 @@ def test_synthetic_1024x4096_replay(S, oracle_mod):
     X, hard = S.Dataset.synthetic(1024, 4096, 16).arrays()
     _replay_case(S, oracle_mod, X, hard, [42], 1, 1)
     run = S.Run(S.Dataset.from_bits(X, hard), 300, seed=1).init().advance(1, False).advance(1, True).sync()
-    assert run.check() == 0
+    assert run.check() == 0 and run.kernel_path() == 2
+
+
+def test_synthetic_1024x4096_groups_equal_warp_batches(S, monkeypatch):
+    """the two forms of the large-shape Gibbs phase on the config-5 shape, free-running: identical chains"""
+    ds = S.Dataset.synthetic(1024, 4096, 16)
+    fp = []
+    for warp in ("1", "0"):
+        monkeypatch.setenv("SER_BIG_WARP", warp)
+        run = S.Run(ds, 160, seed=77, store=S.STORE_PI, max_samples=2).init().advance(1, False).advance(2, True).sync()
+        assert run.check() == 0 and run.kernel_path() == (2 if warp == "1" else 1)
+        fp.append([(run.state(i)["a"].tobytes(), run.state(i)["b"].tobytes(), run.state(i)["pi"].tobytes(), run.state(i)["loglik"])
+                   for i in (0, 1, 147, 148, 159)])
+        run.close()
+    assert fp[0] == fp[1]
 
 
 def test_config3_g5s5_4096_chains_selection_and_po(S, oracle_mod):
@@ -871,7 +908,8 @@ def test_determinism_across_runs_and_schedules(S, monkeypatch):
     base = _batch_fingerprint(S, ds, 4096, 99, 3, 3)
     _same_fingerprint(base, _batch_fingerprint(S, ds, 4096, 99, 3, 3))
     for env in ({"SER_SWEEP_GROUPS": "1"}, {"SER_SWEEP_GROUPS": "4"}, {"SER_CHUNK_CALLS": "1"}, {"SER_SWEEP_SLOTS": "37"},
-                {"SER_CHUNK_CALLS": "2", "SER_SWEEP_SLOTS": "1000"}, {"SER_FORCE_BIG": "256"}):
+                {"SER_CHUNK_CALLS": "2", "SER_SWEEP_SLOTS": "1000"}, {"SER_FORCE_BIG": "256"},
+                {"SER_FORCE_BIG": "256", "SER_BIG_WARP": "0"}, {"SER_FORCE_BIG": "96", "SER_BIG_SMEM_KB": "64"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         _same_fingerprint(base, _batch_fingerprint(S, ds, 4096, 99, 3, 3))

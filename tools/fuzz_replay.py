@@ -72,7 +72,8 @@ def run_fuzz(cases=60, seed=1):
         ds = S.Dataset.from_bits(X, hard)
         variants = [("small", {}, False), ("manycd", {}, True),
                     ("big", {"SER_FORCE_BIG": str(int(rng.choice([32, 64, 256, 1024]))),
-                             "SER_BIG_SMEM_KB": str(int(rng.choice([48, 100, 220])))}, False),
+                             "SER_BIG_SMEM_KB": str(int(rng.choice([48, 100, 220]))),
+                             "SER_BIG_WARP": str(int(rng.choice([0, 1])))}, False),
                     ("groups", {"SER_SWEEP_GROUPS": str(int(rng.integers(1, 9)))}, bool(rng.integers(0, 2)))]
         tapes = {m: oracle_chain(X, hard, seed, burn, samp, m) for m in (False, True)}
         for name, env, manycd in variants:
