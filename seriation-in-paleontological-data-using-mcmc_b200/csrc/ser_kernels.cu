@@ -478,7 +478,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     long long icap = 0;
     std::vector<int> bgrp;
     for (int pass = 0; pass < 4; pass++) {
-      const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap, cfg->manycd);
+      const size_t fixed = big_layout(nullptr, nullptr, N, M, 0, gcap, cfg->manycd, gcap);
       icap = ((long long)budget_kb * 1024 - (long long)fixed - 64) / 10 / 32 * 32;
       icap = std::min<long long>(icap, (long long)(kp.I + 31) / 32 * 32);
       if (icap < std::max(N + 1, M)) { /* one whole column, and the M per-taxon terms of the exact sums */
@@ -508,21 +508,22 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     {
       const char *bw = getenv("SER_BIG_WARP");
       const int nwarps = run->big_threads / 32, wgcap = 32 * nwarps;
-      const size_t wfixed = big_layout(nullptr, nullptr, N, M, 0, wgcap, cfg->manycd);
-      int widest_col = 0;
+      const size_t wfixed = big_layout(nullptr, nullptr, N, M, 0, 0, cfg->manycd, wgcap);
+      int widest_col = 0, minlanes = 28;
+      if (const char *v = getenv("SER_BIG_MINLANES")) minlanes = atoi(v);
       for (int c = 0; c < M; c++) widest_col = std::max(widest_col, off[c + 1] - off[c]);
       long long wcap = ((long long)budget_kb * 1024 - (long long)wfixed - 64) / 10 / nwarps / 8 * 8;
       wcap = std::min<long long>(wcap, (long long)(kp.I + 7) / 8 * 8);
       /* val also holds the M per-taxon terms of the exact sums */
       const long long wicap = std::max<long long>(wcap * nwarps, (std::max(N + 1, M) + 31) / 32 * 32);
       if (!(bw && atoi(bw) == 0) && wcap >= widest_col &&
-          big_layout(nullptr, nullptr, N, M, (int)wicap, wgcap, cfg->manycd) <= (size_t)budget_kb * 1024) {
+          big_layout(nullptr, nullptr, N, M, (int)wicap, 0, cfg->manycd, wgcap) <= (size_t)budget_kb * 1024) {
         for (int c0 = 0; c0 < M;) {
           int c1 = c0;
           while (c1 < M && c1 - c0 < 32 && off[c1 + 1] - off[c0] <= wcap) c1++;
           int nc = c1 - c0, lsh = 0;
           while ((nc << (lsh + 1)) <= 32) lsh++;
-          if ((nc << lsh) < 28) { /* a power of two of columns keeps all 32 lanes busy */
+          if ((nc << lsh) < minlanes) { /* a power of two of columns keeps all 32 lanes busy */
             int p2 = 1;
             while (p2 * 2 <= nc) p2 *= 2;
             if (c0 + p2 < M) { nc = p2; lsh = 0; while ((nc << (lsh + 1)) <= 32) lsh++; }
@@ -532,7 +533,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
           c0 = c1;
         }
         run->big_warp = 1;
-        gcap = wgcap;
+        gcap = 0;
         icap = wicap;
         kp.big_wcap = (int)wcap; kp.big_nb = (int)bbat.size();
         CUDA_TRY(POOL_ALLOC(&run->d_bbat, bbat.size() * sizeof(int4)));
@@ -545,7 +546,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     CUDA_TRY(cudaMemcpyAsync(run->d_bgrp, bgrp.data(), bgrp.size() * sizeof(int), cudaMemcpyHostToDevice, run->stream));
     CUDA_TRY(cudaStreamSynchronize(run->stream));
     kp.bgrp = run->d_bgrp;
-    run->smem_big = big_layout(nullptr, nullptr, N, M, (int)icap, gcap, cfg->manycd);
+    run->smem_big = big_layout(nullptr, nullptr, N, M, (int)icap, gcap, cfg->manycd, run->big_warp ? 32 * (run->big_threads / 32) : gcap);
     if (run->smem_big > SER_SMEM_DYN_MAX) { ser_set_error("ser_run_create: shape needs %zu B of shared memory per chain", run->smem_big); return SER_E_ARG; }
     int per_sm = 1, n_sm = 1;
     if (cfg->manycd) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ser_sweep_kernel_big<true, false>, run->big_threads, run->smem_big));

@@ -29,7 +29,9 @@ struct BigTeam {
   uint16_t *pos; double *val; int cap;
   int *goff; uint16_t *gones; double *lmax; uint16_t *st4; double *uab; double *wcol;
 };
-__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap, int manycd = 0)
+/* gcap = columns of the widest CTA-wide group (0 with warp batches, which keep the per-column values in registers);
+ * wcols = columns the per-taxon weights are staged for (manycd: gcap, or 32 per warp with warp batches) */
+__host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, int N, int M, int icap, int gcap, int manycd, int wcols)
 {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
@@ -38,7 +40,7 @@ __host__ __device__ inline size_t big_layout(BigSmem *s, unsigned char *base, in
   size_t o_a = take(2 * (size_t)M), o_b = take(2 * (size_t)M), o_st = take(2 * 4 * (size_t)gcap), o_hp = take(2 * (size_t)(N + 1));
   size_t o_p = take(2 * (size_t)N), o_q = take(2 * (size_t)N), o_m = take(2 * (size_t)N), o_pos = take(2 * (size_t)icap);
   size_t o_hc = take(4 * (size_t)(N / 32 + 1)), o_hq = take(2 * (size_t)(N / 32 + 2)), o_ua = take(16 * (size_t)gcap);
-  size_t o_wc = take(manycd ? 32 * (size_t)gcap : 0), o_rd = take(manycd ? 8 * 2 * SER_MAX_WARPS : 0);
+  size_t o_wc = take(manycd ? 32 * (size_t)wcols : 0), o_rd = take(manycd ? 8 * 2 * SER_MAX_WARPS : 0);
   size_t o_hr = take(2 * (size_t)(N + 2)), o_nh = take(2 * (size_t)(N + 2)), o_bc = take(16);
   if (s) {
     s->bctr = (int *)(base + o_bc);
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BigSmem sm;
-  big_layout(&sm, smem_raw, p.N, p.M, p.big_icap, p.big_gcap, MANY ? 1 : 0);
+  big_layout(&sm, smem_raw, p.N, p.M, p.big_icap, p.big_gcap, MANY ? 1 : 0, WB ? (int)blockDim.x : p.big_gcap);
   const int tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, W = p.W, Cs = p.Cs;
   uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
   uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
@@ -438,13 +440,117 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             PHASE_MARK(4);
           }
         };
+        /* Warp batches: the same step for a few consecutive columns served by ONE warp on its own (no CTA barrier; the warps of
+         * the CTA drift through their batches independently, so one warp's dependent chains are the other warps' issue slots).
+         * A column's lpc lanes each own a contiguous chunk of its items through all passes: log-weights + maximum, then run
+         * weights accumulated straight into the chunk's cumulative sums (no item -> column map, no per-column tables: geometry,
+         * maximum and uniforms stay in the lanes' registers), scan of the chunk totals, search + pick.  Same arithmetic, item
+         * by item and sum by sum, as the group form. */
+        auto gibbs_warp = [&](uint16_t *posw, double *valw, double *wcolw, const int lane, const int c0, const int e0, const int nc,
+                              const int lsh) {
+          constexpr int TAB = MANY ? 0 : 1;
+          const int lpc = 1 << lsh, units = nc << lsh, sub = lane & (lpc - 1);
+          const bool live = lane < units;
+          const int cl = live ? (lane >> lsh) : 0, c = c0 + cl, head = lane & ~(lpc - 1);
+          const int off_c = p.off[c] - e0;
+          __syncwarp(); /* the previous batch is done with the slices */
+          if (live) { /* postings: the lane expands its run of wq words; the prefix table gives its first slot */
+            const int wq = (W + lpc - 1) >> lsh, w0 = sub * wq, w1 = min(W, w0 + wq);
+            uint32_t vv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) vv[k] = w0 + k < w1 ? V[(w0 + k) * Cs + c] : 0u;
+            const int first = w0 < w1 ? (int)PRE[w0 * Cs + c] : 0;
+            uint16_t *out = posw + off_c + first;
+            for (int wb = w0; wb < w1; wb += 8) {
+              if (wb > w0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) vv[k] = wb + k < w1 ? V[(wb + k) * Cs + c] : 0u;
+              }
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                uint32_t v = vv[k];
+                while (v) { *out++ = (uint16_t)(32 * (wb + k) + SER_FFS(v) - 1); v &= v - 1u; }
+              }
+            }
+          }
+          double u_a = 0.0, u_b = 0.0; /* the column's two uniforms (mcmc.c:951, :963 -> :909): drawn by its first lane */
+          SerWeights w = wt;
+          if (live && sub == 0) {
+            const int taxon = p.order[c];
+            if (p.mode == SER_MODE_REPLAY) {
+              const long long u0 = sc.cursor + (MANY ? 6 * (long long)M : 6) + 2 * taxon;
+              u_a = tape[u0]; u_b = tape[u0 + 1];
+            } else {
+              uint32_t o[4];
+              ser_philox4x32_10((uint32_t)taxon, SER_BLK_AB, sc.sweep, 0u, p.seed, gchain, o);
+              u_a = ser_u53(o[0], o[1]); u_b = ser_u53(o[2], o[3]);
+            }
+            if constexpr (MANY) { /* the column's own weights */
+              SerWeights wo;
+              big_col_weights(cd4, p.Mpad, c, &wo);
+              ser_set_weights_own(&wo, wo.c, wo.cc, wo.d, wo.dd, N);
+              wcolw[4 * cl + 0] = wo.A; wcolw[4 * cl + 1] = wo.g; wcolw[4 * cl + 2] = wo.inv_g; wcolw[4 * cl + 3] = wo.hs;
+            }
+          }
+          u_a = __shfl_sync(0xffffffffu, u_a, head); u_b = __shfl_sync(0xffffffffu, u_b, head);
+          __syncwarp(); /* postings (and the columns' weights) are visible to the column's lanes */
+          if constexpr (MANY) { w.A = wcolw[4 * cl + 0]; w.g = wcolw[4 * cl + 1]; w.inv_g = wcolw[4 * cl + 2]; w.hs = wcolw[4 * cl + 3]; }
+          const uint16_t *pos = posw + off_c;
+          double *val = valw + off_c;
+#pragma unroll 1
+          for (int step = 0; step < 2; step++) {
+            const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
+                                         : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
+            const int kb = st.kb, chunk = (kb + lpc) >> lsh;
+            const int k0 = live ? min(kb + 1, sub * chunk) : 0, k1 = live ? min(kb + 1, k0 + chunk) : 0;
+            const int qfirst = (k0 > 0 && k0 < k1) ? ser_item_q(st, pos, k0 - 1) : -1; /* last candidate of the item before the chunk */
+            double lm = -1.0e300;
+            for (int kk = k0; kk < k1; kk++) { /* log-weights of the chunk's items (ser_item_eval), their maximum */
+              const int q = kk < kb ? ser_item_q(st, pos, kk) : st.bound;
+              const double L = ser_fma(ser_i2d(kk - st.ocur), w.A, SER_MUL(ser_i2d(q - st.cur), w.g));
+              val[kk] = L;
+              lm = ser_fmax(lm, L);
+            }
+            for (int o = lpc >> 1; o > 0; o >>= 1) lm = ser_fmax(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+            double tot = 0.0;
+            int qprev = qfirst;
+            for (int kk = k0; kk < k1; kk++) { /* log-weight -> run weight -> cumulative weight inside the chunk */
+              const int q = kk < kb ? ser_item_q(st, pos, kk) : st.bound;
+              tot = SER_ADD(tot, ser_item_weight_cached<TAB>(w, val[kk], q - qprev, lm));
+              val[kk] = tot;
+              qprev = q;
+            }
+            double incl = tot; /* inclusive scan of the chunk totals over the column's lanes */
+            for (int o = 1; o < lpc; o <<= 1) {
+              const double tt = __shfl_up_sync(0xffffffffu, incl, o);
+              if (sub >= o) incl = SER_ADD(incl, tt);
+            }
+            const double total = __shfl_sync(0xffffffffu, incl, lane | (lpc - 1));
+            const double before = __shfl_up_sync(0xffffffffu, incl, 1);
+            const double base = sub ? before : 0.0, target = SER_MUL(step ? u_b : u_a, total);
+            if (k0 < k1 && incl >= target && (sub == 0 || base < target)) { /* the first chunk that reaches the target */
+              int lo = k0, hi = k1 - 1;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (SER_ADD(base, val[mid]) >= target) hi = mid; else lo = mid + 1;
+              }
+              SER_CHECK(lo <= kb && off_c + lo < p.big_wcap);
+              /* ... and the same lane finishes the column: closed-form pick inside the item's run, new a or b */
+              const double rest = SER_SUB(target, lo > k0 ? SER_ADD(base, val[lo - 1]) : base);
+              int q, n;
+              const double le = SER_SUB(ser_item_eval(w, st, pos, lo, &q, &n), lm);
+              const int pick = q - n + 1 + ser_run_pick<TAB>(w, n, le, 0.0, rest);
+              if (step == 0) { changed += pick != sm.a16[c]; sm.a16[c] = (uint16_t)pick; }
+              else { changed += (N - pick) != sm.b16[c]; sm.b16[c] = (uint16_t)(N - pick); }
+            }
+            __syncwarp(); /* the column's lanes see its new boundary; the chunk sums are consumed */
+          }
+        };
         if constexpr (WB) {
-          /* column batches, one warp each, claimed from a shared-memory counter (largest batches first) */
-          const int warp = tid >> 5, lane = tid & 31, wcap = p.big_wcap;
-          BigTeam TM;
-          TM.pos = sm.pos + (size_t)warp * wcap; TM.val = sm.val + (size_t)warp * wcap; TM.cap = wcap;
-          TM.goff = sm.goff + 32 * warp; TM.gones = sm.gones + 32 * warp; TM.lmax = sm.lmax + 32 * warp;
-          TM.st4 = sm.st4 + 128 * warp; TM.uab = sm.uab + 64 * warp; TM.wcol = sm.wcol + (MANY ? 128 * warp : 0);
+          /* column batches, one warp each, claimed from a shared-memory counter (the widest columns first) */
+          const int warp = tid >> 5, lane = tid & 31;
+          uint16_t *posw = sm.pos + (size_t)warp * p.big_wcap;
+          double *valw = sm.val + (size_t)warp * p.big_wcap, *wcolw = sm.wcol + (MANY ? 128 * warp : 0);
           __syncthreads(); /* publishes H and this sweep's weights; the batch counter is zero (reset behind the last barrier) */
           for (;;) {
             int bt = 0;
@@ -452,7 +558,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             bt = __shfl_sync(0xffffffffu, bt, 0);
             if (bt >= p.big_nb) break;
             const int4 bd = __ldg(p.bbat + bt);
-            gibbs_team(std::true_type{}, TM, lane, 32, bd.x, bd.z, bd.x + (bd.y & 0xffff), bd.w, bd.y >> 16);
+            gibbs_warp(posw, valw, wcolw, lane, bd.x, bd.z, bd.y & 0xffff, bd.y >> 16);
           }
         } else {
           BigTeam TM;
