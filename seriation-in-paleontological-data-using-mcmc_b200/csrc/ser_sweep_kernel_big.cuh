@@ -552,6 +552,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           uint16_t *posw = sm.pos + (size_t)warp * p.big_wcap;
           double *valw = sm.val + (size_t)warp * p.big_wcap, *wcolw = sm.wcol + (MANY ? 128 * warp : 0);
           __syncthreads(); /* publishes H and this sweep's weights; the batch counter is zero (reset behind the last barrier) */
+          PHASE_MARK(0);
           for (;;) {
             int bt = 0;
             if (lane == 0) bt = atomicAdd(sm.bctr, 1);
@@ -560,6 +561,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             const int4 bd = __ldg(p.bbat + bt);
             gibbs_warp(posw, valw, wcolw, lane, bd.x, bd.z, bd.y & 0xffff, bd.y >> 16);
           }
+          PHASE_MARK(3); /* warp 0's batches; what follows up to the barrier is its wait for the last batch of the CTA */
         } else {
           BigTeam TM;
           TM.pos = sm.pos; TM.val = sm.val; TM.cap = p.big_icap; TM.goff = sm.goff; TM.gones = sm.gones; TM.lmax = sm.lmax;
@@ -573,6 +575,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           }
         }
         __syncthreads();
+        PHASE_MARK(4);
         if (WB && tid == 0) *sm.bctr = 0; /* every warp has left the batch loop; the next sweep's loop starts behind several barriers */
         const bool exact = sampling && s == p.sweeps_per_call - 1;
         {
@@ -612,11 +615,11 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           }
         }
 
-        PHASE_MARK(5);
         /* ================= 16 proposals for pi ================= */
         ps.k = 0;
         for (int prop = 0; prop < 16; prop++) {
           const int kind = prop == 0 ? 3 : ((prop - 1) % 3);
+          PHASE_MARK(prop == 0 ? 5 : prop == 1 ? 11 : 8 + (prop - 2) % 3); /* the time since the last mark was the previous proposal's */
           int dt0 = 0, dt1 = 0, nz = 0, D0, D1;
           double delta, tsum = 0.0;
           auto add = [&](int c, int x0, int x1) { /* a column's deltas into the thread's partial sums */
@@ -633,6 +636,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             auto redo = [&](int c, int *x0, int *x1) { ser_pi1_delta(V + c, Cs, sm.a16[c], sm.b16[c], i, j, x0, x1); };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); add(c, x0, x1); }
             if (!mh_decide_big<MANY>(p, sm, wt, cd4, ps, TERMS, dt0, dt1, nz, tsum, exact, &D0, &D1, &delta, redo)) continue;
+            PHASE_MARK(8);
             for (int c = tid; c <= M; c += C) {
               if (c < M) {
                 int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
@@ -643,6 +647,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             __syncthreads();
             for (int n = lo + tid; n <= hi; n += C) sm.rpi[n] = sm.tmp16[n];
             big_rebuild_hard(sm, N);
+            PHASE_MARK(12);
             sc.counters[3]++;
           } else if (kind == 1 || kind == 3) { /* pi2 */
             int i, j;
@@ -695,6 +700,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); add(c, x0, x1); }
             if (!mh_decide_big<MANY>(p, sm, wt, cd4, ps, TERMS, dt0, dt1, nz, tsum, exact, &D0, &D1, &delta, redo)) continue;
+            PHASE_MARK(10);
             for (int n = g.i + tid; n <= g.j; n += C) sm.perm16[n] = (uint16_t)ser_pi3_perm(hd, g, n);
             __syncthreads();
             for (int c = tid; c < M; c += C) {
@@ -707,6 +713,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
             __syncthreads();
             for (int n = g.i + tid; n <= g.j; n += C) sm.rpi[n] = sm.tmp16[n];
+            PHASE_MARK(13);
             sc.counters[6]++;
           }
           sc.t0a += D0; sc.f0a -= D0; sc.t1a += D1; sc.f1a -= D1;
@@ -717,7 +724,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         if (p.mode == SER_MODE_REPLAY) sc.cursor += (MANY ? 8 * (long long)M : 6 + 2 * (long long)M) + ps.k;
         else sc.sweep++;
         sc.counters[7]++;
-        PHASE_MARK(6);
+        PHASE_MARK(10); /* the 16th proposal is a pi3 */
       }
       if (sc.flags & 1) break;
 
