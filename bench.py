@@ -47,9 +47,9 @@ UNIT = "sweeps/s"
 # DRAM traffic of the sweep kernels from the committed `ncu --set full` captures (profiles/r02/README.md).
 # ser_sweep_kernel: dram__bytes_read.sum + dram__bytes_write.sum = 103.29 MB + 167.47 MB over the 8 192 work items of the profiled
 # launch (4 096 chains x 2 one-call items) = 33.05 KB per work item -- the chain state incl. its bit columns going through HBM at an
-# item boundary; the thinned samples add 2 N bytes each.  ser_sweep_kernel_big: 1.310 GB + 1.220 GB over 2 960 chain-sweeps.
+# item boundary; the thinned samples add 2 N bytes each.  ser_sweep_kernel_big (warp batches): 1.263 GB + 1.210 GB over 2 960 chain-sweeps.
 NCU_DRAM = {"g2s2": dict(per_item=(102.342656e6 + 163.281920e6) / 8192, src="profiles/r02/sweep_r02_v3_ncu_raw_selected.txt"),
-            "synthetic": dict(per_sweep=(1.310332e9 + 1.220131e9) / 2960, src="profiles/r02/sweep_big_r02_ncu_raw_selected.txt")}
+            "synthetic": dict(per_sweep=(1.263233e9 + 1.209718e9) / 2960, src="profiles/r02/sweep_big_r02_warpbatch_ncu_raw_selected.txt")}
 
 
 def workload_name(dataset):
