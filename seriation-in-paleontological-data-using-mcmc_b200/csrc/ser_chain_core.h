@@ -94,40 +94,61 @@ SER_HD uint32_t ser_range_mask(int w, int lo, int hi)
 /* A column is addressed as col[w * C] (word w of the column, stride C words). */
 SER_HD int ser_col_bit(const uint32_t *col, int C, int p) { return (col[(p >> 5) * C] >> (p & 31)) & 1u; }
 
+/* The prefix table of a column: G = 0 (columns in shared memory) one entry per word, pre[w * C] = ones in words < w, w = 0..W.
+ * G > 0 (the large-shape kernel's columns in global memory, where the table's bytes compete with the columns for the L2): one
+ * entry per 2^G words, pre[k * C] = ones in words < k 2^G, k = 0..W >> G; the words between an entry and w are counted on the fly. */
+template <int G = 0>
+SER_HD int ser_pre_at(const uint32_t *col, const uint16_t *pre, int C, int w)
+{
+  int r = (int)pre[(w >> G) * C];
+  if (G > 0) for (int x = (w >> G) << G; x < w; x++) r += SER_POPC(col[x * C]);
+  return r;
+}
+template <int G = 0>
+SER_HD void ser_pre_put(uint16_t *pre, int C, int w, int ones_below)
+{
+  if (G == 0 || (w & ((1 << G) - 1)) == 0) pre[(w >> G) * C] = (uint16_t)ones_below;
+}
+
 /* ones in bits [0, p), p in [0, N]: prefix table + one POPC */
+template <int G = 0>
 SER_HD int ser_rank1(const uint32_t *col, const uint16_t *pre, int C, int p)
 {
   SER_CHECK(p >= 0 && p <= 32 * SER_MAXW);
   const int w = p >> 5;
-  return (int)pre[w * C] + SER_POPC(col[w * C] & ser_mask_lo(p & 31));
+  return ser_pre_at<G>(col, pre, C, w) + SER_POPC(col[w * C] & ser_mask_lo(p & 31));
 }
 
 /* popcount of bits [lo, hi) */
+template <int G = 0>
 SER_HD int ser_col_popc(const uint32_t *col, const uint16_t *pre, int C, int lo, int hi)
 {
-  return hi <= lo ? 0 : ser_rank1(col, pre, C, hi) - ser_rank1(col, pre, C, lo);
+  return hi <= lo ? 0 : ser_rank1<G>(col, pre, C, hi) - ser_rank1<G>(col, pre, C, lo);
 }
 
-/* (re)build pre[0..W] from the words */
+/* (re)build the table from the words */
+template <int G = 0>
 SER_HD void ser_col_build_pre(const uint32_t *col, uint16_t *pre, int C, int W)
 {
   int acc = 0;
   pre[0] = 0;
-  for (int w = 0; w < W; w++) { acc += SER_POPC(col[w * C]); pre[(w + 1) * C] = (uint16_t)acc; }
+  for (int w = 0; w < W; w++) { acc += SER_POPC(col[w * C]); ser_pre_put<G>(pre, C, w + 1, acc); }
 }
 
 /* after a permutation of bits inside words w0..w1 (the multiset of bits there is unchanged)
- * only pre[w0+1..w1] can differ */
+ * only the counts of the boundaries w0+1..w1 can differ */
+template <int G = 0>
 SER_HD void ser_col_fix_pre(const uint32_t *col, uint16_t *pre, int C, int w0, int w1)
 {
-  int acc = pre[w0 * C];
-  for (int w = w0; w < w1; w++) { acc += SER_POPC(col[w * C]); pre[(w + 1) * C] = (uint16_t)acc; }
+  int acc = ser_pre_at<G>(col, pre, C, w0);
+  for (int w = w0; w < w1; w++) { acc += SER_POPC(col[w * C]); ser_pre_put<G>(pre, C, w + 1, acc); }
 }
 
 /* The three column moves below take an optional prefix table: with `pre` the counts pre[w0+1..w1] are
  * rewritten from the new words as they are produced (what ser_col_fix_pre would do in a second pass
  * that re-reads the column). */
 /* in-place: reverse bits [i, j] (new[p] = old[i+j-p]) */
+template <int G = 0>
 SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j, uint16_t *pre = 0)
 {
   uint32_t old[SER_MAXW];
@@ -141,7 +162,7 @@ SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j, uint16_t 
   }
   for (int w = w0; w <= w1; w++) old[w] = col[w * C];
   const int s = i + j;
-  int acc = pre ? (int)pre[w0 * C] : 0;
+  int acc = pre ? ser_pre_at<G>(col, pre, C, w0) : 0;
   for (int wn = w0; wn <= w1; wn++) {
     /* new bit p = old[s - p]: 32 old bits ending at s - 32wn, reversed */
     const int q = s - 32 * wn - 31;
@@ -152,13 +173,14 @@ SER_HD void ser_col_reverse(uint32_t *col, int C, int W, int i, int j, uint16_t 
     const uint32_t m = ser_range_mask(wn, i, j + 1);
     const uint32_t nw = (old[wn] & ~m) | (bits & m);
     col[wn * C] = nw;
-    if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
+    if (pre && wn < w1) { acc += SER_POPC(nw); ser_pre_put<G>(pre, C, wn + 1, acc); }
   }
 }
 
 /* in-place: move bit i to position j, shifting the bits in between by one (pi1).  No copy of the column: a word
  * only needs its old neighbour on the side the bits come from, and the words are rewritten in the order that
  * leaves that neighbour untouched (upwards for i < j, downwards for i > j). */
+template <int G = 0>
 SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j, uint16_t *pre = 0)
 {
   const int lo = i < j ? i : j, hi = i < j ? j : i;
@@ -166,7 +188,7 @@ SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j, uint16_t *
   SER_CHECK(lo >= 0 && w1 < W);
   const uint32_t moved = (col[(i >> 5) * C] >> (i & 31)) & 1u;
   if (i < j) { /* new[p] = old[p+1] for p in [i, j-1] */
-    int acc = pre ? (int)pre[w0 * C] : 0;
+    int acc = pre ? ser_pre_at<G>(col, pre, C, w0) : 0;
     uint32_t cur = col[w0 * C];
     for (int wn = w0; wn <= w1; wn++) {
       const uint32_t up = (wn + 1 <= w1) ? col[(wn + 1) * C] : 0u;
@@ -174,7 +196,7 @@ SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j, uint16_t *
       uint32_t nw = (cur & ~m) | (((cur >> 1) | (up << 31)) & m);
       if (wn == w1) nw = (nw & ~(1u << (j & 31))) | (moved << (j & 31));
       col[wn * C] = nw;
-      if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
+      if (pre && wn < w1) { acc += SER_POPC(nw); ser_pre_put<G>(pre, C, wn + 1, acc); }
       cur = up;
     }
   } else { /* new[p] = old[p-1] for p in [j+1, i] */
@@ -187,18 +209,19 @@ SER_HD void ser_col_rotate(uint32_t *col, int C, int W, int i, int j, uint16_t *
       col[wn * C] = nw;
       cur = dn;
     }
-    if (pre) ser_col_fix_pre(col, pre, C, w0, w1);
+    if (pre) ser_col_fix_pre<G>(col, pre, C, w0, w1);
   }
 }
 
 /* in-place: new[p] = old[perm[p]] for p in [i, j] (pi3; perm is an involution on the window) */
+template <int G = 0>
 SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uint16_t *perm, uint16_t *pre = 0)
 {
   uint32_t old[SER_MAXW];
   const int w0 = i >> 5, w1 = j >> 5;
   SER_CHECK(0 <= i && i <= j && w1 < W);
   for (int w = w0; w <= w1; w++) old[w] = col[w * C];
-  int acc = pre ? (int)pre[w0 * C] : 0;
+  int acc = pre ? ser_pre_at<G>(col, pre, C, w0) : 0;
   for (int wn = w0; wn <= w1; wn++) {
     uint32_t nw = old[wn];
     const int p0 = (32 * wn > i) ? 32 * wn : i, p1 = (32 * wn + 31 < j) ? 32 * wn + 31 : j;
@@ -209,7 +232,7 @@ SER_HD void ser_col_permute(uint32_t *col, int C, int W, int i, int j, const uin
       nw = (nw & ~(1u << (p & 31))) | (bit << (p & 31));
     }
     col[wn * C] = nw;
-    if (pre && wn < w1) { acc += SER_POPC(nw); pre[(wn + 1) * C] = (uint16_t)acc; }
+    if (pre && wn < w1) { acc += SER_POPC(nw); ser_pre_put<G>(pre, C, wn + 1, acc); }
   }
 }
 
@@ -417,20 +440,22 @@ SER_HD int ser_expand_ones(const uint32_t *col, int C, int W, uint16_t *out)
   return k;
 }
 
+template <int G = 0>
 SER_HD SerStep ser_step_a(const uint32_t *col, const uint16_t *pre, int C, int W, int N, int a, int b)
 {
   SerStep st;
-  st.cur = a; st.bound = b; st.ocur = ser_rank1(col, pre, C, a); st.kb = ser_rank1(col, pre, C, b);
-  st.nones = pre[W * C]; st.N = N; st.rev = 0;
+  st.cur = a; st.bound = b; st.ocur = ser_rank1<G>(col, pre, C, a); st.kb = ser_rank1<G>(col, pre, C, b);
+  st.nones = ser_pre_at<G>(col, pre, C, W); st.N = N; st.rev = 0;
   return st;
 }
 /* b-step on the reversed column: boundary t = N - b, candidates 0..N-a */
+template <int G = 0>
 SER_HD SerStep ser_step_b(const uint32_t *col, const uint16_t *pre, int C, int W, int N, int a, int b)
 {
   SerStep st;
-  st.nones = pre[W * C]; st.N = N; st.rev = 1;
+  st.nones = ser_pre_at<G>(col, pre, C, W); st.N = N; st.rev = 1;
   st.cur = N - b; st.bound = N - a;
-  st.ocur = st.nones - ser_rank1(col, pre, C, b); st.kb = st.nones - ser_rank1(col, pre, C, a);
+  st.ocur = st.nones - ser_rank1<G>(col, pre, C, b); st.kb = st.nones - ser_rank1<G>(col, pre, C, a);
   return st;
 }
 
@@ -592,6 +617,7 @@ SER_HD void ser_pi1_apply_ab(int *a, int *b, int i, int j)
 }
 
 /* pi2: positions [i, j] reversed */
+template <int G = 0>
 SER_HD void ser_pi2_delta(const uint32_t *col, const uint16_t *pre, int C, int a, int b, int i, int j, int inc1,
                           int inc2, int *dt0, int *dt1)
 {
@@ -599,8 +625,8 @@ SER_HD void ser_pi2_delta(const uint32_t *col, const uint16_t *pre, int C, int a
   *dt0 = 0; *dt1 = 0;
   if (ain == bin) return;
   const int split = ain ? a : b;
-  const int r = ser_rank1(col, pre, C, split);
-  const int oL = r - ser_rank1(col, pre, C, i), oR = ser_rank1(col, pre, C, j + 1) - r;
+  const int r = ser_rank1<G>(col, pre, C, split);
+  const int oL = r - ser_rank1<G>(col, pre, C, i), oR = ser_rank1<G>(col, pre, C, j + 1) - r;
   const int zL = (split - i) - oL, zR = (j + 1 - split) - oR;
   if (ain) { *dt1 = oL - oR; *dt0 = zR - zL; }  /* left part becomes alive, right part dies */
   else { *dt1 = oR - oL; *dt0 = zL - zR; }      /* left part dies, right part becomes alive */
@@ -638,7 +664,7 @@ SER_HD int ser_pi3_perm(const SerHard &h, const SerPi3 &g, int n)
 /* HB: the column's ones at the hard sites come from `hbits` (bit k = the column has a one at the k-th hard site;
  * hard sites keep their relative order, mcmc.c:1049-1072, so this is a constant of the column; needs nh <= 32)
  * instead of a walk over the hard positions inside the two ranges */
-template <bool HB = false>
+template <bool HB = false, int G = 0>
 SER_HD void ser_pi3_delta(const uint32_t *col, const uint16_t *pre, int C, const SerHard &h, const SerPi3 &g, int a,
                           int b, int inc1, int inc2, int *dt0, int *dt1, uint32_t hbits = 0u)
 {
@@ -660,10 +686,10 @@ SER_HD void ser_pi3_delta(const uint32_t *col, const uint16_t *pre, int C, const
   const int lo2 = ser_pi3_wpos(h, g, g.K - ((nbc - i) - (hr_nb - g.hr_i)));
   const int hi2 = ser_pi3_wpos(h, g, g.K - ((nac - i) - (hr_na - g.hr_i)));
   const int hr_lo2 = ser_hard_rank(h, lo2), hr_hi2 = ser_hard_rank(h, hi2);
-  const int nA = ahi > alo ? ahi - alo : 0, oA = ser_col_popc(col, pre, C, alo, ahi);
+  const int nA = ahi > alo ? ahi - alo : 0, oA = ser_col_popc<G>(col, pre, C, alo, ahi);
   /* B = (hard in [nac,nbc)) + (non-hard in [lo2,hi2)) */
   const int nB = (hr_nb - hr_na) + ((hi2 > lo2 ? hi2 - lo2 : 0) - (hr_hi2 - hr_lo2));
-  int oB = ser_col_popc(col, pre, C, lo2, hi2);
+  int oB = ser_col_popc<G>(col, pre, C, lo2, hi2);
   if (HB) { /* hard ranks in [x, y) -> bits x..y-1 of hbits */
     oB -= SER_POPC(hbits & ser_mask_lt(hr_hi2) & ~ser_mask_lt(hr_lo2));
     oB += SER_POPC(hbits & ser_mask_lt(hr_nb) & ~ser_mask_lt(hr_na));

@@ -18,6 +18,15 @@ extern "C" int ser_debug_phase_cycles(unsigned long long out[24])
 #define PHASE_MARK(i) do { } while (0)
 #endif
 
+/* The large-shape kernel's columns live in a global scratch slot per CTA; 148 slots of bit columns + per-word prefix counts are
+ * the size of the L2 (1024 x 4096: 0.54 + 0.28 MB each).  One prefix count per 2^SER_BIG_G words (ser_pre_at, ser_chain_core.h)
+ * shrinks the table by that factor; the words between an entry and the word asked for are counted on the fly.  Measured with
+ * -DSER_BIG_G=2 (parity green): DRAM traffic 2.47 -> 1.18 GB per 2 960 chain-sweeps, but 13 % more instructions and
+ * instruction-cache misses: 242 -> 197 k sweeps/s.  The default stays one count per word. */
+#ifndef SER_BIG_G
+#define SER_BIG_G 0
+#endif
+
 /* ------------------------------------------------------------------ per-chain global state */
 struct __align__(16) ChainScalars { /* a multiple of 16 bytes: loaded / stored as int4 words */
   double c, cc, d, dd; /* log P(false 1), log(1-e^c), log P(false 0), log(1-e^d) */
@@ -49,7 +58,7 @@ struct KParams {
   /* large-shape path (ser_sweep_kernel_big): per-CTA-slot scratch in global memory */
   int Cs;                   /* column stride of the scratch bit matrix (>= M+1) */
   uint32_t *gV;             /* [slot][W][Cs] */
-  uint16_t *gpre;           /* [slot][W+1][Cs] */
+  uint16_t *gpre;           /* [slot][(W >> SER_BIG_G) + 1][Cs]: one prefix count per 2^SER_BIG_G words */
   const int *bgrp;          /* large-shape column groups: [g] = {first column, first item}, big_ng + 1 entries */
   int big_ng, big_icap, big_gcap;
   /* warp-batch Gibbs phase (ser_sweep_kernel_big<.., WB = true>): a batch = consecutive columns one warp serves on its own */

@@ -556,7 +556,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
     kp.Cs = ((M + 1) + 31) / 32 * 32;
     const size_t sl = (size_t)run->big_slots;
     CUDA_TRY(POOL_ALLOC(&run->d_gV, sl * run->W * kp.Cs * sizeof(uint32_t)));
-    CUDA_TRY(POOL_ALLOC(&run->d_gpre, sl * (run->W + 1) * kp.Cs * sizeof(uint16_t)));
+    CUDA_TRY(POOL_ALLOC(&run->d_gpre, sl * ((run->W >> SER_BIG_G) + 1) * kp.Cs * sizeof(uint16_t)));
     kp.gV = run->d_gV; kp.gpre = run->d_gpre;
   }
   kp.n_chains = cfg->n_chains;

@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
   BigSmem sm;
   big_layout(&sm, smem_raw, p.N, p.M, p.big_icap, p.big_gcap, MANY ? 1 : 0, WB ? (int)blockDim.x : p.big_gcap);
   const int tid = threadIdx.x, N = p.N, M = p.M, C = blockDim.x, W = p.W, Cs = p.Cs;
+  constexpr int BG = SER_BIG_G;
   uint32_t *V = p.gV + (size_t)blockIdx.x * W * Cs;
-  uint16_t *PRE = p.gpre + (size_t)blockIdx.x * (W + 1) * Cs;
+  uint16_t *PRE = p.gpre + (size_t)blockIdx.x * ((W >> BG) + 1) * Cs; /* one prefix count per 2^BG words (ser_pre_at) */
   double *TERMS = sm.val; /* per-taxon terms of the exact sums: the item-weight buffer is idle outside the Gibbs phase (icap >= M) */
   if (WB && tid == 0) *sm.bctr = 0;
 
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
         if (c < M) { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)cell(p, sm.rpi, pos, c) << (pos & 31); V[w * Cs + c] = word; }
         else { for (int pos = 32 * w; pos < pend; pos++) word |= (uint32_t)(p.hard[sm.rpi[pos]] != 0) << (pos & 31); sm.hcol[w] = word; }
       }
-      if (c < M) ser_col_build_pre(V + c, PRE + c, Cs, W);
+      if (c < M) ser_col_build_pre<BG>(V + c, PRE + c, Cs, W);
       else ser_col_build_pre(sm.hcol, sm.hpre, 1, W);
     }
     __syncthreads();
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               yc = tc[0]; lyc = tc[1]; l1c = tc[2];
               yd = td[0]; lyd = td[1]; l1d = td[2];
             } else {
-              const int t1 = ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), len = sm.b16[c] - sm.a16[c];
+              const int t1 = ser_col_popc<BG>(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), len = sm.b16[c] - sm.a16[c];
               const int f1 = p.ones[c] - t1, f0 = len - t1, t0 = N - len - f1;
               const uint32_t blk = SER_BLK_MANYCD + 4u * (uint32_t)taxon;
               yc = ser_beta_from_gammas(ser_gamma_ge1(1.0 + (double)f1, p.seed, gchain, sc.sweep, blk),
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               uint32_t vv[8];
 #pragma unroll
               for (int k = 0; k < 8; k++) vv[k] = w0 + k < w1 ? V[(w0 + k) * Cs + c] : 0u;
-              const int first = w0 < w1 ? (int)PRE[w0 * Cs + c] : 0, off_c = p.off[c] - e0;
+              const int first = w0 < w1 ? ser_pre_at<BG>(V + c, PRE + c, Cs, w0) : 0, off_c = p.off[c] - e0;
               if (qq == 0) { TM.goff[cl] = off_c; TM.gones[cl] = (uint16_t)p.ones[c]; } /* the team's column table */
               uint16_t *out = TM.pos + off_c + first;
               for (int wb = w0; wb < w1; wb += 8) {
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               const int u = ub + t;
               const bool live = u < units;
               const int cl = live ? (u >> lsh) : 0, c = c0 + cl;
-              const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
-                                           : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
+              const SerStep st = step == 0 ? ser_step_a<BG>(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
+                                           : ser_step_b<BG>(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
               const uint16_t *pos = TM.pos + TM.goff[cl];
               double lm = -1.0e300;
               if (live) { /* every item's log-weight stays in val for the dense pass */
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             uint32_t vv[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) vv[k] = w0 + k < w1 ? V[(w0 + k) * Cs + c] : 0u;
-            const int first = w0 < w1 ? (int)PRE[w0 * Cs + c] : 0;
+            const int first = w0 < w1 ? ser_pre_at<BG>(V + c, PRE + c, Cs, w0) : 0;
             uint16_t *out = posw + off_c + first;
             for (int wb = w0; wb < w1; wb += 8) {
               if (wb > w0) {
@@ -499,8 +500,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           double *val = valw + off_c;
 #pragma unroll 1
           for (int step = 0; step < 2; step++) {
-            const SerStep st = step == 0 ? ser_step_a(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
-                                         : ser_step_b(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
+            const SerStep st = step == 0 ? ser_step_a<BG>(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c])
+                                         : ser_step_b<BG>(V + c, PRE + c, Cs, W, N, sm.a16[c], sm.b16[c]);
             const int kb = st.kb, chunk = (kb + lpc) >> lsh;
             const int k0 = live ? min(kb + 1, sub * chunk) : 0, k1 = live ? min(kb + 1, k0 + chunk) : 0;
             const int qfirst = (k0 > 0 && k0 < k1) ? ser_item_q(st, pos, k0 - 1) : -1; /* last candidate of the item before the chunk */
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
           int t1 = 0, len = 0, T1, LEN, CH;
           double tsum = 0.0;
           for (int c = tid; c < M; c += C) {
-            const int t1c = ser_col_popc(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), lenc = sm.b16[c] - sm.a16[c];
+            const int t1c = ser_col_popc<BG>(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c]), lenc = sm.b16[c] - sm.a16[c];
             t1 += t1c; len += lenc;
             if (MANY || exact) { /* mcmc_logl's per-taxon term, mcmc.c:643-644 */
               const int f1 = p.ones[c] - t1c, f0 = lenc - t1c, t0 = N - lenc - f1;
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             for (int c = tid; c <= M; c += C) {
               if (c < M) {
                 int a = sm.a16[c], b = sm.b16[c]; ser_pi1_apply_ab(&a, &b, i, j); sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
-                ser_col_rotate(V + c, Cs, W, i, j, PRE + c);
+                ser_col_rotate<BG>(V + c, Cs, W, i, j, PRE + c);
               } else ser_col_rotate(sm.hcol, 1, W, i, j, sm.hpre);
             }
             for (int n = lo + tid; n <= hi; n += C) sm.tmp16[n] = sm.rpi[i < j ? (n < j ? n + 1 : i) : (n > j ? n - 1 : i)];
@@ -665,7 +666,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             if (ser_hard_count(hd, i, j) > 1) continue;
             const int inc1 = ser_draw_int(sm.draws_pi[ps.k], 2), inc2 = ser_draw_int(sm.draws_pi[ps.k + 1], 2);
             ps.k += 2;
-            auto redo = [&](int c, int *x0, int *x1) { ser_pi2_delta(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c], i, j, inc1, inc2, x0, x1); };
+            auto redo = [&](int c, int *x0, int *x1) { ser_pi2_delta<BG>(V + c, PRE + c, Cs, sm.a16[c], sm.b16[c], i, j, inc1, inc2, x0, x1); };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); add(c, x0, x1); }
             if (!mh_decide_big<MANY>(p, sm, wt, cd4, ps, TERMS, dt0, dt1, nz, tsum, exact, &D0, &D1, &delta, redo)) continue;
             for (int c = tid; c <= M; c += C) {
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
                 ser_mirror_ab(a, b, ain, bin, i + j + 1, &a, &b);
                 sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
               }
-              if (c < M) ser_col_reverse(V + c, Cs, W, i, j, PRE + c);
+              if (c < M) ser_col_reverse<BG>(V + c, Cs, W, i, j, PRE + c);
               else ser_col_reverse(sm.hcol, 1, W, i, j, sm.hpre);
             }
             for (int n = i + tid; n <= j; n += C) sm.tmp16[n] = sm.rpi[i + j - n];
@@ -695,8 +696,8 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             ps.k += 2;
             const bool hb = p.nh <= 32;
             auto redo = [&](int c, int *x0, int *x1) {
-              if (hb) ser_pi3_delta<true>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1, __ldg(p.hbits + c));
-              else ser_pi3_delta<false>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1);
+              if (hb) ser_pi3_delta<true, BG>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1, __ldg(p.hbits + c));
+              else ser_pi3_delta<false, BG>(V + c, PRE + c, Cs, hd, g, sm.a16[c], sm.b16[c], inc1, inc2, x0, x1);
             };
             for (int c = tid; c < M; c += C) { int x0, x1; redo(c, &x0, &x1); add(c, x0, x1); }
             if (!mh_decide_big<MANY>(p, sm, wt, cd4, ps, TERMS, dt0, dt1, nz, tsum, exact, &D0, &D1, &delta, redo)) continue;
@@ -708,7 +709,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
               const int ain = ser_in_window(a, g.i, g.j + 1, inc1, inc2), bin = ser_in_window(b, g.i, g.j + 1, inc1, inc2);
               ser_mirror_ab(a, b, ain, bin, g.i + g.j + 1, &a, &b);
               sm.a16[c] = (uint16_t)a; sm.b16[c] = (uint16_t)b;
-              ser_col_permute(V + c, Cs, W, g.i, g.j, sm.perm16, PRE + c);
+              ser_col_permute<BG>(V + c, Cs, W, g.i, g.j, sm.perm16, PRE + c);
             }
             for (int n = g.i + tid; n <= g.j; n += C) sm.tmp16[n] = sm.rpi[sm.perm16[n]];
             __syncthreads();

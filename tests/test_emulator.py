@@ -104,3 +104,12 @@ def test_emulator_random_shapes_and_densities(oracle_mod, emul):
         hard = np.zeros(N, np.uint8)
         hard[rng.choice(N, size=min(nh, N), replace=False)] = 1
         _run_case(oracle_mod, emul, X, hard, int(rng.integers(0, 1 << 30)), 12)
+
+
+def test_coarse_prefix_tables_equal_per_word_tables(emul):
+    """the large-shape kernel keeps one prefix count per 2^G words of a column (ser_pre_at<G>, G = 2 in the product): random moves
+    (site move, reversal, adjacent swap, window permutation) and range queries on a coarse and a per-word table must agree"""
+    emul.emul_coarse_pre_selftest.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    emul.emul_coarse_pre_selftest.restype = C.c_int
+    for seed, N in enumerate((2, 5, 31, 32, 33, 64, 95, 127, 128, 129, 200, 526, 1000, 1024, 2047, 2048)):
+        assert emul.emul_coarse_pre_selftest(seed + 1, N, 300) == 0, N
