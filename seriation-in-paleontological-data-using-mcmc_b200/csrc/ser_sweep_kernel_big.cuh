@@ -1,4 +1,5 @@
-/* ser_sweep_kernel_big.cuh -- the large-shape sweep kernel: persistent CTAs, columns in a global scratch slot, Gibbs phase staged through shared memory.
+/* ser_sweep_kernel_big.cuh -- the large-shape sweep kernel: persistent CTAs, columns in a global scratch slot, Gibbs phase staged through shared memory
+ * (warp batches: one warp serves a few columns on its own; or CTA-wide column groups).
  * Part of the single translation unit ser_kernels.cu (included there, in this order). */
 
 /* ------------------------------------------------------------------ the sweep kernel, large shapes
@@ -273,21 +274,20 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
 
         }
 
-        /* ================= a/b Gibbs, item formulation, one column group at a time =================
-         * The group's postings and item weights live in shared memory (icap items), so the per-column
-         * loops run at shared-memory latency.  A column is served by `lpc` adjacent lanes (1..8, as many as
-         * the block can spare for the group), which split its loops: the maximum is a lane-strided partial
-         * maximum + shuffle, the cumulative weights are a per-lane serial sum over a contiguous chunk + a
-         * shuffle scan of the lane totals.  Per group: postings; then for the a-step and the b-step:
-         * geometry + maximum, run weights (dense over the group's items), scan + inverse CDF. */
+        /* ================= a/b Gibbs, item formulation =================
+         * Two forms: warp batches (WB, gibbs_warp below) and CTA-wide column groups (gibbs_team).
+         *
+         * CTA-wide groups, one column group at a time: the group's postings and item weights live in shared memory (icap
+         * items), so the per-column loops run at shared-memory latency.  A column is served by `lpc` adjacent lanes (1..8, as
+         * many as the block can spare for the group), which split its loops: the maximum is a lane-strided partial maximum +
+         * shuffle, the cumulative weights are a per-lane serial sum over a contiguous chunk + a shuffle scan of the lane
+         * totals.  Per group: postings; then for the a-step and the b-step: geometry + maximum, run weights (dense over the
+         * group's items), scan + inverse CDF.  The body is written for a team of T threads with index t (T = the CTA here;
+         * WARP = true, a team of one warp behind __syncwarp, was the first form of the warp batches). */
         int changed = 0;
-        /* One team = the threads that share a set of columns: the whole CTA (a column group, CTA barriers between the
-         * passes) or ONE WARP (a column batch, __syncwarp only: the warps of the CTA drift through their batches
-         * independently, so one warp's dependent chains and pass boundaries are the other warps' issue slots).
-         * t / T = thread index / size of the team; TM = the team's slices of the group-local arrays. */
-        auto gibbs_team = [&](auto warp_tag, const BigTeam &TM, const int t, const int T, const int c0, const int e0, const int c1,
+        auto gibbs_team = [&](const BigTeam &TM, const int t, const int T, const int c0, const int e0, const int c1,
                               const int e1, const int lsh) {
-          constexpr bool WARP = decltype(warp_tag)::value;
+          constexpr bool WARP = false;
           auto team_sync = [&]() { if constexpr (WARP) __syncwarp(); else __syncthreads(); };
           const int nc = c1 - c0, lpc = 1 << lsh;
           const int units = nc << lsh, sub = t & (lpc - 1);
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(1024, 1) ser_sweep_kernel_big(KParams p)
             const int c0 = p.bgrp[2 * g], e0 = p.bgrp[2 * g + 1], c1 = p.bgrp[2 * g + 2], e1 = p.bgrp[2 * g + 3], nc = c1 - c0;
             int lpc = 1, lsh = 0;
             while (lpc < 8 && nc * lpc * 2 <= C) { lpc <<= 1; lsh++; }
-            gibbs_team(std::false_type{}, TM, tid, C, c0, e0, c1, e1, lsh);
+            gibbs_team(TM, tid, C, c0, e0, c1, e1, lsh);
           }
         }
         __syncthreads();
