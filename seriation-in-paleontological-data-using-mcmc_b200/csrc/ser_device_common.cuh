@@ -22,7 +22,7 @@ extern "C" int ser_debug_phase_cycles(unsigned long long out[24])
  * the size of the L2 (1024 x 4096: 0.54 + 0.28 MB each).  One prefix count per 2^SER_BIG_G words (ser_pre_at, ser_chain_core.h)
  * shrinks the table by that factor; the words between an entry and the word asked for are counted on the fly.  Measured with
  * -DSER_BIG_G=2 (parity green): DRAM traffic 2.47 -> 1.18 GB per 2 960 chain-sweeps, but 13 % more instructions and
- * instruction-cache misses: 242 -> 197 k sweeps/s.  The default stays one count per word. */
+ * instruction-cache misses: 242 -> 197 k sweeps/s (-DSER_BIG_G=1: 201 k).  The default stays one count per word. */
 #ifndef SER_BIG_G
 #define SER_BIG_G 0
 #endif
