@@ -118,6 +118,10 @@ int ser_run_kernel_launches(const ser_run *run, int64_t *n);
 /* which sweep kernel serves this run's shape: 0 = one thread per taxon (ser_sweep_kernel), 1 = large-shape kernel with
  * CTA-wide column groups, 2 = large-shape kernel with warp batches, 3 = cluster kernel */
 int ser_run_kernel_path(const ser_run *run, int32_t *path);
+/* The warp batches the large-shape kernel's Gibbs phase would use for a matrix whose sorted columns hold ones_sorted[c] ones, with
+ * slices of `wcap` items per warp (host only; no device needed): batches[4 b ..] = {first column, columns | lane shift << 16,
+ * first item, last item + 1}; batches may be NULL to only count them. */
+int ser_plan_warp_batches(const int32_t *ones_sorted, int32_t M, int32_t wcap, int32_t *batches, int32_t max_batches, int32_t *n_batches);
 /* CUDA-event time of the SWEEP launches alone since the last reset, and how many there were.  The events are
  * recorded around every launch and only read here, so measuring the dominant kernel puts no host
  * synchronisation between the launches of a timed region. */

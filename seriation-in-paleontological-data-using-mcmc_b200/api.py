@@ -59,6 +59,7 @@ SYMBOLS = [
     ("ser_run_elapsed_ms", C.c_int, [_vp, _dp, C.c_int32]),
     ("ser_run_kernel_launches", C.c_int, [_vp, _i64p]),
     ("ser_run_kernel_path", C.c_int, [_vp, _i32p]),
+    ("ser_plan_warp_batches", C.c_int, [_i32p, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p]),
     ("ser_run_get_state", C.c_int, [_vp, C.c_int32] + [_i32p] * 9 + [_dp, _i64p]),
     ("ser_run_get_counters", C.c_int, [_vp, C.c_int32, _i64p]),
     ("ser_run_check", C.c_int, [_vp, _i32p]),
@@ -132,6 +133,17 @@ def _check(rc: int):
 
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def plan_warp_batches(ones_sorted, wcap: int) -> np.ndarray:
+    """the warp batches of the large-shape kernel's Gibbs phase for sorted columns with these occurrence counts and slices of
+    ``wcap`` items per warp (host only): rows of (first column, columns, lane shift, first item, last item + 1)"""
+    ones = np.ascontiguousarray(ones_sorted, np.int32)
+    n = C.c_int32()
+    _check(lib().ser_plan_warp_batches(_p(ones, C.c_int32), ones.size, int(wcap), None, 0, C.byref(n)))
+    raw = np.empty((n.value, 4), np.int32)
+    _check(lib().ser_plan_warp_batches(_p(ones, C.c_int32), ones.size, int(wcap), _p(raw, C.c_int32), n.value, C.byref(n)))
+    return np.stack([raw[:, 0], raw[:, 1] & 0xffff, raw[:, 1] >> 16, raw[:, 2], raw[:, 3]], axis=1)
 
 
 class Dataset:

@@ -193,6 +193,49 @@ static cudaError_t allow_max_dynamic_smem(void)
   return e;
 }
 
+/* Warp batches of the large-shape kernel's Gibbs phase (ser_sweep_kernel_big<.., WB = true>): off[c] = first item of sorted column c
+ * (a column has ones + 1 items), wcap = items a warp's slice of the item buffers holds (>= the widest column).  A batch = consecutive
+ * columns whose items fit the slice, at most 32; a column gets 32 / columns lanes, rounded down to a power of two.  When the columns
+ * that fit would leave more than 32 - minlanes lanes idle, the batch shrinks to a power of two of columns (all 32 lanes busy).
+ * Entry = {first column, columns | lane shift << 16, first item, last item + 1}. */
+static void plan_warp_batches(const int *off, int M, long long wcap, int minlanes, std::vector<int4> &out)
+{
+  out.clear();
+  for (int c0 = 0; c0 < M;) {
+    int c1 = c0;
+    while (c1 < M && c1 - c0 < 32 && off[c1 + 1] - off[c0] <= wcap) c1++;
+    int nc = c1 - c0, lsh = 0;
+    while ((nc << (lsh + 1)) <= 32) lsh++;
+    if ((nc << lsh) < minlanes) {
+      int p2 = 1;
+      while (p2 * 2 <= nc) p2 *= 2;
+      if (c0 + p2 < M) { nc = p2; lsh = 0; while ((nc << (lsh + 1)) <= 32) lsh++; }
+    }
+    c1 = c0 + nc;
+    out.push_back(make_int4(c0, nc | (lsh << 16), off[c0], off[c1]));
+    c0 = c1;
+  }
+}
+
+/* the same plan from the columns' occurrence counts (host only, no device needed): what a run of such a matrix would use */
+extern "C" int ser_plan_warp_batches(const int32_t *ones_sorted, int32_t M, int32_t wcap, int32_t *batches, int32_t max_batches, int32_t *n_batches)
+{
+  if (!ones_sorted || M < 1 || wcap < 1 || !n_batches) { ser_set_error("ser_plan_warp_batches: bad argument"); return SER_E_ARG; }
+  std::vector<int> off((size_t)M + 1, 0);
+  for (int c = 0; c < M; c++) {
+    if (ones_sorted[c] < 0 || ones_sorted[c] + 1 > wcap) { ser_set_error("ser_plan_warp_batches: column %d has %d items, a slice holds %d", c, ones_sorted[c] + 1, wcap); return SER_E_ARG; }
+    off[c + 1] = off[c] + ones_sorted[c] + 1;
+  }
+  std::vector<int4> plan;
+  plan_warp_batches(off.data(), M, wcap, 28, plan);
+  *n_batches = (int32_t)plan.size();
+  if (batches) {
+    if ((int)plan.size() > max_batches) { ser_set_error("ser_plan_warp_batches: %zu batches, room for %d", plan.size(), max_batches); return SER_E_ARG; }
+    for (size_t b = 0; b < plan.size(); b++) { batches[4 * b] = plan[b].x; batches[4 * b + 1] = plan[b].y; batches[4 * b + 2] = plan[b].z; batches[4 * b + 3] = plan[b].w; }
+  }
+  return SER_OK;
+}
+
 /* Column groups of the Gibbs step: the item weights of a step go through a buffer of Ival doubles,
  * one group of columns at a time.  Fewer, larger groups = fewer barriers; a smaller buffer = more
  * resident chains per SM (measured on B200: +15-20 % per extra resident CTA, -4 % per extra group).
@@ -500,9 +543,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
       gcap = tight;
     }
     /* Warp batches (default whenever every column's items fit a warp's slice of the item buffers; SER_BIG_WARP=0 keeps the
-     * CTA-wide groups): the per-column tables hold 32 columns per warp, the item buffers are cut into one slice per warp.
-     * A batch = consecutive columns whose items fit the slice, at most 32; a column gets 32 / columns lanes (a power of two).
-     * When the columns that fit would leave more than 4 lanes idle, the batch shrinks to a power of two of columns. */
+     * CTA-wide groups): the item buffers are cut into one slice per warp, the batches come from plan_warp_batches. */
     run->big_warp = 0;
     std::vector<int4> bbat;
     {
@@ -518,20 +559,7 @@ static int run_create_impl(const ser_dataset *ds, const ser_run_config *cfg, ser
       const long long wicap = std::max<long long>(wcap * nwarps, (std::max(N + 1, M) + 31) / 32 * 32);
       if (!(bw && atoi(bw) == 0) && wcap >= widest_col &&
           big_layout(nullptr, nullptr, N, M, (int)wicap, 0, cfg->manycd, wgcap) <= (size_t)budget_kb * 1024) {
-        for (int c0 = 0; c0 < M;) {
-          int c1 = c0;
-          while (c1 < M && c1 - c0 < 32 && off[c1 + 1] - off[c0] <= wcap) c1++;
-          int nc = c1 - c0, lsh = 0;
-          while ((nc << (lsh + 1)) <= 32) lsh++;
-          if ((nc << lsh) < minlanes) { /* a power of two of columns keeps all 32 lanes busy */
-            int p2 = 1;
-            while (p2 * 2 <= nc) p2 *= 2;
-            if (c0 + p2 < M) { nc = p2; lsh = 0; while ((nc << (lsh + 1)) <= 32) lsh++; }
-          }
-          c1 = c0 + nc;
-          bbat.push_back(make_int4(c0, nc | (lsh << 16), off[c0], off[c1]));
-          c0 = c1;
-        }
+        plan_warp_batches(off.data(), M, wcap, minlanes, bbat);
         run->big_warp = 1;
         gcap = 0;
         icap = wicap;

@@ -232,3 +232,31 @@ def test_compute_entry_points_fail_loudly_without_a_device(S):
     with pytest.raises(S.SeriationError) as e:
         S.Multi(ds, 4, 2)
     assert "no CUDA device" in str(e.value)
+
+
+def test_warp_batch_plan_of_the_large_shape_kernel(S):
+    """ser_plan_warp_batches (host only): the batches cover every sorted column exactly once and in order, a batch's items fit a
+    warp's slice, it has at most 32 columns, every column gets a power of two of lanes, the lanes of a batch fit one warp, and a
+    batch that would leave more than 4 lanes idle holds a power of two of columns (all 32 lanes busy) unless it is the matrix's tail"""
+    rng = np.random.default_rng(3)
+    cases = [(np.sort(rng.integers(18, 166, 4096))[::-1], 600),      # the 1024 x 4096 synthetic shape: 19 .. 166 items per column
+             (np.sort(rng.integers(0, 40, 1500))[::-1], 200), (np.full(77, 1023), 1024), (np.zeros(500, np.int64), 8),
+             (np.sort(rng.integers(0, 2049, 300))[::-1], 4096), (np.array([5]), 16)]
+    for ones, wcap in cases:
+        plan = S.plan_warp_batches(ones, wcap)
+        off = np.concatenate([[0], np.cumsum(ones + 1)])
+        nxt = 0
+        for c0, nc, lsh, e0, e1 in plan.tolist():
+            assert c0 == nxt and 1 <= nc <= 32 and (nc << lsh) <= 32 and (nc << (lsh + 1)) > 32
+            assert e0 == off[c0] and e1 == off[c0 + nc] and e1 - e0 <= wcap
+            fits = nc                                                 # how many columns would have fitted
+            while c0 + fits < ones.size and fits < 32 and off[c0 + fits + 1] - e0 <= wcap:
+                fits += 1
+            if fits != nc:                                            # shrunk: to the largest power of two, all lanes busy
+                assert nc & (nc - 1) == 0 and 2 * nc > fits and (nc << lsh) == 32
+            elif (nc << lsh) < 28:                                    # idle lanes are only left at the matrix's tail
+                assert c0 + (1 << (nc.bit_length() - 1)) >= ones.size
+            nxt = c0 + nc
+        assert nxt == ones.size
+    with pytest.raises(S.SeriationError):
+        S.plan_warp_batches(np.array([100, 3]), 50)                  # a column wider than a slice: the CTA-wide groups serve such shapes
