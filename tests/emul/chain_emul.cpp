@@ -9,6 +9,7 @@
 // nothing in the package loads it.
 //
 // Replay mode only (tape grammar of oracle/draw_source.h).
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -39,6 +40,7 @@ struct Chain {
   const double *tape;
   size_t tape_len, cur;
   long long n_degenerate;
+  long long chunk_picks = 0, chunk_mismatch = 0, chunk_finder_bad = 0; // the warp batches' chunked passes beside the sequential ones
 
   uint32_t *col(int m) { return V.data() + m; }
   uint16_t *pcol(int m) { return pre.data() + m; }
@@ -233,6 +235,60 @@ void sample_cd(Chain &ch) {
   ch.set_cd(c, cc, d, dd);
 }
 
+// The large-shape kernel's warp batches (ser_sweep_kernel_big.cuh, gibbs_warp): a column's 2^lsh lanes own contiguous chunks of
+// its items through all passes.  Emulated lane by lane: the chunk-fused log-weights / run weights must equal the dense ones bit
+// for bit (same formula, same operands); the chunk-relative cumulative sums, the scan of the chunk totals (the shuffle steps in
+// their order), the first chunk that reaches U x total, the search inside it and the closed-form pick give the column's new
+// boundary, which is compared with the sequential inverse CDF (ser_step_pick).
+int chunked_pick(Chain &ch, const SerWeights &w, const SerStep &st, const uint16_t *pos, const double *dense_w, double lmax, double U, int lsh) {
+  const int lpc = 1 << lsh, kb = st.kb, chunk = (kb + lpc) >> lsh;
+  std::vector<double> cum(kb + 1), incl(lpc), tot(lpc);
+  std::vector<int> k0(lpc), k1(lpc);
+  double lm_all = -1.0e300;
+  std::vector<double> L(kb + 1);
+  for (int sub = 0; sub < lpc; sub++) { // pass 1: log-weights of the chunk, partial maximum
+    k0[sub] = std::min(kb + 1, sub * chunk); k1[sub] = std::min(kb + 1, k0[sub] + chunk);
+    for (int kk = k0[sub]; kk < k1[sub]; kk++) {
+      const int q = kk < kb ? ser_item_q(st, pos, kk) : st.bound;
+      L[kk] = ser_fma(ser_i2d(kk - st.ocur), w.A, SER_MUL(ser_i2d(q - st.cur), w.g));
+      lm_all = ser_fmax(lm_all, L[kk]);
+    }
+  }
+  if (lm_all != lmax) { fprintf(stderr, "emulator: chunked maximum differs\n"); abort(); }
+  for (int sub = 0; sub < lpc; sub++) { // pass 2: run weights into the chunk's cumulative sums
+    int qprev = (k0[sub] > 0 && k0[sub] < k1[sub]) ? ser_item_q(st, pos, k0[sub] - 1) : -1;
+    double t = 0.0;
+    for (int kk = k0[sub]; kk < k1[sub]; kk++) {
+      const int q = kk < kb ? ser_item_q(st, pos, kk) : st.bound;
+      const double wk = ser_item_weight_cached(w, L[kk], q - qprev, lm_all);
+      if (wk != dense_w[kk]) { fprintf(stderr, "emulator: chunk-fused item weight differs\n"); abort(); }
+      t = SER_ADD(t, wk); cum[kk] = t; qprev = q;
+    }
+    tot[sub] = t; incl[sub] = t;
+  }
+  for (int o = 1; o < lpc; o <<= 1) { // the shuffle scan: every lane adds the value of the lane o below, all lanes at once
+    const std::vector<double> old(incl);
+    for (int sub = o; sub < lpc; sub++) incl[sub] = SER_ADD(old[sub], old[sub - o]);
+  }
+  const double total = incl[lpc - 1], target = SER_MUL(U, total);
+  int finder = -1, finders = 0;
+  for (int sub = 0; sub < lpc; sub++) {
+    const double base = sub ? incl[sub - 1] : 0.0;
+    if (k0[sub] < k1[sub] && incl[sub] >= target && (sub == 0 || base < target)) { finders++; if (finder < 0) finder = sub; }
+  }
+  if (finders != 1) { ch.chunk_finder_bad++; if (finder < 0) return -1; }
+  const double base = finder ? incl[finder - 1] : 0.0;
+  int lo = k0[finder], hi = k1[finder] - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (SER_ADD(base, cum[mid]) >= target) hi = mid; else lo = mid + 1;
+  }
+  const double rest = SER_SUB(target, lo > k0[finder] ? SER_ADD(base, cum[lo - 1]) : base);
+  int q, n;
+  const double le = SER_SUB(ser_item_eval(w, st, pos, lo, &q, &n), lm_all);
+  return q - n + 1 + ser_run_pick(w, n, le, 0.0, rest);
+}
+
 int sample_ab(Chain &ch) {
   // item formulation: (1) postings of every column, (2) per step: per-taxon maximum, dense item
   // weights, per-taxon scan + pick -- the loops below are the kernel's phases run sequentially
@@ -260,7 +316,10 @@ int sample_ab(Chain &ch) {
         val[off[m] + kk] = w;
       }
     for (int m = 0; m < M; m++) {
+      const int lsh = (m + step + (int)(ch.cur & 7)) % 6; // 1 .. 32 lanes per column, varied over columns, steps and sweeps
+      const int cpick = chunked_pick(ch, ch.WT(m), st[m], pos.data() + off[m], val.data() + off[m], lmax[m], step == 0 ? ua[m] : ub[m], lsh);
       const int pick = ser_step_pick(ch.WT(m), st[m], pos.data() + off[m], val.data() + off[m], lmax[m], step == 0 ? ua[m] : ub[m]);
+      ch.chunk_picks++; ch.chunk_mismatch += cpick != pick;
       if (step == 0) { changed += pick != ch.a[m]; ch.a[m] = pick; }
       else { changed += (N - pick) != ch.b[m]; ch.b[m] = N - pick; }
     }
@@ -368,6 +427,7 @@ void emul_get_state(void *p, int32_t *a, int32_t *b, int32_t *pi, int32_t *rpi, 
   *slots = (long long)ch.cur;
 }
 long long emul_degenerate(void *p) { return ((Chain *)p)->n_degenerate; }
+void emul_chunk_stats(void *p, long long out[3]) { Chain *ch = (Chain *)p; out[0] = ch->chunk_picks; out[1] = ch->chunk_mismatch; out[2] = ch->chunk_finder_bad; }
 void emul_get_cd(void *p, double *c, double *d) {
   Chain &ch = *(Chain *)p;
   for (int m = 0; m < ch.M; m++) { c[m] = ch.WT(m).c; d[m] = ch.WT(m).d; }

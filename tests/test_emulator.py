@@ -3,7 +3,10 @@
 The emulator compiles the very building blocks the CUDA kernel uses (csrc/ser_chain_core.h) for
 the host, so the bit-level logic -- range popcounts, rank/select over the hard mask, the pi3 mask
 construction, the Gibbs walk, the degenerate-delta rule -- is verified without a GPU.  Replay
-mode: integers bit-exact, c/d bit-exact, loglik within 1e-9 relative."""
+mode: integers bit-exact, c/d bit-exact, loglik within 1e-9 relative.  Every Gibbs step is also run the way the large-shape
+kernel's warp batches run it (a column's 1 .. 32 lanes own contiguous item chunks: chunk-fused weights, chunk-relative sums,
+scan of the chunk totals, search + pick in the first chunk that reaches the target): the fused weights equal the dense ones bit
+for bit and the picked boundary equals the sequential inverse CDF's."""
 import ctypes as C
 import math
 import os
@@ -30,6 +33,7 @@ def emul():
     L.emul_set_tape.argtypes = [C.c_void_p, dp, C.c_size_t]
     L.emul_randomize.argtypes = [C.c_void_p]
     L.emul_sweeps.argtypes = [C.c_void_p, C.c_int]
+    L.emul_chunk_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
     L.emul_get_state.argtypes = [C.c_void_p] + [i32p] * 9 + [dp, C.POINTER(C.c_longlong)]
     return L
 
@@ -69,6 +73,10 @@ def _run_case(O, L, X, hard, seed, sweeps):
                                         if not np.array_equal(getattr(s, f), getattr(r, f))])
             assert s.slots == r.slots and s.c == r.c and s.d == r.d, k
             assert abs(s.loglik - r.loglik) <= 1e-9 * abs(r.loglik), k
+        st3 = (C.c_longlong * 3)()
+        L.emul_chunk_stats(e, st3)
+        # the warp batches' chunked passes (1 .. 32 lanes per column) beside the sequential inverse CDF: same boundary, one finder lane
+        assert st3[0] > 0 and st3[1] == 0 and st3[2] == 0, list(st3)
     finally:
         L.emul_free(e)
     assert o.consistent() == 0
